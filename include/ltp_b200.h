@@ -1,0 +1,160 @@
+/* ltp_b200.h -- C ABI of the B200-native batched planning hot path.
+ *
+ * This is the drop-in boundary. The reference (yannickBurkhardt/LongTermPlanner) has no
+ * FFI layer of its own: its boundary is the C++ class LongTermPlanner
+ * (include/long_term_planner/long_term_planner.h:61-308). Each entry point below names
+ * the reference interface it replaces; include/long_term_planner/long_term_planner.h in
+ * THIS repository re-creates that class on top of these calls.
+ *
+ * Conventions
+ *  - plain C types only; every pointer is either a HOST pointer ("_host" entry points and
+ *    the limit vectors) or a DEVICE pointer on the planner's device (everything else).
+ *  - batched device buffers are structure-of-arrays, JOINT-MAJOR:  x[joint * n + problem];
+ *    switching times are t[(k * dof + joint) * n + problem], k = 0..6.
+ *  - trajectories are written sample-contiguous, one row per (problem, joint):
+ *    q[(problem * dof + joint) * stride + sample], mirroring Trajectory::q[joint][sample]
+ *    (reference long_term_planner.h:41-44).
+ *  - all device work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = the
+ *    legacy default stream); no entry point synchronises unless it says so.
+ *  - return value: LTP_OK or a negative ltp_status. Nothing is printed, nothing throws.
+ *  - there is no CPU fallback: without a CUDA device ltp_create fails with LTP_ERR_CUDA.
+ */
+#ifndef LTP_B200_H
+#define LTP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTP_MAX_DOF 32
+
+typedef enum {
+  LTP_OK = 0,
+  LTP_ERR_ARG = -1,      /* null pointer, dof out of range, n < 0, bad stride ... */
+  LTP_ERR_CUDA = -2,     /* a CUDA runtime call failed; see ltp_last_cuda_error() */
+  LTP_ERR_CAPACITY = -3  /* caller-provided row capacity too small; see ltp_plan_host */
+} ltp_status;
+
+/* case byte (the reference emits no case id; encoding documented in DESIGN.md):
+ *  low nibble 0 brake-only | 1..4 cruise phase exists (1: P2,P6; 2: no P2; 3: no P6; 4: none)
+ *  | 5 no cruise phase (closed form) | 6 quartic #1 | 7 quartic #1 + P2 | 8 quartic #2
+ *  | 14 degenerate zero return | 15 failure;  0x10 modified jerk profile; 0x20 both
+ *  re-insertions fired; 0x40 / 0x80 no-P2 / no-P6 branch taken.
+ * ts_case: 0 slowest joint, 1..8 accepted attempt, 9 search failed (optimal times kept),
+ *  255 plan aborted before time scaling. */
+
+typedef struct ltp_planner ltp_planner;
+
+/* replaces LongTermPlanner::LongTermPlanner(dof, t_sample, q_min, q_max, v_max, a_max,
+ * j_max) (reference long_term_planner.h:118-131). Limit vectors: host, dof doubles. */
+int ltp_create(ltp_planner** out, int device, int dof, double t_sample, const double* q_min,
+               const double* q_max, const double* v_max, const double* a_max,
+               const double* j_max);
+/* replaces setLimits / setSampleTime / setDoF (reference long_term_planner.h:176-205) */
+int ltp_set_limits(ltp_planner* p, const double* q_min, const double* q_max, const double* v_max,
+                   const double* a_max, const double* j_max);
+int ltp_set_sample_time(ltp_planner* p, double t_sample);
+int ltp_set_dof(ltp_planner* p, int dof);
+int ltp_get_dof(const ltp_planner* p);
+int ltp_get_device(const ltp_planner* p);
+void ltp_destroy(ltp_planner* p);
+const char* ltp_status_string(int status);
+const char* ltp_last_cuda_error(void);
+/* number of kernel launches issued through this planner since creation */
+int64_t ltp_launch_count(const ltp_planner* p);
+
+/* ---- per-joint primitives, batched (device pointers, joint-major [dof][n]) ----------- */
+
+/* replaces LongTermPlanner::optBraking (reference long_term_planner.cc:650-701).
+ * t_rel: [3][dof][n]. */
+int ltp_opt_braking_batch(ltp_planner* p, int64_t n, const double* v_0, const double* a_0,
+                          double* q_stop, double* t_rel, double* dir, void* stream);
+
+/* replaces LongTermPlanner::optSwitchTimes (reference long_term_planner.cc:82-353).
+ * t: [7][dof][n] (left at 0 where the reference leaves it unwritten); kase may be NULL. */
+int ltp_opt_switch_times_batch(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
+                               const double* v_0, const double* a_0, const double* v_drive,
+                               double* t, double* dir, uint8_t* mod, uint8_t* kase, uint8_t* ok,
+                               void* stream);
+
+/* replaces LongTermPlanner::timeScaling (reference long_term_planner.cc:358-645).
+ * dir, t_required: [dof][n] inputs. ts_case / final_case may be NULL. */
+int ltp_time_scaling_batch(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
+                           const double* v_0, const double* a_0, const double* dir,
+                           const double* t_required, double* t, double* v_drive, uint8_t* mod,
+                           uint8_t* ts_case, uint8_t* final_case, uint8_t* ok, void* stream);
+
+/* ---- the batched planner: planTrajectories ------------------------------------------ */
+
+/* Result of stages 1-3 (phase times, synchronisation, time scaling). Device pointers.
+ * Pointers marked optional may be NULL. */
+typedef struct {
+  double* t_scaled;    /* [7][dof][n]  final switching times (reference t_scaled, cc:50-55) */
+  double* dir;         /* [dof][n] */
+  double* v_drive;     /* [dof][n] */
+  uint8_t* mod;        /* [dof][n]  modified jerk profile flag */
+  int32_t* slowest;    /* [n]  index of the slowest joint, -1 if none */
+  int32_t* traj_len;   /* [n]  samples of the trajectory (cc:716-719); 0 if not reached */
+  uint8_t* reached;    /* [n]  1 if the reference would go on to getTrajectory (cc:58) */
+  double* t_opt;       /* optional [7][dof][n]  time-optimal switching times (cc:27-30) */
+  uint8_t* opt_case;   /* optional [dof][n] */
+  uint8_t* ts_case;    /* optional [dof][n] */
+  uint8_t* final_case; /* optional [dof][n] */
+} ltp_solution;
+
+/* replaces the solve part of LongTermPlanner::planTrajectory
+ * (reference long_term_planner.cc:14-55) for n independent problems. */
+int ltp_solve_batch(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
+                    const double* v_0, const double* a_0, const ltp_solution* sol, void* stream);
+
+/* replaces LongTermPlanner::getTrajectory + the final joint-limit check
+ * (reference long_term_planner.cc:58-61, 706-841) for n problems.
+ *   horizon == 0: every problem writes exactly traj_len[p] samples per row;
+ *   horizon  > 0: every row holds exactly `horizon` samples (clipped, or continued with
+ *                 the recurrence's own steady state q_last, 0, 0, 0).
+ * stride (doubles per row) must be >= the samples written; rows are written with 32-byte
+ * vector stores when stride % 4 == 0 and the four base pointers are 32-byte aligned.
+ * success: [n], 1 iff reached and every joint ends inside [q_min, q_max]. */
+int ltp_sample_batch(ltp_planner* p, int64_t n, const double* q_0, const double* v_0,
+                     const double* a_0, const ltp_solution* sol, int32_t horizon, int64_t stride,
+                     double* q, double* v, double* a, double* j, uint8_t* success, void* stream);
+
+/* ---- host-buffer entry points (what a caller without device buffers uses) ------------ */
+
+/* Stages 1-3 with HOST buffers: copies the four inputs in, solves, copies the requested
+ * outputs back, and synchronises. Same layouts as ltp_solve_batch; the ltp_solution
+ * holds HOST pointers here (optional ones may be NULL). Pinned host memory makes the
+ * copies asynchronous and lets chunks overlap. */
+int ltp_solve_host(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
+                   const double* v_0, const double* a_0, const ltp_solution* host_sol);
+
+/* Full planTrajectory for n problems with HOST buffers (reference long_term_planner.cc:7-63).
+ * Rows are [n][dof][capacity]. If a trajectory needs more than `capacity` samples nothing is
+ * written for any problem, *needed receives the required capacity and LTP_ERR_CAPACITY is
+ * returned. traj_len / success: [n] host. horizon as in ltp_sample_batch. */
+int ltp_plan_host(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
+                  const double* v_0, const double* a_0, int32_t horizon, int64_t capacity,
+                  double* q, double* v, double* a, double* j, int32_t* traj_len,
+                  uint8_t* success, int64_t* needed);
+
+/* single-item host forms of the protected per-joint methods (used by the C++ drop-in) */
+int ltp_opt_braking_host(ltp_planner* p, int joint, double v_0, double a_0, double* q_stop,
+                         double* t_rel3, double* dir);
+int ltp_opt_switch_times_host(ltp_planner* p, int joint, double q_goal, double q_0, double v_0,
+                              double a_0, double v_drive, double* t7, double* dir, uint8_t* mod,
+                              uint8_t* kase, uint8_t* ok);
+int ltp_time_scaling_host(ltp_planner* p, int joint, double q_goal, double q_0, double v_0,
+                          double a_0, double dir, double t_required, double* t7, double* v_drive,
+                          uint8_t* mod, uint8_t* ts_case, uint8_t* ok);
+/* getTrajectory on given switching times; t7 [dof][7] host, rows [dof][capacity] host */
+int ltp_get_trajectory_host(ltp_planner* p, const double* t7, const double* dir,
+                            const uint8_t* mod, const double* q_0, const double* v_0,
+                            const double* a_0, const double* v_drive, int64_t capacity, double* q,
+                            double* v, double* a, double* j, int32_t* length, int64_t* needed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTP_B200_H */

@@ -1,0 +1,844 @@
+// B200 (sm_100a) kernels and C ABI of the batched planning hot path. See include/ltp_b200.h
+// for the boundary and DESIGN.md for the data layout and the per-kernel rooflines.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false ...
+// (-fmad=false is part of the numerical contract, see ltp_math.cuh).
+//
+// Thread mapping of the solve / sample kernels: a CTA is (32 problems) x (dof joints);
+// warp w works on joint w of 32 consecutive problems. All lanes of a warp therefore share
+// one limit set, every lane is busy for any dof (no padding to a power of two), and the
+// joint-major buffers x[joint * n + problem] are read and written fully coalesced. The
+// per-problem reductions (slowest joint, trajectory length, final limit check) go through
+// a few bytes of shared memory per problem.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/ltp_b200.h"
+#include "ltp_math.cuh"
+
+namespace {
+
+using namespace ltp;
+
+struct PlannerParams {
+  int dof;
+  double ts;
+  JointLimits lim[LTP_MAX_DOF];
+};
+
+struct DeviceSolution {  // ltp_solution, by value
+  double* t_scaled;
+  double* dir;
+  double* v_drive;
+  uint8_t* mod;
+  int32_t* slowest;
+  int32_t* traj_len;
+  uint8_t* reached;
+  double* t_opt;
+  uint8_t* opt_case;
+  uint8_t* ts_case;
+  uint8_t* final_case;
+};
+
+constexpr int kTile = 32;  // problems per CTA
+
+// ------------------------------------------------------------------------------------
+// stages 1-3, generic form: every branch evaluated in-thread (reference cc:14-55)
+// ------------------------------------------------------------------------------------
+template <int MAXW>
+__global__ void __launch_bounds__(kTile * MAXW)
+ltp_solve_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_goal,
+                 const double* __restrict__ q_0, const double* __restrict__ v_0,
+                 const double* __restrict__ a_0, DeviceSolution S) {
+  extern __shared__ unsigned char smem_raw[];
+  const int dof = P.dof;
+  double* s_t6 = reinterpret_cast<double*>(smem_raw);                  // [dof][32]
+  int* s_len = reinterpret_cast<int*>(s_t6 + dof * kTile);             // [dof][32]
+  unsigned char* s_fail = reinterpret_cast<unsigned char*>(s_len + dof * kTile);  // [dof][32]
+
+  const int lane = threadIdx.x, jt = threadIdx.y;
+  const int64_t p = (int64_t)blockIdx.x * kTile + lane;
+  const bool valid = p < n;
+  const JointLimits L = P.lim[jt];
+  const double Ts = P.ts;
+  const int64_t at = (int64_t)jt * n + p;
+
+  double qg = 0, q0 = 0, v0 = 0, a0 = 0;
+  if (valid) {
+    qg = q_goal[at]; q0 = q_0[at]; v0 = v_0[at]; a0 = a_0[at];
+  }
+  // stage 1 (cc:14-30)
+  const bool in_ok = check_joint_input(L, q0, v0, a0);
+  const Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0);
+  double t_opt[7];
+  zero7(t_opt);
+  unsigned char mod = 0, opt_case = 255;
+  const bool ost_ok = ost_body(L, Ts, pro, qg, q0, L.v_max, t_opt, mod, opt_case);
+  s_t6[jt * kTile + lane] = t_opt[6];
+  s_fail[jt * kTile + lane] = (unsigned char)(!(in_ok && ost_ok));
+  __syncthreads();
+  // stage 2 (cc:31-39): strict '>' so the lowest joint index wins ties, NaN never wins
+  double t_req = -1;
+  int slowest = -1;
+  bool any_fail = false;
+  for (int i = 0; i < dof; ++i) {
+    any_fail |= (s_fail[i * kTile + lane] != 0);
+    const double ti = s_t6[i * kTile + lane];
+    if (ti > t_req) {
+      t_req = ti;
+      slowest = i;
+    }
+  }
+  const bool reached = !any_fail && slowest != -1;
+  // stage 3 (cc:42-55)
+  double t_sc[7];
+  zero7(t_sc);
+  double v_drive = L.v_max;
+  unsigned char ts_case = 255, final_case = 255;
+  if (reached) {
+    if (jt == slowest) {
+      ts_case = 0;
+      final_case = opt_case;
+    } else {
+      const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
+      ts_case = (unsigned char)time_scaling_from(1, L, Ts, pro, I, t_sc, v_drive, mod, final_case);
+      if (ts_case == 9) final_case = opt_case;
+    }
+    double m = t_sc[0];
+#pragma unroll
+    for (int k = 1; k < 7; ++k)
+      if (m < t_sc[k]) m = t_sc[k];
+    if (m <= 0.0) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) t_sc[k] = t_opt[k];
+    }
+  }
+  // trajectory length (cc:716-719)
+  int my_len = 0;
+  if (reached) {
+    bool fin = true;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) fin &= (bool)isfinite(t_sc[k]);
+    my_len = (fin && t_sc[6] / Ts <= 2.0e9) ? samples_for(t_sc[6], Ts) : -1;
+  }
+  s_len[jt * kTile + lane] = my_len;
+  __syncthreads();
+  if (!valid) return;
+  if (jt == 0) {
+    int len = 0;
+    bool bad = false;
+    for (int i = 0; i < dof; ++i) {
+      const int li = s_len[i * kTile + lane];
+      bad |= li < 0;
+      len = li > len ? li : len;
+    }
+    S.slowest[p] = slowest;
+    S.traj_len[p] = (reached && !bad) ? len : 0;
+    S.reached[p] = (uint8_t)reached;
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) S.t_scaled[((int64_t)k * dof + jt) * n + p] = t_sc[k];
+  S.dir[at] = pro.dir;
+  S.v_drive[at] = v_drive;
+  S.mod[at] = mod;
+  if (S.t_opt) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) S.t_opt[((int64_t)k * dof + jt) * n + p] = t_opt[k];
+  }
+  if (S.opt_case) S.opt_case[at] = opt_case;
+  if (S.ts_case) S.ts_case[at] = ts_case;
+  if (S.final_case) S.final_case[at] = final_case;
+}
+
+// ------------------------------------------------------------------------------------
+// per-joint primitives. grid.y = joint (or 1 with joint_fixed >= 0), 1 thread per item
+// ------------------------------------------------------------------------------------
+__global__ void ltp_opt_braking_kernel(const __grid_constant__ PlannerParams P, int joint_fixed,
+                                       int64_t n, const double* __restrict__ v_0,
+                                       const double* __restrict__ a_0, double* q_stop, double* t_rel,
+                                       double* dir) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int jt = joint_fixed >= 0 ? joint_fixed : blockIdx.y;
+  const int row = joint_fixed >= 0 ? 0 : jt, rows = joint_fixed >= 0 ? 1 : P.dof;
+  const JointLimits L = P.lim[jt];
+  const int64_t at = (int64_t)row * n + p;
+  double T0, T1, T2, d;
+  const double q = brake_profile(L.a_max, L.j_max, P.ts, v_0[at], a_0[at], T0, T1, T2, d);
+  q_stop[at] = q;
+  dir[at] = d;
+  t_rel[((int64_t)0 * rows + row) * n + p] = T0;
+  t_rel[((int64_t)1 * rows + row) * n + p] = T1;
+  t_rel[((int64_t)2 * rows + row) * n + p] = T2;
+}
+
+__global__ void ltp_opt_switch_times_kernel(const __grid_constant__ PlannerParams P, int joint_fixed,
+                                            int64_t n, const double* __restrict__ q_goal,
+                                            const double* __restrict__ q_0,
+                                            const double* __restrict__ v_0,
+                                            const double* __restrict__ a_0,
+                                            const double* __restrict__ v_drive, double* t, double* dir,
+                                            uint8_t* mod, uint8_t* kase, uint8_t* ok) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int jt = joint_fixed >= 0 ? joint_fixed : blockIdx.y;
+  const int row = joint_fixed >= 0 ? 0 : jt, rows = joint_fixed >= 0 ? 1 : P.dof;
+  const JointLimits L = P.lim[jt];
+  const int64_t at = (int64_t)row * n + p;
+  const double qg = q_goal[at], q0 = q_0[at];
+  const Prologue pro = ost_prologue(L, P.ts, qg, q0, v_0[at], a_0[at]);
+  double tt[7];
+  zero7(tt);
+  unsigned char m = 0, c = 255;
+  const bool good = ost_body(L, P.ts, pro, qg, q0, v_drive[at], tt, m, c);
+#pragma unroll
+  for (int k = 0; k < 7; ++k) t[((int64_t)k * rows + row) * n + p] = tt[k];
+  dir[at] = pro.dir;
+  mod[at] = m;
+  if (kase) kase[at] = c;
+  ok[at] = (uint8_t)good;
+}
+
+__global__ void ltp_time_scaling_kernel(const __grid_constant__ PlannerParams P, int joint_fixed,
+                                        int64_t n, const double* __restrict__ q_goal,
+                                        const double* __restrict__ q_0, const double* __restrict__ v_0,
+                                        const double* __restrict__ a_0, const double* __restrict__ dir,
+                                        const double* __restrict__ t_required, double* t,
+                                        double* v_drive, uint8_t* mod, uint8_t* ts_case,
+                                        uint8_t* final_case, uint8_t* ok) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int jt = joint_fixed >= 0 ? joint_fixed : blockIdx.y;
+  const int row = joint_fixed >= 0 ? 0 : jt, rows = joint_fixed >= 0 ? 1 : P.dof;
+  const JointLimits L = P.lim[jt];
+  const int64_t at = (int64_t)row * n + p;
+  const double qg = q_goal[at], q0 = q_0[at], d = dir[at];
+  const TsInput I = make_ts_input(qg, q0, v_0[at], a_0[at], d, t_required[at]);
+  // the reference re-enters optSwitchTimes with (dir * v_0, dir * a_0) (cc:400); for
+  // dir = +-1 that is the caller's start state again
+  const Prologue pro = ost_prologue(L, P.ts, qg, q0, d * I.v_0, d * I.a_0);
+  double tt[7];
+  zero7(tt);
+  double vd = 0;
+  unsigned char m = 0, fc = 255;
+  const int c = time_scaling_from(1, L, P.ts, pro, I, tt, vd, m, fc);
+#pragma unroll
+  for (int k = 0; k < 7; ++k) t[((int64_t)k * rows + row) * n + p] = tt[k];
+  v_drive[at] = vd;
+  mod[at] = m;
+  if (ts_case) ts_case[at] = (uint8_t)c;
+  if (final_case) final_case[at] = fc;
+  ok[at] = (uint8_t)(c != 9);
+}
+
+// ------------------------------------------------------------------------------------
+// stage 4: dense q/v/a/j sampling (reference cc:706-841) + final limit check (cc:59-61)
+// One thread per (problem, joint) row runs the reference's sequential recurrence and
+// emits four samples per field at a time as 32-byte sector-aligned vector stores.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void store4(double* dst, double x0, double x1, double x2, double x3) {
+  // streaming (evict-first) stores: the trajectory is never re-read by this kernel
+  asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(x0), "d"(x1) : "memory");
+  asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(dst + 2), "d"(x2), "d"(x3) : "memory");
+}
+
+template <bool VEC, int MAXW>
+__global__ void __launch_bounds__(kTile * MAXW)
+ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_0,
+                  const double* __restrict__ v_0, const double* __restrict__ a_0, DeviceSolution S,
+                  int horizon, int64_t stride, double* __restrict__ q, double* __restrict__ v,
+                  double* __restrict__ a, double* __restrict__ j, uint8_t* success) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* s_ok = smem_raw;  // [dof][32]
+  const int dof = P.dof;
+  const int lane = threadIdx.x, jt = threadIdx.y;
+  const int64_t p = (int64_t)blockIdx.x * kTile + lane;
+  const bool valid = p < n;
+  const JointLimits L = P.lim[jt];
+  bool row_ok = false;
+  if (valid && S.reached[p]) {
+    const int len = S.traj_len[p];
+    if (len > 0) {
+      const int64_t at = (int64_t)jt * n + p;
+      double t[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) t[k] = S.t_scaled[((int64_t)k * dof + jt) * n + p];
+      const int n_out = horizon > 0 ? horizon : len;      // samples stored
+      const int n_run = n_out > len ? n_out : len;        // samples computed
+      RowSampler R;
+      R.init(P.ts, L.j_max, t, S.dir[at], S.mod[at], q_0[at], v_0[at], a_0[at], S.v_drive[at],
+             horizon > 0 ? n_run : len);
+      const int64_t base = (p * dof + jt) * stride;
+      double* qo = q + base; double* vo = v + base; double* ao = a + base; double* jo = j + base;
+      double q_last = 0.0;
+      int i = 0;
+      if (VEC) {
+        const int n_vec = n_out & ~3;
+        for (; i < n_vec; i += 4) {
+          double jj[4], aa[4], vv[4], qq[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            R.step(i + u, jj[u], aa[u], vv[u], qq[u]);
+            if (i + u == len - 1) q_last = qq[u];
+          }
+          store4(qo + i, qq[0], qq[1], qq[2], qq[3]);
+          store4(vo + i, vv[0], vv[1], vv[2], vv[3]);
+          store4(ao + i, aa[0], aa[1], aa[2], aa[3]);
+          store4(jo + i, jj[0], jj[1], jj[2], jj[3]);
+        }
+      }
+      for (; i < n_run; ++i) {
+        double jj, aa, vv, qq;
+        R.step(i, jj, aa, vv, qq);
+        if (i == len - 1) q_last = qq;
+        if (i < n_out) {
+          qo[i] = qq; vo[i] = vv; ao[i] = aa; jo[i] = jj;
+        }
+      }
+      row_ok = !(q_last < L.q_min || q_last > L.q_max);  // cc:60
+    }
+  }
+  s_ok[jt * kTile + lane] = (unsigned char)row_ok;
+  __syncthreads();
+  if (valid && jt == 0) {
+    bool ok = true;
+    for (int i = 0; i < dof; ++i) ok &= (s_ok[i * kTile + lane] != 0);
+    success[p] = (uint8_t)ok;
+  }
+}
+
+// [dof][7] host-style times -> [7][dof][1] is trivial on the host; nothing to do on device.
+
+}  // namespace
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+struct ltp_planner {
+  int device;
+  PlannerParams params;
+  std::atomic<int64_t> launches;
+  // scratch for the host-buffer entry points (grown on demand)
+  void* d_scratch;
+  size_t d_scratch_bytes;
+  cudaStream_t stream;  // internal stream of the host entry points
+};
+
+namespace {
+
+thread_local char g_cuda_err[256] = "";
+
+int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_cuda_err, sizeof g_cuda_err, "%s: %s", what, cudaGetErrorString(e));
+  return LTP_ERR_CUDA;
+}
+
+#define LTP_CUDA(call)                                   \
+  do {                                                   \
+    cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);  \
+  } while (0)
+
+struct DeviceGuard {
+  int prev;
+  bool ok;
+  explicit DeviceGuard(int dev) : prev(-1), ok(false) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) return;
+    ok = true;
+  }
+  ~DeviceGuard() {
+    if (ok && prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int fill_limits(PlannerParams& P, const double* q_min, const double* q_max, const double* v_max,
+                const double* a_max, const double* j_max) {
+  if (!q_min || !q_max || !v_max || !a_max || !j_max) return LTP_ERR_ARG;
+  for (int i = 0; i < P.dof; ++i) {
+    P.lim[i].q_min = q_min[i];
+    P.lim[i].q_max = q_max[i];
+    P.lim[i].v_max = v_max[i];
+    P.lim[i].a_max = a_max[i];
+    P.lim[i].j_max = j_max[i];
+  }
+  return LTP_OK;
+}
+
+DeviceSolution to_dev(const ltp_solution* s) {
+  DeviceSolution d;
+  d.t_scaled = s->t_scaled; d.dir = s->dir; d.v_drive = s->v_drive; d.mod = s->mod;
+  d.slowest = s->slowest; d.traj_len = s->traj_len; d.reached = s->reached; d.t_opt = s->t_opt;
+  d.opt_case = s->opt_case; d.ts_case = s->ts_case; d.final_case = s->final_case;
+  return d;
+}
+
+bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
+
+int ensure_scratch(ltp_planner* p, size_t bytes) {
+  if (bytes <= p->d_scratch_bytes) return LTP_OK;
+  if (p->d_scratch) LTP_CUDA(cudaFree(p->d_scratch));
+  p->d_scratch = nullptr;
+  p->d_scratch_bytes = 0;
+  LTP_CUDA(cudaMalloc(&p->d_scratch, bytes));
+  p->d_scratch_bytes = bytes;
+  return LTP_OK;
+}
+
+size_t up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// carve a solution (all fields) out of a scratch block; returns bytes used
+size_t carve_solution(unsigned char* base, int dof, int64_t n, ltp_solution* s) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    unsigned char* r = base ? base + off : nullptr;
+    off += up(bytes, 256);
+    return r;
+  };
+  const size_t dn = (size_t)dof * (size_t)n;
+  s->t_scaled = (double*)take(7 * dn * 8);
+  s->t_opt = (double*)take(7 * dn * 8);
+  s->dir = (double*)take(dn * 8);
+  s->v_drive = (double*)take(dn * 8);
+  s->mod = (uint8_t*)take(dn);
+  s->opt_case = (uint8_t*)take(dn);
+  s->ts_case = (uint8_t*)take(dn);
+  s->final_case = (uint8_t*)take(dn);
+  s->slowest = (int32_t*)take((size_t)n * 4);
+  s->traj_len = (int32_t*)take((size_t)n * 4);
+  s->reached = (uint8_t*)take((size_t)n);
+  return off;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ltp_status_string(int status) {
+  switch (status) {
+    case LTP_OK: return "ok";
+    case LTP_ERR_ARG: return "invalid argument";
+    case LTP_ERR_CUDA: return "CUDA error";
+    case LTP_ERR_CAPACITY: return "row capacity too small";
+    default: return "unknown status";
+  }
+}
+
+const char* ltp_last_cuda_error(void) { return g_cuda_err; }
+
+int ltp_create(ltp_planner** out, int device, int dof, double t_sample, const double* q_min,
+               const double* q_max, const double* v_max, const double* a_max, const double* j_max) {
+  if (!out) return LTP_ERR_ARG;
+  *out = nullptr;
+  if (dof < 0 || dof > LTP_MAX_DOF) return LTP_ERR_ARG;
+  int count = 0;
+  LTP_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return cuda_fail(cudaErrorInvalidDevice, "ltp_create(device)");
+  ltp_planner* p = new (std::nothrow) ltp_planner();
+  if (!p) return LTP_ERR_ARG;
+  p->device = device;
+  p->params.dof = dof;
+  p->params.ts = t_sample;
+  p->launches = 0;
+  p->d_scratch = nullptr;
+  p->d_scratch_bytes = 0;
+  p->stream = nullptr;
+  std::memset(p->params.lim, 0, sizeof p->params.lim);
+  if (dof > 0) {
+    int rc = fill_limits(p->params, q_min, q_max, v_max, a_max, j_max);
+    if (rc != LTP_OK) { delete p; return rc; }
+  }
+  {
+    DeviceGuard g(device);
+    if (!g.ok) { delete p; return cuda_fail(cudaGetLastError(), "cudaSetDevice"); }
+    cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaStreamCreate"); }
+  }
+  *out = p;
+  return LTP_OK;
+}
+
+int ltp_set_limits(ltp_planner* p, const double* q_min, const double* q_max, const double* v_max,
+                   const double* a_max, const double* j_max) {
+  if (!p) return LTP_ERR_ARG;
+  return fill_limits(p->params, q_min, q_max, v_max, a_max, j_max);
+}
+
+int ltp_set_sample_time(ltp_planner* p, double t_sample) {
+  if (!p) return LTP_ERR_ARG;
+  p->params.ts = t_sample;
+  return LTP_OK;
+}
+
+int ltp_set_dof(ltp_planner* p, int dof) {
+  if (!p || dof < 0 || dof > LTP_MAX_DOF) return LTP_ERR_ARG;
+  p->params.dof = dof;
+  return LTP_OK;
+}
+
+int ltp_get_dof(const ltp_planner* p) { return p ? p->params.dof : LTP_ERR_ARG; }
+int ltp_get_device(const ltp_planner* p) { return p ? p->device : LTP_ERR_ARG; }
+int64_t ltp_launch_count(const ltp_planner* p) { return p ? p->launches.load() : 0; }
+
+void ltp_destroy(ltp_planner* p) {
+  if (!p) return;
+  {
+    DeviceGuard g(p->device);
+    if (p->d_scratch) cudaFree(p->d_scratch);
+    if (p->stream) cudaStreamDestroy(p->stream);
+  }
+  delete p;
+}
+
+int ltp_opt_braking_batch(ltp_planner* p, int64_t n, const double* v_0, const double* a_0,
+                          double* q_stop, double* t_rel, double* dir, void* stream) {
+  if (!p || n < 0 || !v_0 || !a_0 || !q_stop || !t_rel || !dir || p->params.dof < 1) return LTP_ERR_ARG;
+  if (n == 0) return LTP_OK;
+  DeviceGuard g(p->device);
+  dim3 block(128), grid((unsigned)((n + 127) / 128), p->params.dof);
+  ltp_opt_braking_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(p->params, -1, n, v_0, a_0, q_stop, t_rel, dir);
+  p->launches++;
+  LTP_CUDA(cudaGetLastError());
+  return LTP_OK;
+}
+
+int ltp_opt_switch_times_batch(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
+                               const double* v_0, const double* a_0, const double* v_drive, double* t,
+                               double* dir, uint8_t* mod, uint8_t* kase, uint8_t* ok, void* stream) {
+  if (!p || n < 0 || !q_goal || !q_0 || !v_0 || !a_0 || !v_drive || !t || !dir || !mod || !ok ||
+      p->params.dof < 1)
+    return LTP_ERR_ARG;
+  if (n == 0) return LTP_OK;
+  DeviceGuard g(p->device);
+  dim3 block(128), grid((unsigned)((n + 127) / 128), p->params.dof);
+  ltp_opt_switch_times_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+      p->params, -1, n, q_goal, q_0, v_0, a_0, v_drive, t, dir, mod, kase, ok);
+  p->launches++;
+  LTP_CUDA(cudaGetLastError());
+  return LTP_OK;
+}
+
+int ltp_time_scaling_batch(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
+                           const double* v_0, const double* a_0, const double* dir,
+                           const double* t_required, double* t, double* v_drive, uint8_t* mod,
+                           uint8_t* ts_case, uint8_t* final_case, uint8_t* ok, void* stream) {
+  if (!p || n < 0 || !q_goal || !q_0 || !v_0 || !a_0 || !dir || !t_required || !t || !v_drive ||
+      !mod || !ok || p->params.dof < 1)
+    return LTP_ERR_ARG;
+  if (n == 0) return LTP_OK;
+  DeviceGuard g(p->device);
+  dim3 block(128), grid((unsigned)((n + 127) / 128), p->params.dof);
+  ltp_time_scaling_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+      p->params, -1, n, q_goal, q_0, v_0, a_0, dir, t_required, t, v_drive, mod, ts_case, final_case, ok);
+  p->launches++;
+  LTP_CUDA(cudaGetLastError());
+  return LTP_OK;
+}
+
+int ltp_solve_batch(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
+                    const double* v_0, const double* a_0, const ltp_solution* sol, void* stream) {
+  if (!p || n < 0 || !q_goal || !q_0 || !v_0 || !a_0 || !sol || p->params.dof < 1) return LTP_ERR_ARG;
+  if (!sol->t_scaled || !sol->dir || !sol->v_drive || !sol->mod || !sol->slowest || !sol->traj_len ||
+      !sol->reached)
+    return LTP_ERR_ARG;
+  if (n == 0) return LTP_OK;
+  DeviceGuard g(p->device);
+  const int dof = p->params.dof;
+  dim3 block(kTile, dof), grid((unsigned)((n + kTile - 1) / kTile));
+  const size_t smem = (size_t)dof * kTile * (sizeof(double) + sizeof(int) + 1);
+#define LTP_LAUNCH_SOLVE(W) \
+  ltp_solve_kernel<W><<<grid, block, smem, (cudaStream_t)stream>>>(p->params, n, q_goal, q_0, v_0, a_0, to_dev(sol))
+  if (dof <= 1) LTP_LAUNCH_SOLVE(1);
+  else if (dof <= 2) LTP_LAUNCH_SOLVE(2);
+  else if (dof <= 4) LTP_LAUNCH_SOLVE(4);
+  else if (dof <= 8) LTP_LAUNCH_SOLVE(8);
+  else if (dof <= 16) LTP_LAUNCH_SOLVE(16);
+  else LTP_LAUNCH_SOLVE(32);
+#undef LTP_LAUNCH_SOLVE
+  p->launches++;
+  LTP_CUDA(cudaGetLastError());
+  return LTP_OK;
+}
+
+int ltp_sample_batch(ltp_planner* p, int64_t n, const double* q_0, const double* v_0, const double* a_0,
+                     const ltp_solution* sol, int32_t horizon, int64_t stride, double* q, double* v,
+                     double* a, double* j, uint8_t* success, void* stream) {
+  if (!p || n < 0 || !q_0 || !v_0 || !a_0 || !sol || !q || !v || !a || !j || !success ||
+      p->params.dof < 1 || horizon < 0 || stride < 1 || (horizon > 0 && stride < horizon))
+    return LTP_ERR_ARG;
+  if (!sol->t_scaled || !sol->dir || !sol->v_drive || !sol->mod || !sol->traj_len || !sol->reached)
+    return LTP_ERR_ARG;
+  if (n == 0) return LTP_OK;
+  DeviceGuard g(p->device);
+  const int dof = p->params.dof;
+  dim3 block(kTile, dof), grid((unsigned)((n + kTile - 1) / kTile));
+  const size_t smem = (size_t)dof * kTile;
+  const bool vec = (stride % 4 == 0) && aligned32(q) && aligned32(v) && aligned32(a) && aligned32(j);
+#define LTP_LAUNCH_SAMPLE(V, W)                                                 \
+  ltp_sample_kernel<V, W><<<grid, block, smem, (cudaStream_t)stream>>>(          \
+      p->params, n, q_0, v_0, a_0, to_dev(sol), horizon, stride, q, v, a, j, success)
+#define LTP_LAUNCH_SAMPLE_W(V)             \
+  do {                                     \
+    if (dof <= 1) LTP_LAUNCH_SAMPLE(V, 1); \
+    else if (dof <= 2) LTP_LAUNCH_SAMPLE(V, 2); \
+    else if (dof <= 4) LTP_LAUNCH_SAMPLE(V, 4); \
+    else if (dof <= 8) LTP_LAUNCH_SAMPLE(V, 8); \
+    else if (dof <= 16) LTP_LAUNCH_SAMPLE(V, 16); \
+    else LTP_LAUNCH_SAMPLE(V, 32);         \
+  } while (0)
+  if (vec) LTP_LAUNCH_SAMPLE_W(true);
+  else LTP_LAUNCH_SAMPLE_W(false);
+#undef LTP_LAUNCH_SAMPLE_W
+#undef LTP_LAUNCH_SAMPLE
+  p->launches++;
+  LTP_CUDA(cudaGetLastError());
+  return LTP_OK;
+}
+
+// ---- host-buffer entry points ---------------------------------------------------------
+
+int ltp_solve_host(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
+                   const double* v_0, const double* a_0, const ltp_solution* hs) {
+  if (!p || n < 0 || !q_goal || !q_0 || !v_0 || !a_0 || !hs || p->params.dof < 1) return LTP_ERR_ARG;
+  if (!hs->t_scaled || !hs->dir || !hs->v_drive || !hs->mod || !hs->slowest || !hs->traj_len ||
+      !hs->reached)
+    return LTP_ERR_ARG;
+  if (n == 0) return LTP_OK;
+  DeviceGuard g(p->device);
+  const int dof = p->params.dof;
+  const size_t dn = (size_t)dof * (size_t)n;
+  ltp_solution ds;
+  const size_t sol_bytes = carve_solution(nullptr, dof, n, &ds);
+  const size_t in_bytes = up(dn * 8, 256);
+  int rc = ensure_scratch(p, sol_bytes + 4 * in_bytes);
+  if (rc != LTP_OK) return rc;
+  unsigned char* base = (unsigned char*)p->d_scratch;
+  double* d_in[4];
+  for (int i = 0; i < 4; ++i) d_in[i] = (double*)(base + i * in_bytes);
+  carve_solution(base + 4 * in_bytes, dof, n, &ds);
+  if (!hs->t_opt) ds.t_opt = nullptr;
+  if (!hs->opt_case) ds.opt_case = nullptr;
+  if (!hs->ts_case) ds.ts_case = nullptr;
+  if (!hs->final_case) ds.final_case = nullptr;
+  cudaStream_t st = p->stream;
+  const double* h_in[4] = {q_goal, q_0, v_0, a_0};
+  for (int i = 0; i < 4; ++i) LTP_CUDA(cudaMemcpyAsync(d_in[i], h_in[i], dn * 8, cudaMemcpyHostToDevice, st));
+  rc = ltp_solve_batch(p, n, d_in[0], d_in[1], d_in[2], d_in[3], &ds, st);
+  if (rc != LTP_OK) return rc;
+  LTP_CUDA(cudaMemcpyAsync(hs->t_scaled, ds.t_scaled, 7 * dn * 8, cudaMemcpyDeviceToHost, st));
+  LTP_CUDA(cudaMemcpyAsync(hs->dir, ds.dir, dn * 8, cudaMemcpyDeviceToHost, st));
+  LTP_CUDA(cudaMemcpyAsync(hs->v_drive, ds.v_drive, dn * 8, cudaMemcpyDeviceToHost, st));
+  LTP_CUDA(cudaMemcpyAsync(hs->mod, ds.mod, dn, cudaMemcpyDeviceToHost, st));
+  LTP_CUDA(cudaMemcpyAsync(hs->slowest, ds.slowest, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  LTP_CUDA(cudaMemcpyAsync(hs->traj_len, ds.traj_len, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  LTP_CUDA(cudaMemcpyAsync(hs->reached, ds.reached, (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (hs->t_opt) LTP_CUDA(cudaMemcpyAsync(hs->t_opt, ds.t_opt, 7 * dn * 8, cudaMemcpyDeviceToHost, st));
+  if (hs->opt_case) LTP_CUDA(cudaMemcpyAsync(hs->opt_case, ds.opt_case, dn, cudaMemcpyDeviceToHost, st));
+  if (hs->ts_case) LTP_CUDA(cudaMemcpyAsync(hs->ts_case, ds.ts_case, dn, cudaMemcpyDeviceToHost, st));
+  if (hs->final_case) LTP_CUDA(cudaMemcpyAsync(hs->final_case, ds.final_case, dn, cudaMemcpyDeviceToHost, st));
+  LTP_CUDA(cudaStreamSynchronize(st));
+  return LTP_OK;
+}
+
+int ltp_plan_host(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0, const double* v_0,
+                  const double* a_0, int32_t horizon, int64_t capacity, double* q, double* v, double* a,
+                  double* j, int32_t* traj_len, uint8_t* success, int64_t* needed) {
+  if (!p || n < 0 || !q_goal || !q_0 || !v_0 || !a_0 || !traj_len || !success || p->params.dof < 1 ||
+      horizon < 0 || capacity < 0)
+    return LTP_ERR_ARG;
+  if (needed) *needed = 0;
+  if (n == 0) return LTP_OK;
+  DeviceGuard g(p->device);
+  const int dof = p->params.dof;
+  const size_t dn = (size_t)dof * (size_t)n;
+  ltp_solution ds;
+  const size_t sol_bytes = carve_solution(nullptr, dof, n, &ds);
+  const size_t in_bytes = up(dn * 8, 256);
+  const size_t succ_bytes = up((size_t)n, 256);
+  // device rows use a stride rounded up to 4 samples so that the vector-store path is taken
+  const int64_t dstride = (capacity + 3) / 4 * 4;
+  const size_t row_bytes = up(dn * (size_t)dstride * 8, 256);
+  int rc = ensure_scratch(p, 4 * in_bytes + sol_bytes + succ_bytes + 4 * row_bytes);
+  if (rc != LTP_OK) return rc;
+  unsigned char* base = (unsigned char*)p->d_scratch;
+  double* d_in[4];
+  for (int i = 0; i < 4; ++i) d_in[i] = (double*)(base + i * in_bytes);
+  size_t off = 4 * in_bytes;
+  off += carve_solution(base + off, dof, n, &ds);
+  ds.t_opt = nullptr; ds.opt_case = nullptr; ds.ts_case = nullptr; ds.final_case = nullptr;
+  uint8_t* d_succ = base + off;
+  off += succ_bytes;
+  double* d_rows[4];
+  for (int i = 0; i < 4; ++i) d_rows[i] = (double*)(base + off + i * row_bytes);
+  cudaStream_t st = p->stream;
+  const double* h_in[4] = {q_goal, q_0, v_0, a_0};
+  for (int i = 0; i < 4; ++i) LTP_CUDA(cudaMemcpyAsync(d_in[i], h_in[i], dn * 8, cudaMemcpyHostToDevice, st));
+  rc = ltp_solve_batch(p, n, d_in[0], d_in[1], d_in[2], d_in[3], &ds, st);
+  if (rc != LTP_OK) return rc;
+  LTP_CUDA(cudaMemcpyAsync(traj_len, ds.traj_len, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  LTP_CUDA(cudaStreamSynchronize(st));
+  int64_t need = horizon;
+  if (horizon == 0)
+    for (int64_t i = 0; i < n; ++i) need = traj_len[i] > need ? traj_len[i] : need;
+  if (needed) *needed = need;
+  if (need > capacity || !q || !v || !a || !j) {
+    for (int64_t i = 0; i < n; ++i) success[i] = 0;
+    return need > capacity ? LTP_ERR_CAPACITY : LTP_ERR_ARG;
+  }
+  rc = ltp_sample_batch(p, n, d_in[1], d_in[2], d_in[3], &ds, horizon, dstride, d_rows[0], d_rows[1],
+                        d_rows[2], d_rows[3], d_succ, st);
+  if (rc != LTP_OK) return rc;
+  double* h_rows[4] = {q, v, a, j};
+  for (int i = 0; i < 4; ++i)
+    LTP_CUDA(cudaMemcpy2DAsync(h_rows[i], (size_t)capacity * 8, d_rows[i], (size_t)dstride * 8,
+                               (size_t)need * 8, dn, cudaMemcpyDeviceToHost, st));
+  LTP_CUDA(cudaMemcpyAsync(success, d_succ, (size_t)n, cudaMemcpyDeviceToHost, st));
+  LTP_CUDA(cudaStreamSynchronize(st));
+  return LTP_OK;
+}
+
+int ltp_opt_braking_host(ltp_planner* p, int joint, double v_0, double a_0, double* q_stop,
+                         double* t_rel3, double* dir) {
+  if (!p || joint < 0 || joint >= p->params.dof || !q_stop || !t_rel3 || !dir) return LTP_ERR_ARG;
+  DeviceGuard g(p->device);
+  int rc = ensure_scratch(p, 4096);
+  if (rc != LTP_OK) return rc;
+  double* d = (double*)p->d_scratch;  // [0]=v0 [1]=a0 [2]=q [3]=dir [4..6]=t_rel
+  double h[7] = {v_0, a_0, 0, 0, 0, 0, 0};
+  cudaStream_t st = p->stream;
+  LTP_CUDA(cudaMemcpyAsync(d, h, sizeof h, cudaMemcpyHostToDevice, st));
+  ltp_opt_braking_kernel<<<1, 32, 0, st>>>(p->params, joint, 1, d, d + 1, d + 2, d + 4, d + 3);
+  p->launches++;
+  LTP_CUDA(cudaGetLastError());
+  LTP_CUDA(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, st));
+  LTP_CUDA(cudaStreamSynchronize(st));
+  *q_stop = h[2];
+  *dir = h[3];
+  t_rel3[0] = h[4]; t_rel3[1] = h[5]; t_rel3[2] = h[6];
+  return LTP_OK;
+}
+
+int ltp_opt_switch_times_host(ltp_planner* p, int joint, double q_goal, double q_0, double v_0,
+                              double a_0, double v_drive, double* t7, double* dir, uint8_t* mod,
+                              uint8_t* kase, uint8_t* ok) {
+  if (!p || joint < 0 || joint >= p->params.dof || !t7 || !dir || !mod || !ok) return LTP_ERR_ARG;
+  DeviceGuard g(p->device);
+  int rc = ensure_scratch(p, 4096);
+  if (rc != LTP_OK) return rc;
+  double* d = (double*)p->d_scratch;  // in: 0..4; out: t 5..11, dir 12; bytes at 16*8
+  uint8_t* db = (uint8_t*)(d + 16);
+  double h[13] = {q_goal, q_0, v_0, a_0, v_drive};
+  cudaStream_t st = p->stream;
+  LTP_CUDA(cudaMemcpyAsync(d, h, sizeof h, cudaMemcpyHostToDevice, st));
+  ltp_opt_switch_times_kernel<<<1, 32, 0, st>>>(p->params, joint, 1, d, d + 1, d + 2, d + 3, d + 4, d + 5,
+                                                d + 12, db, db + 1, db + 2);
+  p->launches++;
+  LTP_CUDA(cudaGetLastError());
+  uint8_t hb[3];
+  LTP_CUDA(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, st));
+  LTP_CUDA(cudaMemcpyAsync(hb, db, 3, cudaMemcpyDeviceToHost, st));
+  LTP_CUDA(cudaStreamSynchronize(st));
+  for (int k = 0; k < 7; ++k) t7[k] = h[5 + k];
+  *dir = h[12];
+  *mod = hb[0];
+  if (kase) *kase = hb[1];
+  *ok = hb[2];
+  return LTP_OK;
+}
+
+int ltp_time_scaling_host(ltp_planner* p, int joint, double q_goal, double q_0, double v_0, double a_0,
+                          double dir, double t_required, double* t7, double* v_drive, uint8_t* mod,
+                          uint8_t* ts_case, uint8_t* ok) {
+  if (!p || joint < 0 || joint >= p->params.dof || !t7 || !v_drive || !mod || !ok) return LTP_ERR_ARG;
+  DeviceGuard g(p->device);
+  int rc = ensure_scratch(p, 4096);
+  if (rc != LTP_OK) return rc;
+  double* d = (double*)p->d_scratch;  // in 0..5; out t 6..12, v_drive 13
+  uint8_t* db = (uint8_t*)(d + 16);
+  double h[14] = {q_goal, q_0, v_0, a_0, dir, t_required};
+  cudaStream_t st = p->stream;
+  LTP_CUDA(cudaMemcpyAsync(d, h, sizeof h, cudaMemcpyHostToDevice, st));
+  ltp_time_scaling_kernel<<<1, 32, 0, st>>>(p->params, joint, 1, d, d + 1, d + 2, d + 3, d + 4, d + 5, d + 6,
+                                            d + 13, db, db + 1, db + 2, db + 3);
+  p->launches++;
+  LTP_CUDA(cudaGetLastError());
+  uint8_t hb[4];
+  LTP_CUDA(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, st));
+  LTP_CUDA(cudaMemcpyAsync(hb, db, 4, cudaMemcpyDeviceToHost, st));
+  LTP_CUDA(cudaStreamSynchronize(st));
+  for (int k = 0; k < 7; ++k) t7[k] = h[6 + k];
+  *v_drive = h[13];
+  *mod = hb[0];
+  if (ts_case) *ts_case = hb[1];
+  *ok = hb[3];
+  return LTP_OK;
+}
+
+int ltp_get_trajectory_host(ltp_planner* p, const double* t7, const double* dir, const uint8_t* mod,
+                            const double* q_0, const double* v_0, const double* a_0,
+                            const double* v_drive, int64_t capacity, double* q, double* v, double* a,
+                            double* j, int32_t* length, int64_t* needed) {
+  if (!p || !t7 || !dir || !mod || !q_0 || !v_0 || !a_0 || !v_drive || !length || capacity < 0 ||
+      p->params.dof < 1)
+    return LTP_ERR_ARG;
+  const int dof = p->params.dof;
+  // cc:716-719 on the host (same IEEE operations as the device would perform)
+  int len = 0;
+  for (int i = 0; i < dof; ++i) {
+    const int li = ltp::samples_for(t7[7 * i + 6], p->params.ts);
+    len = li > len ? li : len;
+  }
+  *length = len;
+  if (needed) *needed = len;
+  if (len > capacity) return LTP_ERR_CAPACITY;
+  if (len == 0) return LTP_OK;
+  if (!q || !v || !a || !j) return LTP_ERR_ARG;
+  DeviceGuard g(p->device);
+  const int64_t dstride = ((int64_t)len + 3) / 4 * 4;
+  ltp_solution ds;
+  const size_t sol_bytes = carve_solution(nullptr, dof, 1, &ds);
+  const size_t in_bytes = up((size_t)dof * 8, 256);
+  const size_t row_bytes = up((size_t)dof * (size_t)dstride * 8, 256);
+  int rc = ensure_scratch(p, 3 * in_bytes + sol_bytes + 256 + 4 * row_bytes);
+  if (rc != LTP_OK) return rc;
+  unsigned char* base = (unsigned char*)p->d_scratch;
+  double* d_in[3];
+  for (int i = 0; i < 3; ++i) d_in[i] = (double*)(base + i * in_bytes);
+  size_t off = 3 * in_bytes;
+  off += carve_solution(base + off, dof, 1, &ds);
+  uint8_t* d_succ = base + off;
+  off += 256;
+  double* d_rows[4];
+  for (int i = 0; i < 4; ++i) d_rows[i] = (double*)(base + off + i * row_bytes);
+  cudaStream_t st = p->stream;
+  // [dof][7] -> [7][dof][1]
+  double tt[7 * LTP_MAX_DOF];
+  for (int i = 0; i < dof; ++i)
+    for (int k = 0; k < 7; ++k) tt[k * dof + i] = t7[7 * i + k];
+  const uint8_t one = 1;
+  const int32_t len32 = len;
+  LTP_CUDA(cudaMemcpyAsync(ds.t_scaled, tt, sizeof(double) * 7 * dof, cudaMemcpyHostToDevice, st));
+  LTP_CUDA(cudaMemcpyAsync(ds.dir, dir, sizeof(double) * dof, cudaMemcpyHostToDevice, st));
+  LTP_CUDA(cudaMemcpyAsync(ds.v_drive, v_drive, sizeof(double) * dof, cudaMemcpyHostToDevice, st));
+  LTP_CUDA(cudaMemcpyAsync(ds.mod, mod, dof, cudaMemcpyHostToDevice, st));
+  LTP_CUDA(cudaMemcpyAsync(ds.traj_len, &len32, 4, cudaMemcpyHostToDevice, st));
+  LTP_CUDA(cudaMemcpyAsync(ds.reached, &one, 1, cudaMemcpyHostToDevice, st));
+  const double* h_in[3] = {q_0, v_0, a_0};
+  for (int i = 0; i < 3; ++i) LTP_CUDA(cudaMemcpyAsync(d_in[i], h_in[i], sizeof(double) * dof, cudaMemcpyHostToDevice, st));
+  LTP_CUDA(cudaStreamSynchronize(st));  // the small host arrays above live on this stack frame
+  rc = ltp_sample_batch(p, 1, d_in[0], d_in[1], d_in[2], &ds, 0, dstride, d_rows[0], d_rows[1], d_rows[2],
+                        d_rows[3], d_succ, st);
+  if (rc != LTP_OK) return rc;
+  double* h_rows[4] = {q, v, a, j};
+  for (int i = 0; i < 4; ++i)
+    LTP_CUDA(cudaMemcpy2DAsync(h_rows[i], (size_t)capacity * 8, d_rows[i], (size_t)dstride * 8,
+                               (size_t)len * 8, dof, cudaMemcpyDeviceToHost, st));
+  LTP_CUDA(cudaStreamSynchronize(st));
+  return LTP_OK;
+}
+
+}  // extern "C"

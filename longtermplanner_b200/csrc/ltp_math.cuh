@@ -1,0 +1,924 @@
+// Per-joint FP64 math of the planning hot path, written for one CUDA thread per
+// (problem, joint). Everything here is a __device__ function used by the kernels in
+// ltp_kernels.cu; the same source can be compiled for the host (LTP_HD empty) by
+// tests/host_shadow.cc so that the device arithmetic can be checked against the oracle
+// in a container without a GPU. That host build is a test artefact only: the product
+// library never links or dispatches to it.
+//
+// What is computed (reference = yannickBurkhardt/LongTermPlanner, src/long_term_planner.cc
+// = "cc", include/long_term_planner/roots.h = "roots.h"):
+//   brake_profile      fastest stop of a velocity                       cc:650-701
+//   ost_prologue/body  seven switching times at a cruise speed V        cc:82-353
+//   ts_candidate       the eight cruise-speed candidates of the search  cc:378-629
+//   time_scaling       ordered search, first accepted candidate wins    cc:358-645
+//   smallest_root      companion-matrix eigenvalues, smallest real > 1e-7   roots.h:22-50
+//   RowSampler         jerk impulses + forward-Euler q/v/a/j recurrence cc:729-831
+//
+// Numerical contract. Results must match the reference binary (g++ -O2, no FMA
+// contraction, glibc libm): every expression keeps the reference's operand order; the
+// translation unit is compiled with -fmad=false so nvcc never fuses a*b+c; FP64 division
+// and sqrt are IEEE-correct on the device. The reference's pow(x,3|4|6) calls go to
+// glibc, whose result is the correctly rounded power in >99.9% of cases (measured); here
+// they are computed as error-free products (explicit fma) rounded once, i.e. the
+// correctly rounded power. pow(x,2) is a plain product on both sides, pow(x,0.5) is sqrt.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define LTP_HD __host__ __device__ __forceinline__
+#define LTP_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define LTP_HD inline
+#define LTP_HD_NOINLINE
+#endif
+
+namespace ltp {
+
+// case byte, identical to oracle/ltp_oracle.h (the reference itself emits no case id)
+enum : unsigned char {
+  CASE_BRAKE_ONLY = 0, CASE_NOP4 = 5, CASE_Q1 = 6, CASE_Q1_P2 = 7, CASE_Q2 = 8,
+  CASE_DEGENERATE = 14, CASE_FAIL = 15,
+  F_MOD = 0x10, F_BOTH = 0x20, F_NOP2 = 0x40, F_NOP6 = 0x80
+};
+
+struct JointLimits {
+  double q_min, q_max, v_max, a_max, j_max;
+};
+
+constexpr double kEps = 4e-3;     // cc:96
+constexpr double kTol = 0.1;      // cc:370
+constexpr double kDblMin = 2.2250738585072014e-308;
+constexpr double kDblEps = 2.220446049250313e-16;
+
+LTP_HD double sq(double x) { return x * x; }
+
+// correctly rounded x^3, x^4, x^6 via double-double products (see file header)
+LTP_HD double pow3(double x) {
+  double p = x * x, e = fma(x, x, -p);
+  double h = p * x, l = fma(p, x, -h) + e * x;
+  return h + l;
+}
+LTP_HD double pow4(double x) {
+  double p = x * x, e = fma(x, x, -p);
+  double h = p * p, l = fma(p, p, -h) + 2.0 * (p * e);
+  return h + l;
+}
+LTP_HD double pow6(double x) {
+  double p = x * x, e = fma(x, x, -p);
+  double h = p * x, l = fma(p, x, -h) + e * x;  // x^3 = h + l
+  double s = h + l, sl = (h - s) + l;
+  double H = s * s, L = fma(s, s, -H) + 2.0 * (s * sl);
+  return H + L;
+}
+
+LTP_HD double sgn(double x) { return (double)((0.0 < x) - (x < 0.0)); }  // h:54-56
+
+// ------------------------------------------------------------------------------------
+// cc:650-701. Returns the signed stop displacement; T[0..2] are the three durations.
+// ------------------------------------------------------------------------------------
+LTP_HD double brake_profile(double A, double J, double Ts, double v_0, double a_0,
+                            double& T0, double& T1, double& T2, double& dir) {
+  if (v_0 * a_0 > 0) {
+    dir = -sgn(v_0);
+  } else if (fabs(v_0) > 1.0 / 2.0 * sq(a_0) / J) {
+    dir = -sgn(v_0);
+  } else {
+    dir = -sgn(a_0);
+  }
+  if (dir < 0) {
+    a_0 = -a_0;
+    v_0 = -v_0;
+  }
+  T0 = (A - a_0) / J;
+  T2 = A / J;
+  T1 = (-v_0 - 1.0 / 2.0 * T0 * a_0) / A - 1.0 / 2.0 * (T0 + T2);
+  if (T1 < -Ts) {
+    T0 = -a_0 / J + sqrt(sq(a_0) / (2 * sq(J)) - v_0 / J);
+    T2 = T0 + a_0 / J;
+    T1 = 0;
+  }
+  double s = v_0 * (T0 + T1 + T2) +
+             a_0 * (1.0 / 2.0 * sq(T0) + T0 * (T1 + T2) + 1.0 / 2.0 * sq(T2)) +
+             J * (1.0 / 6.0 * pow3(T0) + 1.0 / 2.0 * sq(T0) * (T1 + T2) - 1.0 / 6.0 * pow3(T2) +
+                  1.0 / 2.0 * T0 * sq(T2)) +
+             A * (1.0 / 2.0 * sq(T1) + T1 * T2);
+  return dir * s;
+}
+
+// ------------------------------------------------------------------------------------
+// roots.h:22-50 over the eigenvalue algorithm of Eigen 3.4's EigenSolver (real Schur form
+// of the companion matrix by Francis double-shift QR, no balancing).
+// p: coefficients, highest power first, N+1 of them. Returns the smallest real root that
+// is > 1e-7, +inf if there is none (also when the iteration fails or p is not finite).
+// ------------------------------------------------------------------------------------
+template <int N>
+struct SmallSchur {
+  double a[N][N];
+
+  LTP_HD static void householder3(double v0, double v1, double v2, double& e0, double& e1,
+                                  double& tau, double& beta) {
+    double tail = v1 * v1 + v2 * v2;
+    if (tail <= kDblMin) {
+      tau = 0.0; beta = v0; e0 = 0.0; e1 = 0.0;
+    } else {
+      double b = sqrt(v0 * v0 + tail);
+      if (v0 >= 0.0) b = -b;
+      e0 = v1 / (v0 - b);
+      e1 = v2 / (v0 - b);
+      tau = (b - v0) / b;
+      beta = b;
+    }
+  }
+  LTP_HD static void householder2(double v0, double v1, double& e0, double& tau, double& beta) {
+    double tail = v1 * v1;
+    if (tail <= kDblMin) {
+      tau = 0.0; beta = v0; e0 = 0.0;
+    } else {
+      double b = sqrt(v0 * v0 + tail);
+      if (v0 >= 0.0) b = -b;
+      e0 = v1 / (v0 - b);
+      tau = (b - v0) / b;
+      beta = b;
+    }
+  }
+
+  // returns true on convergence; a holds the quasi-triangular factor afterwards
+  LTP_HD_NOINLINE bool run() {
+    double scale = 0.0;
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) {
+        double v = fabs(a[i][j]);
+        if (v > scale) scale = v;
+      }
+    if (scale < kDblMin) {
+      for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) a[i][j] = 0.0;
+      return true;
+    }
+    // Hessenberg reduction of C/scale is the identity for a companion matrix
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) a[i][j] = a[i][j] / scale;
+    const int max_iters = 40 * N;
+    int iu = N - 1, iter = 0, total = 0;
+    double exshift = 0.0, norm = 0.0;
+    for (int j = 0; j < N; ++j) {
+      int lim = (j + 2 < N) ? j + 2 : N;
+      double cs = 0.0;
+      for (int i = 0; i < lim; ++i) cs += fabs(a[i][j]);
+      norm += cs;
+    }
+    double caz = norm * (kDblEps * kDblEps);
+    if (!(caz > kDblMin)) caz = kDblMin;
+    if (norm != 0.0) {
+      while (iu >= 0) {
+        int il = iu;
+        while (il > 0) {
+          double s = fabs(a[il - 1][il - 1]) + fabs(a[il][il]);
+          s = s * kDblEps;
+          if (!(s > caz)) s = caz;
+          if (fabs(a[il][il - 1]) <= s) break;
+          il--;
+        }
+        if (il == iu) {
+          a[iu][iu] = a[iu][iu] + exshift;
+          if (iu > 0) a[iu][iu - 1] = 0.0;
+          iu--;
+          iter = 0;
+        } else if (il == iu - 1) {
+          double p = 0.5 * (a[iu - 1][iu - 1] - a[iu][iu]);
+          double q = p * p + a[iu][iu - 1] * a[iu - 1][iu];
+          a[iu][iu] += exshift;
+          a[iu - 1][iu - 1] += exshift;
+          if (q >= 0.0) {
+            double z = sqrt(fabs(q));
+            double gp = (p >= 0.0) ? p + z : p - z;
+            double gq = a[iu][iu - 1];
+            double c, s;
+            if (gq == 0.0) {
+              c = gp < 0.0 ? -1.0 : 1.0;
+              s = 0.0;
+            } else if (gp == 0.0) {
+              c = 0.0;
+              s = gq < 0.0 ? 1.0 : -1.0;
+            } else if (fabs(gp) > fabs(gq)) {
+              double t = gq / gp;
+              double u = sqrt(1.0 + t * t);
+              if (gp < 0.0) u = -u;
+              c = 1.0 / u;
+              s = -t * c;
+            } else {
+              double t = gp / gq;
+              double u = sqrt(1.0 + t * t);
+              if (gq < 0.0) u = -u;
+              s = -1.0 / u;
+              c = -t * s;
+            }
+            for (int col = iu - 1; col < N; ++col) {
+              double x = a[iu - 1][col], y = a[iu][col];
+              a[iu - 1][col] = c * x - s * y;
+              a[iu][col] = s * x + c * y;
+            }
+            for (int row = 0; row <= iu; ++row) {
+              double x = a[row][iu - 1], y = a[row][iu];
+              a[row][iu - 1] = c * x - s * y;
+              a[row][iu] = s * x + c * y;
+            }
+            a[iu][iu - 1] = 0.0;
+          }
+          if (iu > 1) a[iu - 1][iu - 2] = 0.0;
+          iu -= 2;
+          iter = 0;
+        } else {
+          double sh0 = a[iu][iu], sh1 = a[iu - 1][iu - 1], sh2 = a[iu][iu - 1] * a[iu - 1][iu];
+          if (iter == 10) {
+            exshift += sh0;
+            for (int i = 0; i <= iu; ++i) a[i][i] -= sh0;
+            double s = fabs(a[iu][iu - 1]) + fabs(a[iu - 1][iu - 2]);
+            sh0 = 0.75 * s;
+            sh1 = 0.75 * s;
+            sh2 = -0.4375 * s * s;
+          }
+          if (iter == 30) {
+            double s = (sh1 - sh0) / 2.0;
+            s = s * s + sh2;
+            if (s > 0.0) {
+              s = sqrt(s);
+              if (sh1 < sh0) s = -s;
+              s = s + (sh1 - sh0) / 2.0;
+              s = sh0 - sh2 / s;
+              exshift += s;
+              for (int i = 0; i <= iu; ++i) a[i][i] -= s;
+              sh0 = sh1 = sh2 = 0.964;
+            }
+          }
+          iter++;
+          total++;
+          if (total > max_iters) break;
+          int im;
+          double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+          for (im = iu - 2; im >= il; --im) {
+            double tmm = a[im][im];
+            double r = sh0 - tmm;
+            double s = sh1 - tmm;
+            v0 = (r * s - sh2) / a[im + 1][im] + a[im][im + 1];
+            v1 = a[im + 1][im + 1] - tmm - r - s;
+            v2 = a[im + 2][im + 1];
+            if (im == il) break;
+            double lhs = a[im][im - 1] * (fabs(v1) + fabs(v2));
+            double rhs = v0 * (fabs(a[im - 1][im - 1]) + fabs(tmm) + fabs(a[im + 1][im + 1]));
+            if (fabs(lhs) < kDblEps * rhs) break;
+          }
+          for (int k = im; k <= iu - 2; ++k) {
+            const bool first = (k == im);
+            double w0, w1, w2, e0, e1, tau, beta;
+            if (first) {
+              w0 = v0; w1 = v1; w2 = v2;
+            } else {
+              w0 = a[k][k - 1]; w1 = a[k + 1][k - 1]; w2 = a[k + 2][k - 1];
+            }
+            householder3(w0, w1, w2, e0, e1, tau, beta);
+            if (beta != 0.0) {
+              if (first && k > il)
+                a[k][k - 1] = -a[k][k - 1];
+              else if (!first)
+                a[k][k - 1] = beta;
+              if (tau != 0.0) {
+                for (int c = k; c < N; ++c) {  // rows k..k+2 from the left
+                  double tmp = e0 * a[k + 1][c];
+                  tmp += e1 * a[k + 2][c];
+                  tmp += a[k][c];
+                  a[k][c] -= tau * tmp;
+                  a[k + 1][c] -= (tau * e0) * tmp;
+                  a[k + 2][c] -= (tau * e1) * tmp;
+                }
+                const int r1 = (iu < k + 3) ? iu : k + 3;
+                for (int r = 0; r <= r1; ++r) {  // columns k..k+2 from the right
+                  double tmp = a[r][k + 1] * e0;
+                  tmp += a[r][k + 2] * e1;
+                  tmp += a[r][k];
+                  a[r][k] -= tau * tmp;
+                  a[r][k + 1] -= (tau * tmp) * e0;
+                  a[r][k + 2] -= (tau * tmp) * e1;
+                }
+              }
+            }
+          }
+          {
+            double e0, tau, beta;
+            householder2(a[iu - 1][iu - 2], a[iu][iu - 2], e0, tau, beta);
+            if (beta != 0.0) {
+              a[iu - 1][iu - 2] = beta;
+              if (tau != 0.0) {
+                for (int c = iu - 1; c < N; ++c) {
+                  double tmp = e0 * a[iu][c];
+                  tmp += a[iu - 1][c];
+                  a[iu - 1][c] -= tau * tmp;
+                  a[iu][c] -= (tau * e0) * tmp;
+                }
+                for (int r = 0; r <= iu; ++r) {
+                  double tmp = a[r][iu] * e0;
+                  tmp += a[r][iu - 1];
+                  a[r][iu - 1] -= tau * tmp;
+                  a[r][iu] -= (tau * tmp) * e0;
+                }
+              }
+            }
+          }
+          for (int i = im + 2; i <= iu; ++i) {
+            a[i][i - 2] = 0.0;
+            if (i > im + 2) a[i][i - 3] = 0.0;
+          }
+        }
+      }
+    }
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) a[i][j] = a[i][j] * scale;
+    return total <= max_iters;
+  }
+};
+
+template <int N>
+LTP_HD_NOINLINE double smallest_root(const double* p) {
+  SmallSchur<N> S;
+  // roots.h:28-31
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) S.a[i][j] = 0.0;
+  for (int i = 0; i + 1 < N; ++i) S.a[i + 1][i] = 1.0;
+  for (int i = 0; i < N; ++i) S.a[i][N - 1] = (-1.0 * p[N - i]) / p[0];
+  double best = INFINITY;
+  if (!S.run()) return best;
+  int i = 0;
+  while (i < N) {
+    if (i == N - 1 || S.a[i + 1][i] == 0.0) {
+      double r = S.a[i][i];
+      if (!isfinite(r)) break;
+      if (r > 1e-7) best = fmin(best, r);  // roots.h:47 (imag == 0 exactly for a 1x1 block)
+      ++i;
+    } else {
+      // complex pair unless z == 0 exactly; Eigen reports (re, +-z) and roots.h:47 tests
+      // imag() == 0, so a 2x2 block whose discriminant rounds to 0 still counts as real
+      double pp = 0.5 * (S.a[i][i] - S.a[i + 1][i + 1]);
+      double t0 = S.a[i + 1][i], t1 = S.a[i][i + 1];
+      double mx = fabs(pp);
+      if (fabs(t0) > mx) mx = fabs(t0);
+      if (fabs(t1) > mx) mx = fabs(t1);
+      t0 /= mx;
+      t1 /= mx;
+      double p0 = pp / mx;
+      double z = mx * sqrt(fabs(p0 * p0 + t0 * t1));
+      double rr = S.a[i + 1][i + 1] + pp;
+      if (!(isfinite(rr) && isfinite(z))) break;
+      if (z == 0 && rr > 1e-7) best = fmin(best, rr);
+      i += 2;
+    }
+  }
+  return best;
+}
+
+// ------------------------------------------------------------------------------------
+// cc:82-353 split into the part that does not depend on the cruise speed (prologue:
+// braking solution, goal direction, BRAKE_ONLY exit) and the part that does (body).
+// timeScaling re-enters optSwitchTimes up to eight times with the same start state
+// (cc:400 restores the original signs), so the prologue is evaluated once per joint.
+// ------------------------------------------------------------------------------------
+struct Prologue {
+  double v0m, a0m;      // start state mapped to the positive direction (cc:110-113)
+  double dir;           // braking direction on the BRAKE_ONLY exit, else sign(q_diff)
+  double dist;          // (q_goal - q_0) * dir                        (cc:190)
+  double b0, b1, b2;    // braking durations (cc:100)
+  bool brake_only;      // cc:102
+};
+
+LTP_HD Prologue ost_prologue(const JointLimits& L, double Ts, double q_goal, double q_0,
+                             double v_0, double a_0) {
+  Prologue P;
+  double dirb;
+  double q_stop = brake_profile(L.a_max, L.j_max, Ts, v_0, a_0, P.b0, P.b1, P.b2, dirb);
+  double q_diff = q_goal - (q_0 + q_stop);
+  P.brake_only = fabs(q_diff) < kEps;
+  if (P.brake_only) {
+    P.dir = dirb;
+    P.v0m = v_0;
+    P.a0m = a_0;
+    P.dist = 0.0;
+    return P;
+  }
+  P.dir = sgn(q_diff);
+  if (P.dir < 0) {
+    v_0 = -v_0;
+    a_0 = -a_0;
+  }
+  P.v0m = v_0;
+  P.a0m = a_0;
+  P.dist = (q_goal - q_0) * P.dir;
+  return P;
+}
+
+LTP_HD void cumsum7(const double* T, double* t) {
+  double acc = T[0];
+  t[0] = acc;
+#pragma unroll
+  for (int i = 1; i < 7; ++i) {
+    acc = acc + T[i];
+    t[i] = acc;
+  }
+}
+
+LTP_HD void zero7(double* t) {
+#pragma unroll
+  for (int i = 0; i < 7; ++i) t[i] = 0.0;
+}
+
+// The rare tail of cc:245-337 (quartic root solves). Kept out of line: it carries the
+// 4x4 Schur workspace and is taken by well under 1% of joints for realistic limits.
+LTP_HD_NOINLINE unsigned char ost_quartic_tail(const JointLimits& L, const Prologue& P,
+                                               double q_goal, double q_0, double* T,
+                                               unsigned char& flags) {
+  const double A = L.a_max, J = L.j_max, v_0 = P.v0m, a_0 = P.a0m, dir = P.dir;
+  unsigned char base;
+  double c[5];
+  c[0] = 12;
+  c[1] = 0;
+  c[2] = -24 * sq(a_0) + 48 * J * v_0;
+  c[3] = 48 * dir * sq(J) * q_0 - 48 * dir * sq(J) * q_goal + 16 * pow3(a_0) - 48 * a_0 * J * v_0;
+  c[4] = -3 * pow4(a_0) + 12.0 * sq(a_0) * J * v_0 - 12.0 * sq(J) * sq(v_0);
+  double r = smallest_root<4>(c);
+  T[0] = (2.0 * sq(r) - 4 * a_0 * r + sq(a_0) - 2.0 * v_0 * J) / (4 * J * r);
+  T[6] = sqrt(4 * sq(J) * sq(T[0]) + 8 * a_0 * J * T[0] + 2.0 * sq(a_0) + 4 * J * v_0) / (2.0 * J);
+  T[4] = a_0 / J + T[0] + T[6];
+  T[1] = 0;
+  T[5] = 0;
+  base = CASE_Q1;
+  if (a_0 + T[0] * J > A) {  // cc:273-296
+    T[0] = (A - a_0) / J;
+    T[6] = 1.0 / J *
+           (A / 2 +
+            sqrt(9 * sq(A) +
+                 6 * sqrt(-12.0 * A * pow3(J) * pow3(T[0]) + 9 * sq(a_0) * sq(J) * sq(T[0]) -
+                          18 * a_0 * A * sq(J) * sq(T[0]) + 9 * sq(A) * sq(J) * sq(T[0]) +
+                          36 * a_0 * sq(J) * T[0] * v_0 - 72.0 * A * dir * sq(J) * q_0 +
+                          72.0 * A * dir * sq(J) * q_goal - 36 * A * sq(J) * T[0] * v_0 +
+                          3 * pow4(A) + 36 * sq(J) * sq(v_0))) /
+                6.0 -
+            A);
+    T[4] = T[6] + A / J;
+    T[1] = -(-J * sq(T[4]) - 2.0 * J * T[4] * T[6] + J * sq(T[6]) + a_0 * T[0] + A * T[0] +
+             2.0 * A * T[4] + 2.0 * A * T[6] + 2.0 * v_0) /
+           (2.0 * A);
+    T[5] = 0;
+    base = CASE_Q1_P2;
+  }
+  if (T[6] * J > A) {  // cc:299-333
+    T[6] = A / J;
+    c[0] = 12;
+    c[1] = -24 * A;
+    c[2] = -12.0 * sq(a_0) + 12.0 * sq(A) + 24 * J * v_0;
+    c[3] = 0;
+    c[4] = 24 * dir * sq(J) * q_0 * A - 24 * dir * sq(J) * q_goal * A + 3 * pow4(a_0) +
+           8 * pow3(a_0) * A + 6 * sq(a_0) * sq(A) - 12.0 * sq(a_0) * J * v_0 -
+           24 * a_0 * J * v_0 * A - 12.0 * sq(A) * J * v_0 + 12.0 * sq(J) * sq(v_0);
+    r = smallest_root<4>(c);
+    T[0] = (r - a_0 - A) / J;
+    T[4] = (a_0 + A) / J + T[0];
+    T[5] = (sq(J) * sq(T[0]) + 2.0 * sq(J) * T[0] * T[4] - sq(J) * sq(T[4]) + 2.0 * a_0 * J * T[0] +
+            2.0 * a_0 * J * T[4] - sq(A) + 2.0 * J * v_0) /
+           (2.0 * J * A);
+    T[1] = 0;
+    if (base == CASE_Q1_P2) flags |= F_BOTH;
+    base = CASE_Q2;
+  }
+  T[2] = 0;  // cc:335-336
+  T[3] = 0;
+  return base;
+}
+
+// Body of optSwitchTimes for cruise speed V. t receives the cumulative switching times;
+// on the cc:340-344 failure it is left untouched, exactly like the reference.
+LTP_HD bool ost_body(const JointLimits& L, double Ts, const Prologue& P, double q_goal, double q_0,
+                     double V, double* t, unsigned char& mod, unsigned char& kase) {
+  const double A = L.a_max, J = L.j_max;
+  const double eps = kEps;
+  double T[7];
+  unsigned char flags = 0;
+  mod = 0;
+  if (P.brake_only) {  // cc:102-107
+    T[0] = P.b0; T[1] = P.b1; T[2] = P.b2; T[3] = 0; T[4] = 0; T[5] = 0; T[6] = 0;
+    cumsum7(T, t);
+    kase = CASE_BRAKE_ONLY;
+    return true;
+  }
+  const double v_0 = P.v0m, a_0 = P.a0m;
+  double q_brake = 0.0;
+  if (v_0 + 0.5 * a_0 * fabs(a_0) / J > V) {  // cc:119-122
+    mod = 1;
+    flags |= F_MOD;
+    double unused;
+    q_brake = brake_profile(A, J, Ts, v_0 - V, a_0, T[0], T[1], T[2], unused);
+  } else {  // cc:125-143
+    T[0] = (A - a_0) / J;
+    T[2] = A / J;
+    T[1] = (V - v_0 - 0.5 * T[0] * a_0) / A - 0.5 * (T[0] + T[2]);
+    if (T[1] < -eps) {
+      double rad = J * (V - v_0) + 0.5 * sq(a_0);
+      if (rad > 0) {
+        T[2] = sqrt(rad) / J;
+        T[0] = T[2] - a_0 / J;
+        T[1] = 0;
+        flags |= F_NOP2;
+      } else {
+        zero7(t);
+        kase = CASE_DEGENERATE | flags;
+        return true;
+      }
+    }
+  }
+  // cc:147-165
+  T[4] = A / J;
+  T[6] = T[4];
+  T[5] = V / A - 1.0 / 2.0 * (T[4] + T[6]);
+  if (T[5] < -eps) {
+    double rad = V / J;
+    if (rad > 0) {
+      T[4] = sqrt(rad);
+      T[6] = T[4];
+      T[5] = 0;
+      flags |= F_NOP6;
+    } else {
+      zero7(t);
+      kase = CASE_DEGENERATE | flags;
+      return true;
+    }
+  }
+  // cc:168-190
+  double part1;
+  if (mod == 1) {
+    part1 = q_brake + V * (T[0] + T[1] + T[2]);
+  } else {
+    part1 = v_0 * (T[0] + T[1] + T[2]) +
+            a_0 * (1.0 / 2.0 * sq(T[0]) + T[0] * (T[1] + T[2]) + 1.0 / 2.0 * sq(T[2])) +
+            J * (1.0 / 6.0 * pow3(T[0]) + 1.0 / 2.0 * sq(T[0]) * (T[1] + T[2]) -
+                 1.0 / 6.0 * pow3(T[2]) + 1.0 / 2.0 * T[0] * sq(T[2])) +
+            A * (1.0 / 2.0 * sq(T[1]) + T[1] * T[2]);
+  }
+  double part2 = J * (1.0 / 6.0 * pow3(T[6]) + 1.0 / 2.0 * sq(T[6]) * (T[5] + T[4]) -
+                      1.0 / 6.0 * pow3(T[4]) + 1.0 / 2.0 * T[6] * sq(T[4])) +
+                 A * (1.0 / 2.0 * sq(T[5]) + T[5] * T[4]);
+  T[3] = (P.dist - part1 - part2) / V;
+
+  unsigned char base = (unsigned char)(1 + ((flags & F_NOP2) ? 1 : 0) + ((flags & F_NOP6) ? 2 : 0));
+
+  if (T[3] < -eps) {  // cc:194
+    if (mod == 1) {   // cc:195-199
+      zero7(t);
+      kase = CASE_FAIL | flags;
+      return false;
+    }
+    // cc:202-223
+    double rad = (sq(J) * pow4(T[0])) / 2 - (sq(J) * pow4(T[2])) / 4 +
+                 (sq(J) * sq(T[2]) * sq(T[4])) / 2 - (sq(J) * pow4(T[4])) / 4 +
+                 (sq(J) * pow4(T[6])) / 2 + 2.0 * J * a_0 * pow3(T[0]) -
+                 (2.0 * J * A * pow3(T[0])) / 3 - 2.0 * J * A * T[0] * sq(T[2]) +
+                 (2.0 * J * A * pow3(T[2])) / 3 + (2.0 * J * A * pow3(T[4])) / 3 -
+                 2.0 * J * A * sq(T[4]) * T[6] - (2.0 * J * A * pow3(T[6])) / 3 +
+                 2.0 * J * v_0 * sq(T[0]) + 2.0 * sq(a_0) * sq(T[0]) - 2.0 * a_0 * A * sq(T[0]) -
+                 2.0 * a_0 * A * sq(T[2]) + 4 * a_0 * v_0 * T[0] + 2.0 * sq(A) * sq(T[2]) +
+                 2.0 * sq(A) * sq(T[4]) - 4 * A * v_0 * T[0] + 4 * P.dist * A + 2.0 * sq(v_0);
+    if (rad > 0) {  // cc:224-236
+      T[5] = -(4 * A * T[4] - 2.0 * sqrt(rad) + J * sq(T[2]) - J * sq(T[4]) + 2.0 * J * sq(T[6])) /
+             (4 * A);
+      T[1] = (-v_0 - a_0 * T[0] - 1.0 / 2.0 * J * sq(T[0]) + 1.0 / 2.0 * J * sq(T[2]) +
+              1.0 / 2.0 * J * sq(T[6]) - 1.0 / 2.0 * J * sq(T[4])) /
+                 A -
+             T[2] + T[5] + T[4];
+      T[3] = 0;
+      base = CASE_NOP4;
+    } else {
+      zero7(t);
+      kase = CASE_DEGENERATE | flags;
+      return true;
+    }
+    if (T[5] < -eps || T[1] < -eps) base = ost_quartic_tail(L, P, q_goal, q_0, T, flags);
+  }
+  // cc:340-348
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    if (T[i] < -eps) {
+      kase = CASE_FAIL | flags;
+      return false;
+    } else if (T[i] < 0.0 && T[i] >= -eps) {
+      T[i] = 0.0;
+    }
+  }
+  cumsum7(T, t);  // cc:351
+  kase = base | flags;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------
+// cc:378-629: the k-th cruise-speed candidate (k = 1..8) of the time-scaling search.
+// v_0, a_0 are in the mapped frame (cc:372-375); tr is the required end time.
+// ------------------------------------------------------------------------------------
+struct TsInput {
+  double q_goal, q_0, v_0, a_0, dir, tr;
+};
+
+LTP_HD double ts_candidate1(const JointLimits& L, const TsInput& I) {
+  const double A = L.a_max, J = L.j_max, a_0 = I.a_0, v_0 = I.v_0, tr = I.tr, dir = I.dir;
+  return (A * J * tr / 2 - sq(a_0) / 4 + a_0 * A / 2 - sq(A) / 2 + v_0 * J / 2 -
+          sqrt(36 * sq(A) * sq(J) * sq(tr) - 36 * sq(a_0) * A * J * tr + 72.0 * a_0 * sq(A) * J * tr -
+               72.0 * pow3(A) * J * tr + 144 * A * dir * sq(J) * I.q_0 -
+               144 * A * dir * sq(J) * I.q_goal + 72.0 * A * sq(J) * v_0 * tr - 9 * pow4(a_0) +
+               12.0 * pow3(a_0) * A + 36 * sq(a_0) * sq(A) + 36 * sq(a_0) * J * v_0 -
+               72.0 * a_0 * pow3(A) - 72.0 * a_0 * A * J * v_0 + 36 * pow4(A) -
+               36 * sq(J) * sq(v_0)) /
+              12) /
+         J;
+}
+
+LTP_HD double ts_candidate2(const JointLimits& L, const TsInput& I) {
+  const double A = L.a_max, J = L.j_max, a_0 = I.a_0, v_0 = I.v_0, tr = I.tr, dir = I.dir;
+  // w, h, g: sub-expressions the reference writes out repeatedly (cc:413-431)
+  const double w = (v_0 + (a_0 * (a_0 - A)) / (2.0 * J)) / A;
+  const double h = A / (2.0 * J);
+  const double g = (a_0 - A) / (2.0 * J);
+  const double sA = a_0 + A;
+  const double J3 = pow3(J);
+  return -(dir * (I.q_0 - I.q_goal) -
+           J * (pow3(sA) / (6 * J3) - pow3(A) / (6 * J3) + (sq(A) * sA) / (2.0 * J3) +
+                (sq(sA) * (w + h + g)) / (2.0 * sq(J))) +
+           a_0 * (sq(sA) / (2.0 * sq(J)) + sq(A) / (2.0 * sq(J)) + (sA * (w + h + g)) / J) -
+           A * (sq(w - h + g) / 2 + (A * (w - h + g)) / J) + v_0 * (w + sA / J + h + g)) /
+         (h - v_0 / A + A * ((w - h + g) / A + 1.0 / J) -
+          (sq(a_0) + 2.0 * a_0 * A + 4 * sq(A) - 2.0 * J * tr * A + 2.0 * J * v_0) / (2.0 * A * J) +
+          sq(sA) / (2.0 * A * J) - (a_0 * sA) / (A * J));
+}
+
+// candidates 3..8 need a polynomial root (quartic, quartic, quintic, quartic, quartic, sextic)
+LTP_HD_NOINLINE double ts_candidate_root(int k, const JointLimits& L, const TsInput& I) {
+  const double A = L.a_max, J = L.j_max, a_0 = I.a_0, v_0 = I.v_0, tr = I.tr, dir = I.dir;
+  const double q_0 = I.q_0, q_goal = I.q_goal;
+  double p[7], r;
+  switch (k) {
+    case 3:  // cc:449-473
+      p[0] = 3;
+      p[1] = 12.0 * A;
+      p[2] = -24 * A * J * tr - 12.0 * sq(a_0) - 24 * a_0 * A + 12.0 * sq(A) + 24 * J * v_0;
+      p[3] = 0;
+      p[4] = 48 * sq(a_0) * A * J * tr - 96 * dir * sq(J) * A * q_0 + 96 * dir * sq(J) * A * q_goal -
+             96 * A * sq(J) * v_0 * tr + 12.0 * pow4(a_0) + 16 * pow3(a_0) * A -
+             24 * sq(a_0) * sq(A) - 48 * sq(a_0) * J * v_0 + 48 * sq(A) * J * v_0 +
+             48 * sq(J) * sq(v_0);
+      r = smallest_root<4>(p);
+      return (-2.0 * sq(a_0) + 4 * J * v_0 + sq(r)) / (4 * J);
+    case 4:  // cc:485-514
+      p[0] = 12;
+      p[1] = 24 * A;
+      p[2] = -24 * A * J * tr + 24 * sq(a_0) - 48 * a_0 * A + 24 * sq(A) - 24 * J * v_0 + 12.0 * a_0 -
+             12.0 * A;
+      p[3] = 0;
+      p[4] = -24 * dir * sq(J) * A * q_0 + 24 * dir * sq(J) * A * q_goal + 9 * pow4(a_0) -
+             12.0 * pow3(a_0) * A - 24 * sq(a_0) * J * v_0 + 48 * a_0 * A * J * v_0 + 4 * pow4(A) -
+             24 * sq(A) * J * v_0 + 12.0 * sq(J) * sq(v_0) + 6 * pow3(a_0) + 6 * sq(a_0) * A -
+             12.0 * a_0 * sq(A) - 12.0 * a_0 * J * v_0 + 12.0 * A * J * v_0 + 4 * a_0 * A - 4 * sq(A);
+      r = smallest_root<4>(p);
+      return sq(r) / J;
+    case 5: {  // cc:526-541
+      const double J3 = pow3(J), J4 = pow4(J), a3 = pow3(a_0), a4 = pow4(a_0);
+      p[0] = (144 * J * tr + 144 * a_0);
+      p[1] = (-72.0 * sq(J) * sq(tr) - 144 * a_0 * J * tr + 36 * sq(a_0) - 216 * J * v_0);
+      p[2] = (144 * dir * sq(J) * q_0 - 144 * dir * sq(J) * q_goal + 48 * a3 - 144 * a_0 * J * v_0);
+      p[3] = (-144 * dir * J3 * q_0 * tr + 144 * dir * J3 * q_goal * tr - 48 * a3 * J * tr -
+              144 * a_0 * dir * sq(J) * q_0 + 144 * a_0 * dir * sq(J) * q_goal +
+              144 * a_0 * sq(J) * v_0 * tr + 6 * a4 - 72.0 * sq(a_0) * J * v_0 + 216 * sq(J) * sq(v_0));
+      p[4] = 0;
+      p[5] = -72.0 * sq(dir) * J4 * sq(q_0) + 144 * sq(dir) * J4 * q_0 * q_goal -
+             72.0 * sq(dir) * J4 * sq(q_goal) - 48 * a3 * dir * sq(J) * q_0 +
+             48 * a3 * dir * sq(J) * q_goal + 144 * a_0 * dir * J3 * q_0 * v_0 -
+             144 * a_0 * dir * J3 * q_goal * v_0 + pow6(a_0) - 6 * a4 * J * v_0 +
+             36 * sq(a_0) * sq(J) * sq(v_0) - 72.0 * J3 * pow3(v_0);
+      r = smallest_root<5>(p);
+      return sq(r) / J;
+    }
+    case 6:  // cc:553-567
+      p[0] = 3;
+      p[1] = -6 * 1.4142135623730951 * A;  // -6*sqrt(2)*a_max
+      p[2] = (12.0 * A * J * tr - 6 * sq(a_0) - 12.0 * a_0 * A - 6 * sq(A) - 12.0 * J * v_0);
+      p[3] = 0;
+      p[4] = -12.0 * sq(a_0) * A * J * tr - 24 * dir * sq(J) * A * q_0 + 24 * dir * sq(J) * A * q_goal -
+             24 * A * sq(J) * v_0 * tr + 3 * pow4(a_0) + 4 * pow3(a_0) * A + 6 * sq(a_0) * sq(A) +
+             12.0 * sq(a_0) * J * v_0 + 12.0 * sq(A) * J * v_0 + 12.0 * sq(J) * sq(v_0);
+      r = smallest_root<4>(p);
+      return -(sq(r) - sq(a_0) - 2.0 * J * v_0) / (2.0 * J);
+    case 7:  // cc:579-593
+      p[0] = 12;
+      p[1] = -24 * A;
+      p[2] = (24 * A * J * tr - 12.0 * sq(a_0) - 24 * a_0 * A - 12.0 * sq(A) - 24 * J * v_0);
+      p[3] = 0;
+      p[4] = 24 * dir * sq(J) * A * q_0 - 24 * dir * sq(J) * A * q_goal + 3 * pow4(a_0) +
+             8 * pow3(a_0) * A + 6 * sq(a_0) * sq(A) + 12.0 * sq(a_0) * J * v_0 +
+             24 * a_0 * A * J * v_0 + 12.0 * sq(A) * J * v_0 + 12.0 * sq(J) * sq(v_0);
+      r = smallest_root<4>(p);
+      return sq(r) / J;
+    default: {  // 8, cc:606-629
+      const double J3 = pow3(J), J4 = pow4(J), a3 = pow3(a_0), a4 = pow4(a_0);
+      p[0] = 144;
+      p[1] = (-144 * J * tr + 144 * a_0);
+      p[2] = (72.0 * sq(J) * sq(tr) - 144 * a_0 * J * tr - 36 * sq(a_0) - 216 * J * v_0);
+      p[3] = (-144 * dir * sq(J) * q_0 + 144 * dir * sq(J) * q_goal - 48 * a3 - 144 * a_0 * J * v_0);
+      p[4] = (144 * dir * J3 * q_0 * tr - 144 * dir * J3 * q_goal * tr + 48 * a3 * J * tr -
+              144 * a_0 * dir * sq(J) * q_0 + 144 * a_0 * dir * sq(J) * q_goal +
+              144 * a_0 * sq(J) * v_0 * tr + 6 * a4 + 72.0 * sq(a_0) * J * v_0 + 216 * sq(J) * sq(v_0));
+      p[5] = 0;
+      p[6] = 72.0 * sq(dir) * J4 * sq(q_0) - 144 * sq(dir) * J4 * q_0 * q_goal +
+             72.0 * sq(dir) * J4 * sq(q_goal) + 48 * a3 * dir * sq(J) * q_0 -
+             48 * a3 * dir * sq(J) * q_goal + 144 * a_0 * dir * J3 * q_0 * v_0 -
+             144 * a_0 * dir * J3 * q_goal * v_0 - pow6(a_0) - 6 * a4 * J * v_0 -
+             36 * sq(a_0) * sq(J) * sq(v_0) - 72.0 * J3 * pow3(v_0);
+      r = smallest_root<6>(p);
+      return sq(r) / J;
+    }
+  }
+}
+
+// One attempt of the search (the block repeated at cc:398-405, 439-446, ...): if the
+// candidate is usable, re-solve the switching times at that cruise speed and accept when
+// the end time falls inside (t_req - 0.1, t_req + 0.01).
+LTP_HD bool ts_try(const JointLimits& L, double Ts, const Prologue& P, const TsInput& I, double V,
+                   double* scaled_t, unsigned char& mod, unsigned char& kase) {
+  if (!isnan(V) && V > 0) {
+    bool ok = ost_body(L, Ts, P, I.q_goal, I.q_0, V, scaled_t, mod, kase);
+    if (ok && I.tr - scaled_t[6] < kTol && I.tr - scaled_t[6] > -kTol / 10) return true;
+  }
+  return false;
+}
+
+// cc:358-645 from attempt `first` on (1 = whole search). P must be the prologue of this
+// joint's start state. Returns the accepted attempt (1..8) or 9 after the cc:641-644 reset.
+LTP_HD int time_scaling_from(int first, const JointLimits& L, double Ts, const Prologue& P,
+                             const TsInput& I, double* scaled_t, double& v_drive,
+                             unsigned char& mod, unsigned char& final_case) {
+  double V;
+  if (first <= 1) {
+    V = ts_candidate1(L, I);
+    v_drive = V;
+    if (ts_try(L, Ts, P, I, V, scaled_t, mod, final_case)) return 1;
+  }
+  if (first <= 2) {
+    V = ts_candidate2(L, I);
+    v_drive = V;
+    if (ts_try(L, Ts, P, I, V, scaled_t, mod, final_case)) return 2;
+  }
+  for (int k = (first > 3 ? first : 3); k <= 8; ++k) {
+    V = ts_candidate_root(k, L, I);
+    v_drive = V;
+    if (ts_try(L, Ts, P, I, V, scaled_t, mod, final_case)) return k;
+  }
+  mod = 0;
+  zero7(scaled_t);
+  v_drive = L.v_max;
+  final_case = CASE_FAIL;
+  return 9;
+}
+
+LTP_HD TsInput make_ts_input(double q_goal, double q_0, double v_0, double a_0, double dir,
+                             double tr) {
+  TsInput I;
+  I.q_goal = q_goal;
+  I.q_0 = q_0;
+  if (dir < 0) {  // cc:372-375
+    v_0 = -v_0;
+    a_0 = -a_0;
+  }
+  I.v_0 = v_0;
+  I.a_0 = a_0;
+  I.dir = dir;
+  I.tr = tr;
+  return I;
+}
+
+// cc:68-77 for one joint
+LTP_HD bool check_joint_input(const JointLimits& L, double q_0, double v_0, double a_0) {
+  if (q_0 < L.q_min || q_0 > L.q_max || fabs(v_0) > L.v_max || fabs(a_0) > L.a_max) return false;
+  if (fabs(v_0 + 0.5 * a_0 * fabs(a_0) / L.j_max) > L.v_max) return false;
+  return true;
+}
+
+// cc:718 for one joint: (int)ceil(t6/Ts) + 1, or 0 when the time is not representable
+// (the reference would invoke undefined behaviour there).
+LTP_HD int samples_for(double t6, double Ts) {
+  double x = ceil(t6 / Ts);
+  if (!(x >= -1.0e9 && x <= 2.0e9)) return 0;
+  return (int)x + 1;
+}
+
+// ------------------------------------------------------------------------------------
+// cc:729-831 for one (problem, joint) row, as a streaming state machine: init() derives the
+// sample indices, the piecewise-constant jerk and the (up to 8) fractional impulses;
+// step(i) returns sample i of j/a/v/q. Sample 0 is t = Ts (cc:810-812).
+// Impulses whose index falls outside [0, limit) are dropped (the reference writes them
+// out of bounds).
+// ------------------------------------------------------------------------------------
+struct RowSampler {
+  double Ts, jp0, jp2, jp4, jp6;  // jerk of the four non-zero phases (phases 2, 4, 6 are 0)
+  double vcruise;                 // v_drive * dir (cc:823)
+  int s[7];
+  int imp_idx[8];
+  double imp_a[8], imp_b[8], imp_c[8];  // value added = ((j + a) + b) + c, source order
+  unsigned char imp_n[8];               // how many of a,b,c are used (0 = slot unused)
+  bool phase4;
+  double a, v, q;
+
+  LTP_HD void add_imp(int slot, int idx, int limit, double x, double y, double z, int n) {
+    imp_idx[slot] = idx;
+    imp_a[slot] = x; imp_b[slot] = y; imp_c[slot] = z;
+    imp_n[slot] = (idx >= 0 && idx < limit) ? (unsigned char)n : (unsigned char)0;
+  }
+
+  LTP_HD void init(double Ts_, double J, const double* t, double dir, unsigned char mod,
+                   double q_0, double v_0, double a_0, double v_drive, int limit) {
+    Ts = Ts_;
+    // cc:734-744: profile {+1,0,-1,0,-1,0,+1} or modified {-1,0,+1,0,-1,0,+1}
+    const double dj = dir * J;
+    jp0 = dj * (mod == 1 ? -1 : 1);
+    jp2 = dj * (mod == 1 ? 1 : -1);
+    jp4 = dj * -1;
+    jp6 = dj * 1;
+    vcruise = v_drive * dir;
+    double fr[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      double r = t[k] / Ts;
+      double fl = floor(r);
+      fr[k] = t[k] - Ts * fl;  // cc:747
+      double idx = (k & 1) ? ceil(r) : fl;  // cc:751-757
+      // clamp before the cast: NaN / huge values are undefined in the reference
+      if (!(idx >= -2.0e9)) idx = -2.0e9;
+      if (idx > 2.0e9) idx = 2.0e9;
+      s[k] = (int)idx;
+    }
+    // cc:768-807, source order
+    if (s[2] >= s[1]) {
+      add_imp(0, s[0] + 1, limit, fr[0] / Ts * jp0, 0, 0, 1);
+      add_imp(1, s[1], (s[1] > 0) ? limit : 0, (1 - fr[1] / Ts) * jp2, 0, 0, 1);
+      add_imp(2, s[2] + 1, limit, fr[2] / Ts * jp2, 0, 0, 1);
+    } else {
+      add_imp(0, s[1], (s[1] > 0) ? limit : 0, fr[0] / Ts * jp0, (fr[2] - fr[0]) / Ts * jp2, 0, 2);
+      add_imp(1, -1, 0, 0, 0, 0, 0);
+      add_imp(2, -1, 0, 0, 0, 0, 0);
+    }
+    add_imp(3, s[3], (s[3] > 0) ? limit : 0, (1 - fr[3] / Ts) * jp4, 0, 0, 1);
+    if (s[2] - s[0] > 0) {
+      add_imp(4, s[4] + 1, limit, fr[4] / Ts * jp4, 0, 0, 1);
+    } else {
+      add_imp(4, s[4], (s[4] > 0) ? limit : 0, fr[4] / Ts * jp4, fr[0] / Ts * jp0,
+              (fr[2] - fr[0]) / Ts * jp2, 3);
+    }
+    add_imp(5, s[5], (s[5] > 0) ? limit : 0, (1 - fr[5] / Ts) * jp6, 0, 0, 1);
+    add_imp(6, s[6] + 1, limit, fr[6] / Ts * jp6, 0, 0, 1);
+    imp_n[7] = 0;
+    imp_idx[7] = -1;
+    phase4 = s[3] - s[2] > 2;  // cc:813
+    a = a_0; v = v_0; q = q_0;
+  }
+
+  // piecewise-constant part of the jerk at sample i: the reference fills ranges in phase
+  // order and later fills overwrite earlier ones (cc:759-766) -> last writer wins
+  LTP_HD double base_jerk(int i) const {
+    if (s[6] - s[5] > 0 && i >= s[5] && i < s[6]) return jp6;
+    if (s[5] - s[4] > 0 && i >= s[4] && i < s[5]) return 0.0;
+    if (s[4] - s[3] > 0 && i >= s[3] && i < s[4]) return jp4;
+    if (s[3] - s[2] > 0 && i >= s[2] && i < s[3]) return 0.0;
+    if (s[2] - s[1] > 0 && i >= s[1] && i < s[2]) return jp2;
+    if (s[1] - s[0] > 0 && i >= s[0] && i < s[1]) return 0.0;
+    if (s[0] > 0 && i < s[0]) return jp0;
+    return 0.0;
+  }
+
+  LTP_HD double jerk_at(int i) const {
+    double j = base_jerk(i);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      if (imp_n[k] != 0 && imp_idx[k] == i) {
+        j = j + imp_a[k];
+        if (imp_n[k] > 1) j = j + imp_b[k];
+        if (imp_n[k] > 2) j = j + imp_c[k];
+      }
+    }
+    return j;
+  }
+
+  // cc:810-831
+  LTP_HD void step(int i, double& jo, double& ao, double& vo, double& qo) {
+    const double j = jerk_at(i);
+    if (i == 0 || i <= s[6]) a = a + Ts * j; else a = 0.0;
+    if (i > 0 && phase4 && i >= s[2] + 1 && i < s[3] - 1) v = vcruise;
+    else if (i == 0 || i <= s[6]) v = v + Ts * a;
+    else v = 0.0;
+    q = q + Ts * v;
+    jo = j; ao = a; vo = v; qo = q;
+  }
+};
+
+}  // namespace ltp

@@ -1,0 +1,321 @@
+"""Python mirror of the reference's LongTermPlanner interface over the C ABI.
+
+Same names, argument order and error behaviour as the reference class
+(include/long_term_planner/long_term_planner.h:61-308 of yannickBurkhardt/LongTermPlanner):
+``planTrajectory`` returns a bool and fills a ``Trajectory``; the protected per-joint
+methods are exposed the way the reference's own test fixture exposes them
+(tests/include/long_term_planner_fixture.h:34-57). ``planTrajectories`` is the new batched
+entry point over structure-of-arrays CUDA tensors.
+
+torch is used for device memory and streams only. Every call lands in the hand-written
+kernels of csrc/ltp_b200.cu through include/ltp_b200.h; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _capi as capi
+
+
+@dataclasses.dataclass
+class Trajectory:
+    """reference long_term_planner.h:37-45"""
+    dof: int = 0
+    t_sample: float = 0.0
+    length: int = 0
+    q: List[List[float]] = dataclasses.field(default_factory=list)
+    v: List[List[float]] = dataclasses.field(default_factory=list)
+    a: List[List[float]] = dataclasses.field(default_factory=list)
+    j: List[List[float]] = dataclasses.field(default_factory=list)
+
+
+@dataclasses.dataclass
+class BatchSolution:
+    """Device-resident result of stages 1-3 for n problems (joint-major tensors)."""
+    n: int
+    dof: int
+    t_scaled: torch.Tensor   # [7, dof, n] f64
+    dir: torch.Tensor        # [dof, n] f64
+    v_drive: torch.Tensor    # [dof, n] f64
+    mod: torch.Tensor        # [dof, n] u8
+    slowest: torch.Tensor    # [n] i32
+    traj_len: torch.Tensor   # [n] i32
+    reached: torch.Tensor    # [n] u8
+    t_opt: Optional[torch.Tensor] = None       # [7, dof, n]
+    opt_case: Optional[torch.Tensor] = None    # [dof, n] u8
+    ts_case: Optional[torch.Tensor] = None
+    final_case: Optional[torch.Tensor] = None
+
+    def c_struct(self) -> capi.Solution:
+        def ptr(t):
+            return None if t is None else t.data_ptr()
+        return capi.Solution(ptr(self.t_scaled), ptr(self.dir), ptr(self.v_drive), ptr(self.mod),
+                             ptr(self.slowest), ptr(self.traj_len), ptr(self.reached), ptr(self.t_opt),
+                             ptr(self.opt_case), ptr(self.ts_case), ptr(self.final_case))
+
+
+@dataclasses.dataclass
+class BatchTrajectories:
+    """Device-resident sampled trajectories: rows [n, dof, stride], sample-contiguous."""
+    horizon: int
+    stride: int
+    q: torch.Tensor
+    v: torch.Tensor
+    a: torch.Tensor
+    j: torch.Tensor
+    success: torch.Tensor   # [n] u8
+    traj_len: torch.Tensor  # [n] i32
+
+
+def _vec(x: Sequence[float], dof: int) -> np.ndarray:
+    a = np.ascontiguousarray(x, dtype=np.float64)
+    if a.shape != (dof,):
+        raise ValueError(f"expected {dof} values, got shape {a.shape}")
+    return a
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class LongTermPlanner:
+    def __init__(self, dof: int = 0, t_sample: float = 0.001, q_min=(), q_max=(), v_max=(), a_max=(),
+                 j_max=(), device: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("longtermplanner_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self._h = capi.vp()
+        lims = [_vec(x, dof) for x in (q_min, q_max, v_max, a_max, j_max)]
+        capi.check(capi.create(C.byref(self._h), self.device, int(dof), float(t_sample),
+                               *[_np_ptr(x) for x in lims]), "ltp_create")
+        self.dof_, self.t_sample_ = int(dof), float(t_sample)
+        self.limits_ = lims
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            capi.destroy(h)
+            self._h = None
+
+    # ---- setters (reference long_term_planner.h:176-205) --------------------------------
+    def setLimits(self, q_min, q_max, v_max, a_max, j_max) -> None:
+        lims = [_vec(x, self.dof_) for x in (q_min, q_max, v_max, a_max, j_max)]
+        capi.check(capi.set_limits(self._h, *[_np_ptr(x) for x in lims]), "ltp_set_limits")
+        self.limits_ = lims
+
+    def setSampleTime(self, t_sample: float) -> None:
+        capi.check(capi.set_sample_time(self._h, float(t_sample)), "ltp_set_sample_time")
+        self.t_sample_ = float(t_sample)
+
+    def setDoF(self, dof) -> None:
+        capi.check(capi.set_dof(self._h, int(dof)), "ltp_set_dof")
+        self.dof_ = int(dof)
+
+    @property
+    def launches(self) -> int:
+        return int(capi.launch_count(self._h))
+
+    # ---- reference long_term_planner.cc:68-77 ---------------------------------------------
+    def checkInputs(self, q_0, v_0, a_0) -> bool:
+        q_min, q_max, v_max, a_max, j_max = self.limits_
+        q_0, v_0, a_0 = (_vec(x, self.dof_) for x in (q_0, v_0, a_0))
+        for i in range(self.dof_):
+            if q_0[i] < q_min[i] or q_0[i] > q_max[i] or abs(v_0[i]) > v_max[i] or abs(a_0[i]) > a_max[i]:
+                return False
+            if abs(v_0[i] + 0.5 * a_0[i] * abs(a_0[i]) / j_max[i]) > v_max[i]:
+                return False
+        return True
+
+    # ---- reference long_term_planner.cc:7-63 ----------------------------------------------
+    def planTrajectory(self, q_goal, q_0, v_0, a_0, traj: Trajectory) -> bool:
+        dof = self.dof_
+        ins = [_vec(x, dof) for x in (q_goal, q_0, v_0, a_0)]
+        cap = 4096
+        while True:
+            rows = [np.empty((dof, cap)) for _ in range(4)]
+            ln = np.zeros(1, np.int32)
+            ok = np.zeros(1, np.uint8)
+            needed = capi.i64(0)
+            rc = capi.plan_host(self._h, 1, *[_np_ptr(x) for x in ins], 0, cap, *[_np_ptr(r) for r in rows],
+                                _np_ptr(ln), _np_ptr(ok), C.byref(needed))
+            if rc == capi.LTP_ERR_CAPACITY:
+                cap = int(needed.value)
+                continue
+            capi.check(rc, "ltp_plan_host")
+            break
+        n = int(ln[0])
+        if n <= 0:
+            return False  # early `return false` of the reference: traj untouched
+        traj.dof, traj.t_sample, traj.length = dof, self.t_sample_, n
+        traj.q, traj.v, traj.a, traj.j = (r[:, :n].tolist() for r in rows)
+        return bool(ok[0])
+
+    # ---- protected methods of the reference, single item ----------------------------------
+    def optBraking(self, joint: int, v_0: float, a_0: float):
+        """-> (True, q, t_rel[0..2], dir)   reference long_term_planner.cc:650-701"""
+        q, d = C.c_double(), C.c_double()
+        t3 = np.zeros(3)
+        capi.check(capi.opt_braking_host(self._h, joint, v_0, a_0, C.byref(q), _np_ptr(t3), C.byref(d)))
+        return True, q.value, t3, d.value
+
+    def optSwitchTimes(self, joint, q_goal, q_0, v_0, a_0, v_drive):
+        """-> (success, t[7], dir, mod_jerk_profile)   reference long_term_planner.cc:82-353"""
+        t7 = np.zeros(7)
+        d = C.c_double()
+        mod, kase, ok = C.c_uint8(), C.c_uint8(), C.c_uint8()
+        capi.check(capi.opt_switch_times_host(self._h, joint, q_goal, q_0, v_0, a_0, v_drive, _np_ptr(t7),
+                                              C.byref(d), C.byref(mod), C.byref(kase), C.byref(ok)))
+        return bool(ok.value), t7, d.value, int(mod.value)
+
+    def timeScaling(self, joint, q_goal, q_0, v_0, a_0, dir, t_required):
+        """-> (success, scaled_t[7], v_drive, mod_jerk_profile)   reference cc:358-645"""
+        t7 = np.zeros(7)
+        vd = C.c_double()
+        mod, tsc, ok = C.c_uint8(), C.c_uint8(), C.c_uint8()
+        capi.check(capi.time_scaling_host(self._h, joint, q_goal, q_0, v_0, a_0, dir, t_required, _np_ptr(t7),
+                                          C.byref(vd), C.byref(mod), C.byref(tsc), C.byref(ok)))
+        return bool(ok.value), t7, vd.value, int(mod.value)
+
+    def getTrajectory(self, t, dir, mod_jerk_profile, q_0, v_0, a_0, v_drive) -> Trajectory:
+        """reference long_term_planner.cc:706-841"""
+        dof = self.dof_
+        t7 = np.ascontiguousarray(t, dtype=np.float64).reshape(dof, 7)
+        d, q0, v0, a0, vd = (_vec(x, dof) for x in (dir, q_0, v_0, a_0, v_drive))
+        mod = np.ascontiguousarray(mod_jerk_profile, dtype=np.uint8).reshape(dof)
+        cap = 4096
+        while True:
+            rows = [np.empty((dof, cap)) for _ in range(4)]
+            ln = C.c_int32(0)
+            needed = capi.i64(0)
+            rc = capi.get_trajectory_host(self._h, _np_ptr(t7), _np_ptr(d), _np_ptr(mod), _np_ptr(q0),
+                                          _np_ptr(v0), _np_ptr(a0), _np_ptr(vd), cap,
+                                          *[_np_ptr(r) for r in rows], C.byref(ln), C.byref(needed))
+            if rc == capi.LTP_ERR_CAPACITY:
+                cap = int(needed.value)
+                continue
+            capi.check(rc, "ltp_get_trajectory_host")
+            break
+        n = int(ln.value)
+        tr = Trajectory(dof=dof, t_sample=self.t_sample_, length=n)
+        tr.q, tr.v, tr.a, tr.j = (r[:, :n].tolist() for r in rows)
+        return tr
+
+    # ---- batched entry points over SoA device buffers --------------------------------------
+    def _chk(self, t: torch.Tensor, n: int, name: str) -> torch.Tensor:
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == (self.dof_, n)):
+            raise ValueError(f"{name}: expected contiguous float64 CUDA tensor of shape ({self.dof_}, {n})")
+        if t.device.index != self.device:
+            raise ValueError(f"{name}: tensor lives on cuda:{t.device.index}, planner on cuda:{self.device}")
+        return t
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def alloc_solution(self, n: int, with_opt: bool = False, with_cases: bool = False) -> BatchSolution:
+        dev = torch.device("cuda", self.device)
+        dof = self.dof_
+        f = lambda *s: torch.empty(*s, dtype=torch.float64, device=dev)
+        b = lambda *s: torch.empty(*s, dtype=torch.uint8, device=dev)
+        i = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
+        return BatchSolution(n, dof, f(7, dof, n), f(dof, n), f(dof, n), b(dof, n), i(n), i(n), b(n),
+                             f(7, dof, n) if with_opt else None,
+                             b(dof, n) if with_cases else None, b(dof, n) if with_cases else None,
+                             b(dof, n) if with_cases else None)
+
+    def solve(self, q_goal, q_0, v_0, a_0, out: Optional[BatchSolution] = None, with_opt=False,
+              with_cases=False) -> BatchSolution:
+        """stages 1-3 for n problems; inputs [dof, n] float64 CUDA tensors."""
+        n = q_goal.shape[1]
+        ins = [self._chk(t, n, nm) for t, nm in zip((q_goal, q_0, v_0, a_0), ("q_goal", "q_0", "v_0", "a_0"))]
+        sol = out if out is not None else self.alloc_solution(n, with_opt, with_cases)
+        cs = sol.c_struct()
+        capi.check(capi.solve_batch(self._h, n, *[t.data_ptr() for t in ins], C.byref(cs), self._stream()),
+                   "ltp_solve_batch")
+        return sol
+
+    def alloc_trajectories(self, n: int, samples: int) -> BatchTrajectories:
+        dev = torch.device("cuda", self.device)
+        stride = (samples + 3) // 4 * 4
+        rows = [torch.empty(n, self.dof_, stride, dtype=torch.float64, device=dev) for _ in range(4)]
+        return BatchTrajectories(0, stride, *rows, torch.empty(n, dtype=torch.uint8, device=dev), None)
+
+    def sample(self, q_0, v_0, a_0, sol: BatchSolution, horizon: int = 0,
+               out: Optional[BatchTrajectories] = None) -> BatchTrajectories:
+        """stage 4. horizon = 0: exact length per problem (synchronises once to size the rows
+        unless `out` is given); horizon > 0: fixed number of samples per row."""
+        n = sol.n
+        ins = [self._chk(t, n, nm) for t, nm in zip((q_0, v_0, a_0), ("q_0", "v_0", "a_0"))]
+        if out is None:
+            samples = horizon if horizon > 0 else max(int(sol.traj_len.max().item()), 1)
+            out = self.alloc_trajectories(n, samples)
+        out.horizon = horizon
+        out.traj_len = sol.traj_len
+        cs = sol.c_struct()
+        capi.check(capi.sample_batch(self._h, n, *[t.data_ptr() for t in ins], C.byref(cs), horizon, out.stride,
+                                     out.q.data_ptr(), out.v.data_ptr(), out.a.data_ptr(), out.j.data_ptr(),
+                                     out.success.data_ptr(), self._stream()), "ltp_sample_batch")
+        return out
+
+    def planTrajectories(self, q_goal, q_0, v_0, a_0, horizon: int = 0):
+        """Batched planTrajectory: -> (BatchSolution, BatchTrajectories)."""
+        sol = self.solve(q_goal, q_0, v_0, a_0)
+        return sol, self.sample(q_0, v_0, a_0, sol, horizon)
+
+    # per-joint primitives, batched
+    def optBrakingBatch(self, v_0, a_0):
+        n = v_0.shape[1]
+        self._chk(v_0, n, "v_0"), self._chk(a_0, n, "a_0")
+        q, d = torch.empty_like(v_0), torch.empty_like(v_0)
+        t_rel = torch.empty(3, self.dof_, n, dtype=torch.float64, device=v_0.device)
+        capi.check(capi.opt_braking_batch(self._h, n, v_0.data_ptr(), a_0.data_ptr(), q.data_ptr(),
+                                          t_rel.data_ptr(), d.data_ptr(), self._stream()))
+        return dict(q=q, t_rel=t_rel, dir=d)
+
+    def optSwitchTimesBatch(self, q_goal, q_0, v_0, a_0, v_drive):
+        n = q_goal.shape[1]
+        ins = [self._chk(t, n, "input") for t in (q_goal, q_0, v_0, a_0, v_drive)]
+        dev = q_goal.device
+        t = torch.zeros(7, self.dof_, n, dtype=torch.float64, device=dev)
+        d = torch.empty_like(q_goal)
+        mod, kase, ok = (torch.empty(self.dof_, n, dtype=torch.uint8, device=dev) for _ in range(3))
+        capi.check(capi.opt_switch_times_batch(self._h, n, *[x.data_ptr() for x in ins], t.data_ptr(),
+                                               d.data_ptr(), mod.data_ptr(), kase.data_ptr(), ok.data_ptr(),
+                                               self._stream()))
+        return dict(t=t, dir=d, mod=mod, case=kase, ok=ok)
+
+    def timeScalingBatch(self, q_goal, q_0, v_0, a_0, dir, t_required):
+        n = q_goal.shape[1]
+        ins = [self._chk(t, n, "input") for t in (q_goal, q_0, v_0, a_0, dir, t_required)]
+        dev = q_goal.device
+        t = torch.zeros(7, self.dof_, n, dtype=torch.float64, device=dev)
+        vd = torch.empty_like(q_goal)
+        mod, tsc, fc, ok = (torch.empty(self.dof_, n, dtype=torch.uint8, device=dev) for _ in range(4))
+        capi.check(capi.time_scaling_batch(self._h, n, *[x.data_ptr() for x in ins], t.data_ptr(), vd.data_ptr(),
+                                           mod.data_ptr(), tsc.data_ptr(), fc.data_ptr(), ok.data_ptr(),
+                                           self._stream()))
+        return dict(t=t, v_drive=vd, mod=mod, ts_case=tsc, final_case=fc, ok=ok)
+
+    # host-buffer forms (numpy, joint-major [dof, n]); copies are inside the call
+    def solve_host(self, q_goal, q_0, v_0, a_0, out: Optional[dict] = None, with_opt=False,
+                   with_cases=False) -> dict:
+        dof = self.dof_
+        ins = [np.ascontiguousarray(x, dtype=np.float64) for x in (q_goal, q_0, v_0, a_0)]
+        n = ins[0].shape[1]
+        if out is None:
+            out = dict(t_scaled=np.empty((7, dof, n)), dir=np.empty((dof, n)), v_drive=np.empty((dof, n)),
+                       mod=np.empty((dof, n), np.uint8), slowest=np.empty(n, np.int32),
+                       traj_len=np.empty(n, np.int32), reached=np.empty(n, np.uint8),
+                       t_opt=np.empty((7, dof, n)) if with_opt else None,
+                       opt_case=np.empty((dof, n), np.uint8) if with_cases else None,
+                       ts_case=np.empty((dof, n), np.uint8) if with_cases else None,
+                       final_case=np.empty((dof, n), np.uint8) if with_cases else None)
+        cs = capi.Solution(*[_np_ptr(out.get(k)) for k in ("t_scaled", "dir", "v_drive", "mod", "slowest",
+                                                            "traj_len", "reached", "t_opt", "opt_case",
+                                                            "ts_case", "final_case")])
+        capi.check(capi.solve_host(self._h, n, *[_np_ptr(x) for x in ins], C.byref(cs)), "ltp_solve_host")
+        return out

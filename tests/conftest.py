@@ -1,0 +1,21 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _build_checkers():
+    """CPU checkers (oracle/) are test infrastructure; build them once per session."""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "all"], check=True,
+                   stdout=subprocess.DEVNULL)
+    yield

@@ -1,0 +1,170 @@
+// TEST ARTEFACT ONLY. Compiles the product's per-thread device math
+// (longtermplanner_b200/csrc/ltp_math.cuh) for the host so that its arithmetic can be
+// compared with the oracle in a container that has no GPU (tests/test_devmath_host.py).
+// The product library never links, loads or falls back to this: it exists because every
+// GPU run costs minutes, and a formula typo should be caught before spending them.
+// Build: g++ -O2 -ffp-contract=off (no FMA contraction; explicit fma() stays exact).
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../longtermplanner_b200/csrc/ltp_math.cuh"
+
+using namespace ltp;
+
+namespace {
+struct Shadow {
+  int dof;
+  double ts;
+  std::vector<JointLimits> lim;
+};
+}  // namespace
+
+extern "C" {
+
+void* shadow_create(int dof, double ts, const double* q_min, const double* q_max, const double* v_max,
+                    const double* a_max, const double* j_max) {
+  Shadow* s = new Shadow;
+  s->dof = dof;
+  s->ts = ts;
+  s->lim.resize(dof);
+  for (int i = 0; i < dof; ++i) s->lim[i] = JointLimits{q_min[i], q_max[i], v_max[i], a_max[i], j_max[i]};
+  return s;
+}
+void shadow_destroy(void* h) { delete static_cast<Shadow*>(h); }
+
+void shadow_opt_braking_items(void* h, int64_t n, const int* joint, const double* v_0, const double* a_0,
+                              double* q, double* t_rel3, double* dir) {
+  Shadow* s = static_cast<Shadow*>(h);
+  for (int64_t i = 0; i < n; ++i) {
+    const JointLimits& L = s->lim[joint ? joint[i] : 0];
+    q[i] = brake_profile(L.a_max, L.j_max, s->ts, v_0[i], a_0[i], t_rel3[3 * i], t_rel3[3 * i + 1],
+                         t_rel3[3 * i + 2], dir[i]);
+  }
+}
+
+void shadow_opt_switch_times_items(void* h, int64_t n, const int* joint, const double* q_goal,
+                                   const double* q_0, const double* v_0, const double* a_0,
+                                   const double* v_drive, double* t7, double* dir, unsigned char* mod,
+                                   unsigned char* kase, unsigned char* ok, int) {
+  Shadow* s = static_cast<Shadow*>(h);
+  for (int64_t i = 0; i < n; ++i) {
+    const JointLimits& L = s->lim[joint ? joint[i] : 0];
+    Prologue P = ost_prologue(L, s->ts, q_goal[i], q_0[i], v_0[i], a_0[i]);
+    double t[7];
+    zero7(t);
+    unsigned char m = 0, c = 255;
+    ok[i] = ost_body(L, s->ts, P, q_goal[i], q_0[i], v_drive[i], t, m, c);
+    std::memcpy(t7 + 7 * i, t, 56);
+    dir[i] = P.dir;
+    mod[i] = m;
+    kase[i] = c;
+  }
+}
+
+void shadow_time_scaling_items(void* h, int64_t n, const int* joint, const double* q_goal,
+                               const double* q_0, const double* v_0, const double* a_0, const double* dir,
+                               const double* t_required, double* t7, double* v_drive, unsigned char* mod,
+                               unsigned char* ts_case, unsigned char* final_case, unsigned char* ok, int) {
+  Shadow* s = static_cast<Shadow*>(h);
+  for (int64_t i = 0; i < n; ++i) {
+    const JointLimits& L = s->lim[joint ? joint[i] : 0];
+    TsInput I = make_ts_input(q_goal[i], q_0[i], v_0[i], a_0[i], dir[i], t_required[i]);
+    Prologue P = ost_prologue(L, s->ts, q_goal[i], q_0[i], dir[i] * I.v_0, dir[i] * I.a_0);
+    double t[7];
+    zero7(t);
+    unsigned char m = 0, fc = 255;
+    int c = time_scaling_from(1, L, s->ts, P, I, t, v_drive[i], m, fc);
+    std::memcpy(t7 + 7 * i, t, 56);
+    mod[i] = m;
+    ts_case[i] = (unsigned char)c;
+    final_case[i] = fc;
+    ok[i] = c != 9;
+  }
+}
+
+// same sequence of device-function calls as ltp_solve_kernel, problem-major arrays
+void shadow_solve_batch(void* h, int64_t n, const double* q_goal, const double* q_0, const double* v_0,
+                        const double* a_0, double* t_opt, double* t_scaled, double* dir, double* v_drive,
+                        unsigned char* mod, unsigned char* opt_case, unsigned char* ts_case,
+                        unsigned char* final_case, int* slowest, int* traj_len, unsigned char* reached, int) {
+  Shadow* s = static_cast<Shadow*>(h);
+  const int dof = s->dof;
+  std::vector<Prologue> pro(dof);
+  for (int64_t p = 0; p < n; ++p) {
+    const int64_t o = p * dof;
+    bool any_fail = false;
+    for (int j = 0; j < dof; ++j) {
+      const JointLimits& L = s->lim[j];
+      bool in_ok = check_joint_input(L, q_0[o + j], v_0[o + j], a_0[o + j]);
+      pro[j] = ost_prologue(L, s->ts, q_goal[o + j], q_0[o + j], v_0[o + j], a_0[o + j]);
+      double* t = t_opt + 7 * (o + j);
+      zero7(t);
+      mod[o + j] = 0;
+      opt_case[o + j] = 255;
+      bool ok = ost_body(L, s->ts, pro[j], q_goal[o + j], q_0[o + j], L.v_max, t, mod[o + j], opt_case[o + j]);
+      any_fail |= !(in_ok && ok);
+      dir[o + j] = pro[j].dir;
+    }
+    double t_req = -1;
+    int sl = -1;
+    for (int j = 0; j < dof; ++j)
+      if (t_opt[7 * (o + j) + 6] > t_req) { t_req = t_opt[7 * (o + j) + 6]; sl = j; }
+    const bool rch = !any_fail && sl != -1;
+    int len = 0;
+    bool bad = false;
+    for (int j = 0; j < dof; ++j) {
+      const JointLimits& L = s->lim[j];
+      double* t = t_scaled + 7 * (o + j);
+      zero7(t);
+      v_drive[o + j] = L.v_max;
+      ts_case[o + j] = 255;
+      final_case[o + j] = 255;
+      if (rch) {
+        if (j == sl) {
+          ts_case[o + j] = 0;
+          final_case[o + j] = opt_case[o + j];
+        } else {
+          TsInput I = make_ts_input(q_goal[o + j], q_0[o + j], v_0[o + j], a_0[o + j], pro[j].dir, t_req);
+          ts_case[o + j] = (unsigned char)time_scaling_from(1, L, s->ts, pro[j], I, t, v_drive[o + j],
+                                                            mod[o + j], final_case[o + j]);
+          if (ts_case[o + j] == 9) final_case[o + j] = opt_case[o + j];
+        }
+        double m = t[0];
+        for (int k = 1; k < 7; ++k)
+          if (m < t[k]) m = t[k];
+        if (m <= 0.0) std::memcpy(t, t_opt + 7 * (o + j), 56);
+        bool fin = true;
+        for (int k = 0; k < 7; ++k) fin &= (bool)std::isfinite(t[k]);
+        int li = (fin && t[6] / s->ts <= 2.0e9) ? samples_for(t[6], s->ts) : -1;
+        bad |= li < 0;
+        len = li > len ? li : len;
+      }
+    }
+    slowest[p] = sl;
+    traj_len[p] = (rch && !bad) ? len : 0;
+    reached[p] = rch;
+  }
+}
+
+int shadow_get_trajectory(void* h, const double* t7, const double* dir, const unsigned char* mod,
+                          const double* q_0, const double* v_0, const double* a_0, const double* v_drive,
+                          int64_t stride, double* q, double* v, double* a, double* j) {
+  Shadow* s = static_cast<Shadow*>(h);
+  const int dof = s->dof;
+  int len = 0;
+  for (int i = 0; i < dof; ++i) {
+    int li = samples_for(t7[7 * i + 6], s->ts);
+    len = li > len ? li : len;
+  }
+  if (len > stride) return -len;
+  for (int jt = 0; jt < dof; ++jt) {
+    RowSampler R;
+    R.init(s->ts, s->lim[jt].j_max, t7 + 7 * jt, dir[jt], mod[jt], q_0[jt], v_0[jt], a_0[jt], v_drive[jt], len);
+    for (int i = 0; i < len; ++i)
+      R.step(i, j[jt * stride + i], a[jt * stride + i], v[jt * stride + i], q[jt * stride + i]);
+  }
+  return len;
+}
+
+}  // extern "C"

@@ -1,0 +1,207 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on
+the same seeded inputs. Exact: reached/success, case ids, slowest joint, trajectory
+length, dir, mod. Numeric: 1e-9 rel / 1e-12 abs on times, v_drive and samples."""
+import numpy as np
+import pytest
+
+from helpers import bitdiff, close, count_bad, jm, pm
+from longtermplanner_b200 import workloads as W
+from oracle.bindings import OraclePort, Reference
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _planner(lim):
+    from longtermplanner_b200 import LongTermPlanner
+    return LongTermPlanner(lim.dof, lim.t_sample, *lim.arrays(), device=0)
+
+
+def _dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _solve_both(lim, n, seed):
+    qg, q0, v0, a0 = W.random_states(lim, n, seed)
+    ltp = _planner(lim)
+    ins = [_dev(jm(x)) for x in (qg, q0, v0, a0)]
+    sol = ltp.solve(*ins, with_opt=True, with_cases=True)
+    torch.cuda.synchronize()
+    ref = OraclePort.from_limits(lim).solve(qg, q0, v0, a0, threads=8)
+    return ltp, ins, sol, ref, (qg, q0, v0, a0)
+
+
+@pytest.mark.parametrize("lim,n,seed", [(W.FRANKA7, 100_000, W.SEEDS[2]), (W.FRANKA12, 30_000, W.SEEDS[5]),
+                                        (W.REF_RANDOM6, 60_000, 7), (W.FRANKA7, 1, 3), (W.FRANKA7, 33, 4)])
+def test_solve_matches_oracle(lim, n, seed):
+    ltp, ins, sol, ref, _ = _solve_both(lim, n, seed)
+    assert np.array_equal(sol.reached.cpu().numpy(), ref["reached"])
+    assert np.array_equal(sol.slowest.cpu().numpy(), ref["slowest"])
+    assert np.array_equal(sol.traj_len.cpu().numpy(), ref["traj_len"])
+    for k in ("mod", "opt_case", "ts_case", "final_case"):
+        assert np.array_equal(pm(getattr(sol, k).cpu().numpy()), ref[k]), k
+    assert np.array_equal(pm(sol.dir.cpu().numpy()), ref["dir"])
+    for k in ("t_opt", "t_scaled", "v_drive"):
+        got = pm(getattr(sol, k).cpu().numpy())
+        assert count_bad(got, ref[k]) == 0, (k, bitdiff(got, ref[k]))
+
+
+def test_solve_matches_reference_build():
+    """same, against the reference's own .cc (oracle/_ref), observable fields only"""
+    if not Reference.available():
+        pytest.skip("oracle/_ref/libltp_ref.so not present")
+    lim, n = W.REF_RANDOM6, 40_000
+    qg, q0, v0, a0 = W.random_states(lim, n, 99)
+    ltp = _planner(lim)
+    sol = ltp.solve(*[_dev(jm(x)) for x in (qg, q0, v0, a0)])
+    torch.cuda.synchronize()
+    ref = Reference.from_limits(lim).solve(qg, q0, v0, a0, threads=8)
+    assert np.array_equal(sol.reached.cpu().numpy(), ref["reached"])
+    assert np.array_equal(sol.slowest.cpu().numpy(), ref["slowest"])
+    assert np.array_equal(pm(sol.mod.cpu().numpy()), ref["mod"])
+    assert count_bad(pm(sol.t_scaled.cpu().numpy()), ref["t_scaled"]) == 0
+    assert count_bad(pm(sol.v_drive.cpu().numpy()), ref["v_drive"]) == 0
+
+
+@pytest.mark.parametrize("lim,n,seed", [(W.FRANKA7, 96, W.SEEDS[1]), (W.REF_RANDOM6, 300, 11), (W.FRANKA12, 40, 5)])
+def test_sampled_trajectories_match_oracle(lim, n, seed):
+    ltp, ins, sol, ref, (qg, q0, v0, a0) = _solve_both(lim, n, seed)
+    traj = ltp.sample(ins[1], ins[2], ins[3], sol)
+    torch.cuda.synchronize()
+    P = OraclePort.from_limits(lim)
+    rows = {k: getattr(traj, k).cpu().numpy() for k in "qvaj"}
+    succ = traj.success.cpu().numpy()
+    tl = sol.traj_len.cpu().numpy()
+    bad = 0
+    for i in range(n):
+        full = P.plan(qg[i], q0[i], v0[i], a0[i])
+        assert full["length"] == tl[i]
+        assert bool(succ[i]) == full["success"]
+        for k in "qvaj":
+            bad += count_bad(rows[k][i, :, :tl[i]], full[k])
+    assert bad == 0
+
+
+def test_fixed_horizon_mode():
+    """horizon > traj_len continues with the recurrence's steady state (q_last, 0, 0, 0);
+    horizon < traj_len clips; the first min(horizon, traj_len) samples equal the exact mode"""
+    lim, n = W.FRANKA7, 64
+    ltp, ins, sol, ref, _ = _solve_both(lim, n, 21)
+    exact = ltp.sample(ins[1], ins[2], ins[3], sol)
+    tl = sol.traj_len.cpu().numpy()
+    for H in (int(tl.max()) + 37, int(tl.min()) // 2):
+        fixed = ltp.sample(ins[1], ins[2], ins[3], sol, horizon=H)
+        torch.cuda.synchronize()
+        assert np.array_equal(fixed.success.cpu().numpy(), exact.success.cpu().numpy())
+        for k in "qvaj":
+            e, f = getattr(exact, k).cpu().numpy(), getattr(fixed, k).cpu().numpy()
+            for i in range(n):
+                m = min(H, tl[i])
+                # sample index tl-1+1 may carry the late jerk impulse the exact mode drops
+                assert np.array_equal(e[i, :, :m], f[i, :, :m]), (k, i)
+                if H > tl[i] + 1:
+                    tail = f[i, :, tl[i] + 1:H]
+                    if k == "q":
+                        assert np.array_equal(tail, np.repeat(f[i, :, tl[i]:tl[i] + 1], tail.shape[1], axis=1))
+                    else:
+                        assert not tail.any()
+
+
+def test_per_joint_primitives_on_reference_grids():
+    """optSwitchTimes / timeScaling on the exact point sets of the reference's two grid
+    tests (tests/src/long_term_planner_tests.cc:264-407)"""
+    lim = W.REF_GRID
+    ltp = _planner(lim)
+    P = OraclePort.from_limits(lim)
+    for ts in (False, True):
+        qg, v0, a0 = W.reference_grid_points(ts)
+        q0 = np.full_like(qg, 0.5)
+        vd = np.full_like(qg, 1.0)
+        d = [_dev(x[None, :]) for x in (qg, q0, v0, a0, vd)]
+        got = ltp.optSwitchTimesBatch(*d)
+        torch.cuda.synchronize()
+        ref = P.opt_switch_times(qg, q0, v0, a0, vd)
+        assert np.array_equal(got["ok"].cpu().numpy()[0], ref["ok"])
+        assert np.array_equal(got["case"].cpu().numpy()[0], ref["case"])
+        assert np.array_equal(got["mod"].cpu().numpy()[0], ref["mod"])
+        assert np.array_equal(got["dir"].cpu().numpy()[0], ref["dir"])
+        assert count_bad(pm(got["t"].cpu().numpy())[:, 0, :], ref["t"]) == 0
+        if ts:
+            for inc in (0.05, 0.1, 0.2, 0.5, 1.0, 2.0):
+                tr = ref["t"][:, 6] + inc
+                g2 = ltp.timeScalingBatch(d[0], d[1], d[2], d[3], _dev(ref["dir"][None, :]), _dev(tr[None, :]))
+                torch.cuda.synchronize()
+                r2 = P.time_scaling(qg, q0, v0, a0, ref["dir"], tr, threads=8)
+                for k in ("ok", "mod", "ts_case", "final_case"):
+                    assert np.array_equal(g2[k].cpu().numpy()[0], r2[k]), (inc, k)
+                assert count_bad(pm(g2["t"].cpu().numpy())[:, 0, :], r2["t"]) == 0
+                assert count_bad(g2["v_drive"].cpu().numpy()[0], r2["v_drive"]) == 0
+
+
+def test_opt_braking_batch():
+    lim = W.REF_RANDOM6
+    rng = np.random.default_rng(5)
+    n = 5000
+    v0 = rng.uniform(-1, 1, (n, 6))
+    a0 = rng.uniform(-2, 2, (n, 6))
+    ltp = _planner(lim)
+    got = ltp.optBrakingBatch(_dev(jm(v0)), _dev(jm(a0)))
+    torch.cuda.synchronize()
+    P = OraclePort.from_limits(lim)
+    joint = np.tile(np.arange(6, dtype=np.int32), n)
+    ref = P.opt_braking(v0.ravel(), a0.ravel(), joint)
+    assert np.array_equal(pm(got["dir"].cpu().numpy()).ravel(), ref["dir"])
+    assert count_bad(pm(got["q"].cpu().numpy()).ravel(), ref["q"]) == 0
+    assert count_bad(pm(got["t_rel"].cpu().numpy()).reshape(-1, 3), ref["t_rel"]) == 0
+
+
+def test_single_plan_api_matches_oracle():
+    """LongTermPlanner.planTrajectory / protected methods, one problem at a time"""
+    from longtermplanner_b200 import Trajectory
+    lim = W.FRANKA7
+    ltp = _planner(lim)
+    P = OraclePort.from_limits(lim)
+    qg, q0, v0, a0 = W.random_states(lim, 5, 1234)
+    for i in range(5):
+        tr = Trajectory()
+        ok = ltp.planTrajectory(qg[i], q0[i], v0[i], a0[i], tr)
+        full = P.plan(qg[i], q0[i], v0[i], a0[i])
+        assert ok == full["success"] and tr.length == full["length"] and tr.dof == 7
+        for k in "qvaj":
+            assert count_bad(np.asarray(getattr(tr, k)), full[k]) == 0
+    # out-of-limits start state: early false, trajectory untouched (cc:14-15)
+    tr = Trajectory()
+    bad_q0 = q0[0].copy()
+    bad_q0[0] = 10.0
+    assert ltp.planTrajectory(qg[0], bad_q0, v0[0], a0[0], tr) is False and tr.length == 0
+    assert ltp.checkInputs(bad_q0, v0[0], a0[0]) is False
+
+
+def test_host_entry_point_equals_device_entry_point():
+    lim, n = W.FRANKA7, 5000
+    qg, q0, v0, a0 = W.random_states(lim, n, 77)
+    ltp = _planner(lim)
+    host = ltp.solve_host(*[jm(x) for x in (qg, q0, v0, a0)], with_opt=True, with_cases=True)
+    sol = ltp.solve(*[_dev(jm(x)) for x in (qg, q0, v0, a0)], with_opt=True, with_cases=True)
+    torch.cuda.synchronize()
+    for k in ("t_scaled", "dir", "v_drive", "mod", "slowest", "traj_len", "reached", "t_opt", "opt_case",
+              "ts_case", "final_case"):
+        a, b = host[k], getattr(sol, k).cpu().numpy()
+        assert np.array_equal(a, b, equal_nan=True) if a.dtype.kind == "f" else np.array_equal(a, b), k
+
+
+def test_rejected_inputs_and_empty_batch():
+    lim = W.FRANKA7
+    ltp = _planner(lim)
+    qg, q0, v0, a0 = W.random_states(lim, 64, 5)
+    q0[3, 2] = 99.0      # outside [q_min, q_max]
+    v0[7, 0] = 1e3       # outside v_max
+    sol = ltp.solve(*[_dev(jm(x)) for x in (qg, q0, v0, a0)])
+    torch.cuda.synchronize()
+    reached = sol.reached.cpu().numpy()
+    ref = OraclePort.from_limits(lim).solve(qg, q0, v0, a0)
+    assert np.array_equal(reached, ref["reached"]) and reached[3] == 0 and reached[7] == 0
+    assert sol.traj_len.cpu().numpy()[3] == 0
+    empty = torch.empty(7, 0, dtype=torch.float64, device="cuda")
+    s0 = ltp.solve(empty, empty, empty, empty)
+    assert s0.n == 0
