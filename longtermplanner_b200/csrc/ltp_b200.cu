@@ -496,8 +496,9 @@ void ltp_destroy(ltp_planner* p) {
 
 int ltp_opt_braking_batch(ltp_planner* p, int64_t n, const double* v_0, const double* a_0,
                           double* q_stop, double* t_rel, double* dir, void* stream) {
-  if (!p || n < 0 || !v_0 || !a_0 || !q_stop || !t_rel || !dir || p->params.dof < 1) return LTP_ERR_ARG;
+  if (!p || n < 0 || p->params.dof < 1) return LTP_ERR_ARG;
   if (n == 0) return LTP_OK;
+  if (!v_0 || !a_0 || !q_stop || !t_rel || !dir) return LTP_ERR_ARG;
   DeviceGuard g(p->device);
   dim3 block(128), grid((unsigned)((n + 127) / 128), p->params.dof);
   ltp_opt_braking_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(p->params, -1, n, v_0, a_0, q_stop, t_rel, dir);
@@ -509,10 +510,9 @@ int ltp_opt_braking_batch(ltp_planner* p, int64_t n, const double* v_0, const do
 int ltp_opt_switch_times_batch(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
                                const double* v_0, const double* a_0, const double* v_drive, double* t,
                                double* dir, uint8_t* mod, uint8_t* kase, uint8_t* ok, void* stream) {
-  if (!p || n < 0 || !q_goal || !q_0 || !v_0 || !a_0 || !v_drive || !t || !dir || !mod || !ok ||
-      p->params.dof < 1)
-    return LTP_ERR_ARG;
+  if (!p || n < 0 || p->params.dof < 1) return LTP_ERR_ARG;
   if (n == 0) return LTP_OK;
+  if (!q_goal || !q_0 || !v_0 || !a_0 || !v_drive || !t || !dir || !mod || !ok) return LTP_ERR_ARG;
   DeviceGuard g(p->device);
   dim3 block(128), grid((unsigned)((n + 127) / 128), p->params.dof);
   ltp_opt_switch_times_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
@@ -526,10 +526,10 @@ int ltp_time_scaling_batch(ltp_planner* p, int64_t n, const double* q_goal, cons
                            const double* v_0, const double* a_0, const double* dir,
                            const double* t_required, double* t, double* v_drive, uint8_t* mod,
                            uint8_t* ts_case, uint8_t* final_case, uint8_t* ok, void* stream) {
-  if (!p || n < 0 || !q_goal || !q_0 || !v_0 || !a_0 || !dir || !t_required || !t || !v_drive ||
-      !mod || !ok || p->params.dof < 1)
-    return LTP_ERR_ARG;
+  if (!p || n < 0 || p->params.dof < 1) return LTP_ERR_ARG;
   if (n == 0) return LTP_OK;
+  if (!q_goal || !q_0 || !v_0 || !a_0 || !dir || !t_required || !t || !v_drive || !mod || !ok)
+    return LTP_ERR_ARG;
   DeviceGuard g(p->device);
   dim3 block(128), grid((unsigned)((n + 127) / 128), p->params.dof);
   ltp_time_scaling_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
@@ -541,11 +541,12 @@ int ltp_time_scaling_batch(ltp_planner* p, int64_t n, const double* q_goal, cons
 
 int ltp_solve_batch(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
                     const double* v_0, const double* a_0, const ltp_solution* sol, void* stream) {
-  if (!p || n < 0 || !q_goal || !q_0 || !v_0 || !a_0 || !sol || p->params.dof < 1) return LTP_ERR_ARG;
+  if (!p || n < 0 || p->params.dof < 1) return LTP_ERR_ARG;
+  if (n == 0) return LTP_OK;
+  if (!q_goal || !q_0 || !v_0 || !a_0 || !sol) return LTP_ERR_ARG;
   if (!sol->t_scaled || !sol->dir || !sol->v_drive || !sol->mod || !sol->slowest || !sol->traj_len ||
       !sol->reached)
     return LTP_ERR_ARG;
-  if (n == 0) return LTP_OK;
   DeviceGuard g(p->device);
   const int dof = p->params.dof;
   dim3 block(kTile, dof), grid((unsigned)((n + kTile - 1) / kTile));
@@ -567,12 +568,13 @@ int ltp_solve_batch(ltp_planner* p, int64_t n, const double* q_goal, const doubl
 int ltp_sample_batch(ltp_planner* p, int64_t n, const double* q_0, const double* v_0, const double* a_0,
                      const ltp_solution* sol, int32_t horizon, int64_t stride, double* q, double* v,
                      double* a, double* j, uint8_t* success, void* stream) {
-  if (!p || n < 0 || !q_0 || !v_0 || !a_0 || !sol || !q || !v || !a || !j || !success ||
-      p->params.dof < 1 || horizon < 0 || stride < 1 || (horizon > 0 && stride < horizon))
+  if (!p || n < 0 || p->params.dof < 1 || horizon < 0) return LTP_ERR_ARG;
+  if (n == 0) return LTP_OK;
+  if (!q_0 || !v_0 || !a_0 || !sol || !q || !v || !a || !j || !success || stride < 1 ||
+      (horizon > 0 && stride < horizon))
     return LTP_ERR_ARG;
   if (!sol->t_scaled || !sol->dir || !sol->v_drive || !sol->mod || !sol->traj_len || !sol->reached)
     return LTP_ERR_ARG;
-  if (n == 0) return LTP_OK;
   DeviceGuard g(p->device);
   const int dof = p->params.dof;
   dim3 block(kTile, dof), grid((unsigned)((n + kTile - 1) / kTile));

@@ -1,0 +1,78 @@
+"""CPU suite, part 2: the product's device math (csrc/ltp_math.cuh) compiled for the host
+by tests/host_shadow.cc, against the oracle. This catches formula/branch errors without a
+GPU; the real parity tests are the `-m gpu` ones, which call the CUDA kernels through the
+C ABI. The shadow library is a test artefact, never loaded by the product."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import bitdiff, count_bad
+from longtermplanner_b200 import workloads as W
+from oracle.bindings import OraclePort
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SHADOW = os.path.join(HERE, "_build", "libltp_shadow.so")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _shadow_lib():
+    os.makedirs(os.path.dirname(SHADOW), exist_ok=True)
+    src = os.path.join(HERE, "host_shadow.cc")
+    hdr = os.path.join(HERE, "..", "longtermplanner_b200", "csrc", "ltp_math.cuh")
+    if (not os.path.exists(SHADOW)) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(SHADOW):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", src, "-o", SHADOW],
+                       check=True)
+
+
+class Shadow(OraclePort):
+    prefix = "shadow_"
+    libname = os.path.join("..", "..", "tests", "_build", "libltp_shadow.so")
+
+
+@pytest.mark.parametrize("lim,n,seed", [(W.FRANKA7, 40_000, 201), (W.FRANKA12, 10_000, 202), (W.REF_RANDOM6, 40_000, 203)])
+def test_device_math_solve_matches_oracle(lim, n, seed):
+    qg, q0, v0, a0 = W.random_states(lim, n, seed)
+    ref = OraclePort.from_limits(lim).solve(qg, q0, v0, a0, threads=4)
+    got = Shadow.from_limits(lim).solve(qg, q0, v0, a0)
+    for k in ("dir", "mod", "opt_case", "ts_case", "final_case", "slowest", "traj_len", "reached"):
+        assert np.array_equal(got[k], ref[k]), k
+    for k in ("t_opt", "t_scaled", "v_drive"):
+        assert count_bad(got[k], ref[k]) == 0, k
+        # the only legitimate source of bit differences is glibc pow() vs the correctly
+        # rounded power: a handful per million values
+        assert bitdiff(got[k], ref[k]) < 1e-3 * ref[k].size, k
+
+
+def test_device_math_sampler_is_bit_exact():
+    for lim, n, seed in ((W.FRANKA7, 40, 211), (W.REF_RANDOM6, 300, 212)):
+        qg, q0, v0, a0 = W.random_states(lim, n, seed)
+        P, S = OraclePort.from_limits(lim), Shadow.from_limits(lim)
+        s = P.solve(qg, q0, v0, a0)
+        for i in range(n):
+            a = P.get_trajectory(s["t_scaled"][i], s["dir"][i], s["mod"][i], q0[i], v0[i], a0[i], s["v_drive"][i])
+            b = S.get_trajectory(s["t_scaled"][i], s["dir"][i], s["mod"][i], q0[i], v0[i], a0[i], s["v_drive"][i])
+            assert a["length"] == b["length"]
+            for k in "qvaj":
+                assert bitdiff(b[k], a[k]) == 0, (lim.name, i, k)
+
+
+def test_device_math_on_reference_time_scaling_grid():
+    lim = W.REF_GRID
+    P, S = OraclePort.from_limits(lim), Shadow.from_limits(lim)
+    qg, v0, a0 = W.reference_grid_points(True)
+    sel = np.arange(0, len(qg), 5)
+    qg, v0, a0 = qg[sel], v0[sel], a0[sel]
+    q0, vd = np.full_like(qg, 0.5), np.full_like(qg, 1.0)
+    a, b = P.opt_switch_times(qg, q0, v0, a0, vd, threads=4), S.opt_switch_times(qg, q0, v0, a0, vd)
+    for k in ("dir", "mod", "case", "ok"):
+        assert np.array_equal(a[k], b[k]), k
+    assert count_bad(b["t"], a["t"]) == 0
+    for inc in (0.05, 0.5, 2.0):
+        tr = a["t"][:, 6] + inc
+        x = P.time_scaling(qg, q0, v0, a0, a["dir"], tr, threads=4)
+        y = S.time_scaling(qg, q0, v0, a0, a["dir"], tr)
+        for k in ("mod", "ts_case", "final_case", "ok"):
+            assert np.array_equal(x[k], y[k]), (inc, k)
+        assert count_bad(y["t"], x["t"]) == 0 and count_bad(y["v_drive"], x["v_drive"]) == 0
