@@ -47,6 +47,19 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+PROBELIB = os.path.join(LIBDIR, "libltp_probe.so")
+
+
+def build_probe_library(force: bool = False) -> str:
+    """bench-only roofline probes (FP64 FMA rate, HBM streaming-store bandwidth)"""
+    os.makedirs(LIBDIR, exist_ok=True)
+    src = os.path.join(CSRC, "ltp_probe.cu")
+    if force or _stale(PROBELIB, [src]):
+        subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+                        "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared", src, "-o", PROBELIB], check=True)
+    return PROBELIB
+
+
 def build_host_library(force: bool = False) -> str:
     """g++ -> lib/liblong_term_planner.so: the C++ drop-in class over the C ABI."""
     os.makedirs(LIBDIR, exist_ok=True)
