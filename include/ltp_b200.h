@@ -57,6 +57,12 @@ int ltp_set_limits(ltp_planner* p, const double* q_min, const double* q_max, con
                    const double* a_max, const double* j_max);
 int ltp_set_sample_time(ltp_planner* p, double t_sample);
 int ltp_set_dof(ltp_planner* p, int dof);
+/* how ltp_solve_batch runs: AUTO = closed-form kernel for every problem + generic kernel for
+ * the problems that need a polynomial root solve (default); GENERIC = the generic kernel for
+ * every problem. Results are identical; the switch exists for validation and profiling. */
+#define LTP_SOLVE_AUTO 0
+#define LTP_SOLVE_GENERIC 1
+int ltp_set_solve_mode(ltp_planner* p, int mode);
 int ltp_get_dof(const ltp_planner* p);
 int ltp_get_device(const ltp_planner* p);
 void ltp_destroy(ltp_planner* p);

@@ -34,7 +34,7 @@ def _sig(name, restype, *argtypes):
 
 
 EXPORTS = [
-    "ltp_create", "ltp_set_limits", "ltp_set_sample_time", "ltp_set_dof", "ltp_get_dof", "ltp_get_device",
+    "ltp_create", "ltp_set_limits", "ltp_set_sample_time", "ltp_set_dof", "ltp_set_solve_mode", "ltp_get_dof", "ltp_get_device",
     "ltp_destroy", "ltp_status_string", "ltp_last_cuda_error", "ltp_launch_count",
     "ltp_opt_braking_batch", "ltp_opt_switch_times_batch", "ltp_time_scaling_batch", "ltp_solve_batch",
     "ltp_sample_batch", "ltp_solve_host", "ltp_plan_host", "ltp_opt_braking_host",
@@ -45,6 +45,7 @@ create = _sig("ltp_create", C.c_int, C.POINTER(vp), C.c_int, C.c_int, f64, vp, v
 set_limits = _sig("ltp_set_limits", C.c_int, vp, vp, vp, vp, vp, vp)
 set_sample_time = _sig("ltp_set_sample_time", C.c_int, vp, f64)
 set_dof = _sig("ltp_set_dof", C.c_int, vp, C.c_int)
+set_solve_mode = _sig("ltp_set_solve_mode", C.c_int, vp, C.c_int)
 get_dof = _sig("ltp_get_dof", C.c_int, vp)
 get_device = _sig("ltp_get_device", C.c_int, vp)
 destroy = _sig("ltp_destroy", None, vp)

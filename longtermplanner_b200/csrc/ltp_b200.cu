@@ -47,19 +47,107 @@ struct DeviceSolution {  // ltp_solution, by value
 constexpr int kTile = 32;  // problems per CTA
 
 // ------------------------------------------------------------------------------------
-// stages 1-3, generic form: every branch evaluated in-thread (reference cc:14-55)
+// Stages 1-3 (reference cc:14-55) run as two kernels on one stream:
+//
+//   ltp_solve_fast_kernel    every problem. Closed-form work only: the phase solve without
+//                            the quartic tail, the slowest-joint reduction, and attempts 1
+//                            and 2 of the time-scaling search (both closed form). A problem
+//                            in which any joint needs a polynomial root solve is appended to
+//                            a work list and left for the second kernel.
+//   ltp_solve_generic_kernel the work list (or, in generic-only mode, every problem): every
+//                            branch of the reference evaluated in-thread, including the
+//                            Francis-QR root finder. It overwrites whatever the fast kernel
+//                            stored for a deferred problem.
+//
+// Keeping the root solver out of the first kernel keeps its code small and its warps
+// converged; grouping the root-solve problems keeps the lanes of the second kernel busy.
+// The split changes no result: a deferred problem is recomputed from its inputs by exactly
+// the code that handles it in generic-only mode.
 // ------------------------------------------------------------------------------------
+struct SolveShared {
+  double* t6;            // [dof][32]
+  int* len;              // [dof][32]
+  unsigned char* flag;   // [dof][32]  bit0 fail, bit1 defer
+  int* arrived;          // [32]
+};
+
+__device__ __forceinline__ SolveShared carve_shared(unsigned char* raw, int dof) {
+  SolveShared s;
+  s.t6 = reinterpret_cast<double*>(raw);
+  s.len = reinterpret_cast<int*>(s.t6 + dof * kTile);
+  s.arrived = s.len + dof * kTile;
+  s.flag = reinterpret_cast<unsigned char*>(s.arrived + kTile);
+  return s;
+}
+
+static size_t solve_smem_bytes(int dof) {
+  return (size_t)dof * kTile * (sizeof(double) + sizeof(int) + 1) + kTile * sizeof(int);
+}
+
+// per-joint stores shared by both kernels
+__device__ __forceinline__ void store_joint(const DeviceSolution& S, int dof, int jt, int64_t n, int64_t p,
+                                            const double* t_sc, const double* t_opt, double dir,
+                                            double v_drive, unsigned char mod, unsigned char opt_case,
+                                            unsigned char ts_case, unsigned char final_case) {
+  const int64_t at = (int64_t)jt * n + p;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) S.t_scaled[((int64_t)k * dof + jt) * n + p] = t_sc[k];
+  S.dir[at] = dir;
+  S.v_drive[at] = v_drive;
+  S.mod[at] = mod;
+  if (S.t_opt) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) S.t_opt[((int64_t)k * dof + jt) * n + p] = t_opt[k];
+  }
+  if (S.opt_case) S.opt_case[at] = opt_case;
+  if (S.ts_case) S.ts_case[at] = ts_case;
+  if (S.final_case) S.final_case[at] = final_case;
+}
+
+// cc:718 for one joint, -1 when a switching time is not finite / not representable
+__device__ __forceinline__ int joint_samples(const double* t_sc, double Ts) {
+  bool fin = true;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) fin &= (bool)isfinite(t_sc[k]);
+  return (fin && t_sc[6] / Ts <= 2.0e9) ? samples_for(t_sc[6], Ts) : -1;
+}
+
+// The last of a problem's dof threads to get here reduces the per-joint lengths and writes
+// the per-problem outputs; no CTA-wide barrier, so a warp that is still busy with a slow
+// joint does not hold the others back. Returns true in that last thread if the problem
+// must be appended to the work list.
+__device__ __forceinline__ bool finish_problem(const SolveShared& sh, const DeviceSolution& S, int dof,
+                                               int lane, int jt, int64_t p, int my_len, bool my_defer,
+                                               bool reached, int slowest) {
+  sh.len[jt * kTile + lane] = my_len;
+  if (my_defer) sh.flag[jt * kTile + lane] |= 2;
+  __threadfence_block();
+  const int prev = atomicAdd(&sh.arrived[lane], 1);
+  if (prev != dof - 1) return false;
+  __threadfence_block();
+  int len = 0;
+  bool bad = false, defer = false;
+  for (int i = 0; i < dof; ++i) {
+    const int li = sh.len[i * kTile + lane];
+    bad |= li < 0;
+    len = li > len ? li : len;
+    defer |= (sh.flag[i * kTile + lane] & 2) != 0;
+  }
+  S.slowest[p] = slowest;
+  S.traj_len[p] = (reached && !bad) ? len : 0;
+  S.reached[p] = (uint8_t)reached;
+  return defer;
+}
+
 template <int MAXW>
 __global__ void __launch_bounds__(kTile * MAXW)
-ltp_solve_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_goal,
-                 const double* __restrict__ q_0, const double* __restrict__ v_0,
-                 const double* __restrict__ a_0, DeviceSolution S) {
+ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_goal,
+                      const double* __restrict__ q_0, const double* __restrict__ v_0,
+                      const double* __restrict__ a_0, DeviceSolution S, int* __restrict__ work_list,
+                      int* __restrict__ work_count) {
   extern __shared__ unsigned char smem_raw[];
   const int dof = P.dof;
-  double* s_t6 = reinterpret_cast<double*>(smem_raw);                  // [dof][32]
-  int* s_len = reinterpret_cast<int*>(s_t6 + dof * kTile);             // [dof][32]
-  unsigned char* s_fail = reinterpret_cast<unsigned char*>(s_len + dof * kTile);  // [dof][32]
-
+  const SolveShared sh = carve_shared(smem_raw, dof);
   const int lane = threadIdx.x, jt = threadIdx.y;
   const int64_t p = (int64_t)blockIdx.x * kTile + lane;
   const bool valid = p < n;
@@ -71,42 +159,48 @@ ltp_solve_kernel(const __grid_constant__ PlannerParams P, int64_t n, const doubl
   if (valid) {
     qg = q_goal[at]; q0 = q_0[at]; v0 = v_0[at]; a0 = a_0[at];
   }
+  if (jt == 0) sh.arrived[lane] = 0;
   // stage 1 (cc:14-30)
   const bool in_ok = check_joint_input(L, q0, v0, a0);
   const Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0);
   double t_opt[7];
   zero7(t_opt);
   unsigned char mod = 0, opt_case = 255;
-  const bool ost_ok = ost_body(L, Ts, pro, qg, q0, L.v_max, t_opt, mod, opt_case);
-  s_t6[jt * kTile + lane] = t_opt[6];
-  s_fail[jt * kTile + lane] = (unsigned char)(!(in_ok && ost_ok));
+  const int st1 = ost_body_t<false>(L, Ts, pro, qg, q0, L.v_max, t_opt, mod, opt_case);
+  sh.t6[jt * kTile + lane] = t_opt[6];
+  sh.flag[jt * kTile + lane] = (unsigned char)((!(in_ok && st1 != OST_FAIL) ? 1 : 0) | (st1 == OST_DEFER ? 2 : 0));
   __syncthreads();
   // stage 2 (cc:31-39): strict '>' so the lowest joint index wins ties, NaN never wins
   double t_req = -1;
   int slowest = -1;
-  bool any_fail = false;
+  unsigned char any = 0;
   for (int i = 0; i < dof; ++i) {
-    any_fail |= (s_fail[i * kTile + lane] != 0);
-    const double ti = s_t6[i * kTile + lane];
+    any |= sh.flag[i * kTile + lane];
+    const double ti = sh.t6[i * kTile + lane];
     if (ti > t_req) {
       t_req = ti;
       slowest = i;
     }
   }
-  const bool reached = !any_fail && slowest != -1;
-  // stage 3 (cc:42-55)
+  // a joint that needs the quartic tail has no t_opt yet: the whole problem is deferred
+  const bool defer1 = (any & 2) != 0;
+  const bool reached = !(any & 1) && slowest != -1;
+  // stage 3 (cc:42-55), closed-form attempts only
   double t_sc[7];
   zero7(t_sc);
   double v_drive = L.v_max;
   unsigned char ts_case = 255, final_case = 255;
-  if (reached) {
+  bool my_defer = false;
+  if (reached && !defer1) {
     if (jt == slowest) {
       ts_case = 0;
       final_case = opt_case;
     } else {
       const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
-      ts_case = (unsigned char)time_scaling_from(1, L, Ts, pro, I, t_sc, v_drive, mod, final_case);
-      if (ts_case == 9) final_case = opt_case;
+      const int c = time_scaling_closed_form(L, Ts, pro, I, t_sc, v_drive, mod, final_case);
+      my_defer = (c == 0);
+      ts_case = (unsigned char)c;
+      if (c == 9) final_case = opt_case;
     }
     double m = t_sc[0];
 #pragma unroll
@@ -117,41 +211,93 @@ ltp_solve_kernel(const __grid_constant__ PlannerParams P, int64_t n, const doubl
       for (int k = 0; k < 7; ++k) t_sc[k] = t_opt[k];
     }
   }
-  // trajectory length (cc:716-719)
-  int my_len = 0;
-  if (reached) {
-    bool fin = true;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) fin &= (bool)isfinite(t_sc[k]);
-    my_len = (fin && t_sc[6] / Ts <= 2.0e9) ? samples_for(t_sc[6], Ts) : -1;
-  }
-  s_len[jt * kTile + lane] = my_len;
-  __syncthreads();
+  const int my_len = (reached && !defer1 && !my_defer) ? joint_samples(t_sc, Ts) : 0;
   if (!valid) return;
-  if (jt == 0) {
-    int len = 0;
-    bool bad = false;
-    for (int i = 0; i < dof; ++i) {
-      const int li = s_len[i * kTile + lane];
-      bad |= li < 0;
-      len = li > len ? li : len;
+  if (finish_problem(sh, S, dof, lane, jt, p, my_len, my_defer, reached, slowest)) {
+    const int slot = atomicAdd(work_count, 1);
+    work_list[slot] = (int)p;
+  }
+  store_joint(S, dof, jt, n, p, t_sc, t_opt, pro.dir, v_drive, mod, opt_case, ts_case, final_case);
+}
+
+// every branch evaluated in-thread. work_list == nullptr: problem = tile index (generic-only
+// mode); otherwise tiles of 32 entries of the work list, grid-stride.
+template <int MAXW>
+__global__ void __launch_bounds__(kTile * MAXW)
+ltp_solve_generic_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_goal,
+                         const double* __restrict__ q_0, const double* __restrict__ v_0,
+                         const double* __restrict__ a_0, DeviceSolution S, const int* __restrict__ work_list,
+                         const int* __restrict__ work_count) {
+  extern __shared__ unsigned char smem_raw[];
+  const int dof = P.dof;
+  const SolveShared sh = carve_shared(smem_raw, dof);
+  const int lane = threadIdx.x, jt = threadIdx.y;
+  const JointLimits L = P.lim[jt];
+  const double Ts = P.ts;
+  const int64_t count = work_list ? (int64_t)*work_count : n;
+  for (int64_t tile = blockIdx.x; tile * kTile < count; tile += gridDim.x) {
+    const int64_t w = tile * kTile + lane;
+    const bool valid = w < count;
+    const int64_t p = valid ? (work_list ? (int64_t)work_list[w] : w) : 0;
+    const int64_t at = (int64_t)jt * n + p;
+    double qg = 0, q0 = 0, v0 = 0, a0 = 0;
+    if (valid) {
+      qg = q_goal[at]; q0 = q_0[at]; v0 = v_0[at]; a0 = a_0[at];
     }
-    S.slowest[p] = slowest;
-    S.traj_len[p] = (reached && !bad) ? len : 0;
-    S.reached[p] = (uint8_t)reached;
-  }
+    if (jt == 0) sh.arrived[lane] = 0;
+    // stage 1 (cc:14-30)
+    const bool in_ok = check_joint_input(L, q0, v0, a0);
+    const Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0);
+    double t_opt[7];
+    zero7(t_opt);
+    unsigned char mod = 0, opt_case = 255;
+    const bool ost_ok = ost_body(L, Ts, pro, qg, q0, L.v_max, t_opt, mod, opt_case);
+    sh.t6[jt * kTile + lane] = t_opt[6];
+    sh.flag[jt * kTile + lane] = (unsigned char)(!(in_ok && ost_ok));
+    __syncthreads();
+    // stage 2 (cc:31-39)
+    double t_req = -1;
+    int slowest = -1;
+    bool any_fail = false;
+    for (int i = 0; i < dof; ++i) {
+      any_fail |= (sh.flag[i * kTile + lane] & 1) != 0;
+      const double ti = sh.t6[i * kTile + lane];
+      if (ti > t_req) {
+        t_req = ti;
+        slowest = i;
+      }
+    }
+    const bool reached = !any_fail && slowest != -1;
+    // stage 3 (cc:42-55)
+    double t_sc[7];
+    zero7(t_sc);
+    double v_drive = L.v_max;
+    unsigned char ts_case = 255, final_case = 255;
+    if (reached) {
+      if (jt == slowest) {
+        ts_case = 0;
+        final_case = opt_case;
+      } else {
+        const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
+        ts_case = (unsigned char)time_scaling_from(1, L, Ts, pro, I, t_sc, v_drive, mod, final_case);
+        if (ts_case == 9) final_case = opt_case;
+      }
+      double m = t_sc[0];
 #pragma unroll
-  for (int k = 0; k < 7; ++k) S.t_scaled[((int64_t)k * dof + jt) * n + p] = t_sc[k];
-  S.dir[at] = pro.dir;
-  S.v_drive[at] = v_drive;
-  S.mod[at] = mod;
-  if (S.t_opt) {
+      for (int k = 1; k < 7; ++k)
+        if (m < t_sc[k]) m = t_sc[k];
+      if (m <= 0.0) {
 #pragma unroll
-    for (int k = 0; k < 7; ++k) S.t_opt[((int64_t)k * dof + jt) * n + p] = t_opt[k];
+        for (int k = 0; k < 7; ++k) t_sc[k] = t_opt[k];
+      }
+    }
+    const int my_len = reached ? joint_samples(t_sc, Ts) : 0;
+    if (valid) {
+      finish_problem(sh, S, dof, lane, jt, p, my_len, false, reached, slowest);
+      store_joint(S, dof, jt, n, p, t_sc, t_opt, pro.dir, v_drive, mod, opt_case, ts_case, final_case);
+    }
+    __syncthreads();  // shared arrays are reused by the next tile
   }
-  if (S.opt_case) S.opt_case[at] = opt_case;
-  if (S.ts_case) S.ts_case[at] = ts_case;
-  if (S.final_case) S.final_case[at] = final_case;
 }
 
 // ------------------------------------------------------------------------------------
@@ -237,41 +383,49 @@ __global__ void ltp_time_scaling_kernel(const __grid_constant__ PlannerParams P,
 
 // ------------------------------------------------------------------------------------
 // stage 4: dense q/v/a/j sampling (reference cc:706-841) + final limit check (cc:59-61)
-// One thread per (problem, joint) row runs the reference's sequential recurrence and
-// emits four samples per field at a time as 32-byte sector-aligned vector stores.
+//
+// One thread per (problem, joint) row runs the reference's sequential recurrence (it is what
+// defines the result: a closed form would differ in the last bits) and streams the row out
+// four samples per field at a time: one 256-bit, sector-aligned, evict-first store per field
+// (STG.E.EF.256), so every 32-byte sector is written exactly once and completely. The
+// arithmetic is ~5 FP64 operations per 32 output bytes; the kernel is bound by HBM writes.
+// A CTA is one warp: floor(32/dof) whole problems, joint index fastest, so the final
+// per-problem limit check is a warp vote and the grid (n*dof/28 CTAs for 7 joints) spreads
+// evenly over the SMs even for a few thousand problems.
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ void store4(double* dst, double x0, double x1, double x2, double x3) {
-  // streaming (evict-first) stores: the trajectory is never re-read by this kernel
-  asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(x0), "d"(x1) : "memory");
-  asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(dst + 2), "d"(x2), "d"(x3) : "memory");
+  asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(x0), "d"(x1), "d"(x2), "d"(x3)
+               : "memory");
 }
 
-template <bool VEC, int MAXW>
-__global__ void __launch_bounds__(kTile * MAXW)
-ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_0,
+template <bool VEC>
+__global__ void __launch_bounds__(32)
+ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, int ppb, const double* __restrict__ q_0,
                   const double* __restrict__ v_0, const double* __restrict__ a_0, DeviceSolution S,
                   int horizon, int64_t stride, double* __restrict__ q, double* __restrict__ v,
                   double* __restrict__ a, double* __restrict__ j, uint8_t* success) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* s_ok = smem_raw;  // [dof][32]
   const int dof = P.dof;
-  const int lane = threadIdx.x, jt = threadIdx.y;
-  const int64_t p = (int64_t)blockIdx.x * kTile + lane;
-  const bool valid = p < n;
-  const JointLimits L = P.lim[jt];
+  const int lane = threadIdx.x;
+  const int slot = lane / dof, jt = lane - slot * dof;   // problem slot within the CTA, joint
+  const int64_t p = (int64_t)blockIdx.x * ppb + slot;
+  const bool valid = slot < ppb && p < n;
   bool row_ok = false;
   if (valid && S.reached[p]) {
     const int len = S.traj_len[p];
     if (len > 0) {
+      const JointLimits L = P.lim[jt];
       const int64_t at = (int64_t)jt * n + p;
       double t[7];
 #pragma unroll
       for (int k = 0; k < 7; ++k) t[k] = S.t_scaled[((int64_t)k * dof + jt) * n + p];
-      const int n_out = horizon > 0 ? horizon : len;      // samples stored
-      const int n_run = n_out > len ? n_out : len;        // samples computed
+      const int n_out = horizon > 0 ? horizon : len;  // samples stored
+      const int n_run = n_out > len ? n_out : len;    // samples computed
       RowSampler R;
-      R.init(P.ts, L.j_max, t, S.dir[at], S.mod[at], q_0[at], v_0[at], a_0[at], S.v_drive[at],
-             horizon > 0 ? n_run : len);
+      R.init(P.ts, L.j_max, t, S.dir[at], S.mod[at], q_0[at], v_0[at], a_0[at], S.v_drive[at], n_run);
+      SegTable T;
+      T.build(R, n_run);
+      SegCursor C;
+      C.enter(T, R, 0);
       const int64_t base = (p * dof + jt) * stride;
       double* qo = q + base; double* vo = v + base; double* ao = a + base; double* jo = j + base;
       double q_last = 0.0;
@@ -281,10 +435,9 @@ ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, const doub
         for (; i < n_vec; i += 4) {
           double jj[4], aa[4], vv[4], qq[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            R.step(i + u, jj[u], aa[u], vv[u], qq[u]);
-            if (i + u == len - 1) q_last = qq[u];
-          }
+          for (int u = 0; u < 4; ++u) C.step(T, R, i + u, jj[u], aa[u], vv[u], qq[u]);
+          const unsigned k = (unsigned)(len - 1 - i);
+          if (k < 4u) q_last = k == 0 ? qq[0] : k == 1 ? qq[1] : k == 2 ? qq[2] : qq[3];
           store4(qo + i, qq[0], qq[1], qq[2], qq[3]);
           store4(vo + i, vv[0], vv[1], vv[2], vv[3]);
           store4(ao + i, aa[0], aa[1], aa[2], aa[3]);
@@ -293,7 +446,7 @@ ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, const doub
       }
       for (; i < n_run; ++i) {
         double jj, aa, vv, qq;
-        R.step(i, jj, aa, vv, qq);
+        C.step(T, R, i, jj, aa, vv, qq);
         if (i == len - 1) q_last = qq;
         if (i < n_out) {
           qo[i] = qq; vo[i] = vv; ao[i] = aa; jo[i] = jj;
@@ -302,12 +455,11 @@ ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, const doub
       row_ok = !(q_last < L.q_min || q_last > L.q_max);  // cc:60
     }
   }
-  s_ok[jt * kTile + lane] = (unsigned char)row_ok;
-  __syncthreads();
+  // all joints of a problem sit in adjacent lanes of this warp
+  const unsigned ok_mask = __ballot_sync(0xffffffffu, row_ok);
   if (valid && jt == 0) {
-    bool ok = true;
-    for (int i = 0; i < dof; ++i) ok &= (s_ok[i * kTile + lane] != 0);
-    success[p] = (uint8_t)ok;
+    const unsigned want = ((dof >= 32) ? 0xffffffffu : ((1u << dof) - 1u)) << (slot * dof);
+    success[p] = (uint8_t)((ok_mask & want) == want);
   }
 }
 
@@ -326,6 +478,11 @@ struct ltp_planner {
   void* d_scratch;
   size_t d_scratch_bytes;
   cudaStream_t stream;  // internal stream of the host entry points
+  // work list of the two-kernel solve: [0] = count, [1..] = problem indices
+  int* d_work;
+  int64_t d_work_capacity;
+  int solve_mode;  // LTP_SOLVE_AUTO / LTP_SOLVE_GENERIC
+  int sm_count;
 };
 
 namespace {
@@ -447,6 +604,10 @@ int ltp_create(ltp_planner** out, int device, int dof, double t_sample, const do
   p->d_scratch = nullptr;
   p->d_scratch_bytes = 0;
   p->stream = nullptr;
+  p->d_work = nullptr;
+  p->d_work_capacity = 0;
+  p->solve_mode = LTP_SOLVE_AUTO;
+  p->sm_count = 148;
   std::memset(p->params.lim, 0, sizeof p->params.lim);
   if (dof > 0) {
     int rc = fill_limits(p->params, q_min, q_max, v_max, a_max, j_max);
@@ -457,6 +618,7 @@ int ltp_create(ltp_planner** out, int device, int dof, double t_sample, const do
     if (!g.ok) { delete p; return cuda_fail(cudaGetLastError(), "cudaSetDevice"); }
     cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaStreamCreate"); }
+    cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
   }
   *out = p;
   return LTP_OK;
@@ -480,6 +642,12 @@ int ltp_set_dof(ltp_planner* p, int dof) {
   return LTP_OK;
 }
 
+int ltp_set_solve_mode(ltp_planner* p, int mode) {
+  if (!p || (mode != LTP_SOLVE_AUTO && mode != LTP_SOLVE_GENERIC)) return LTP_ERR_ARG;
+  p->solve_mode = mode;
+  return LTP_OK;
+}
+
 int ltp_get_dof(const ltp_planner* p) { return p ? p->params.dof : LTP_ERR_ARG; }
 int ltp_get_device(const ltp_planner* p) { return p ? p->device : LTP_ERR_ARG; }
 int64_t ltp_launch_count(const ltp_planner* p) { return p ? p->launches.load() : 0; }
@@ -489,6 +657,7 @@ void ltp_destroy(ltp_planner* p) {
   {
     DeviceGuard g(p->device);
     if (p->d_scratch) cudaFree(p->d_scratch);
+    if (p->d_work) cudaFree(p->d_work);
     if (p->stream) cudaStreamDestroy(p->stream);
   }
   delete p;
@@ -547,20 +716,45 @@ int ltp_solve_batch(ltp_planner* p, int64_t n, const double* q_goal, const doubl
   if (!sol->t_scaled || !sol->dir || !sol->v_drive || !sol->mod || !sol->slowest || !sol->traj_len ||
       !sol->reached)
     return LTP_ERR_ARG;
+  if (n > 0x7fffffff) return LTP_ERR_ARG;  // problem indices travel as int32 in the work list
   DeviceGuard g(p->device);
   const int dof = p->params.dof;
-  dim3 block(kTile, dof), grid((unsigned)((n + kTile - 1) / kTile));
-  const size_t smem = (size_t)dof * kTile * (sizeof(double) + sizeof(int) + 1);
-#define LTP_LAUNCH_SOLVE(W) \
-  ltp_solve_kernel<W><<<grid, block, smem, (cudaStream_t)stream>>>(p->params, n, q_goal, q_0, v_0, a_0, to_dev(sol))
-  if (dof <= 1) LTP_LAUNCH_SOLVE(1);
-  else if (dof <= 2) LTP_LAUNCH_SOLVE(2);
-  else if (dof <= 4) LTP_LAUNCH_SOLVE(4);
-  else if (dof <= 8) LTP_LAUNCH_SOLVE(8);
-  else if (dof <= 16) LTP_LAUNCH_SOLVE(16);
-  else LTP_LAUNCH_SOLVE(32);
-#undef LTP_LAUNCH_SOLVE
-  p->launches++;
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 block(kTile, dof);
+  const unsigned tiles = (unsigned)((n + kTile - 1) / kTile);
+  const size_t smem = solve_smem_bytes(dof);
+  const DeviceSolution ds = to_dev(sol);
+#define LTP_DISPATCH_W(KERNEL, GRID, ...)                                                   \
+  do {                                                                                      \
+    if (dof <= 1) KERNEL<1><<<GRID, block, smem, st>>>(__VA_ARGS__);                        \
+    else if (dof <= 2) KERNEL<2><<<GRID, block, smem, st>>>(__VA_ARGS__);                   \
+    else if (dof <= 4) KERNEL<4><<<GRID, block, smem, st>>>(__VA_ARGS__);                   \
+    else if (dof <= 8) KERNEL<8><<<GRID, block, smem, st>>>(__VA_ARGS__);                   \
+    else if (dof <= 16) KERNEL<16><<<GRID, block, smem, st>>>(__VA_ARGS__);                 \
+    else KERNEL<32><<<GRID, block, smem, st>>>(__VA_ARGS__);                                \
+    p->launches++;                                                                          \
+  } while (0)
+  if (p->solve_mode == LTP_SOLVE_GENERIC) {
+    LTP_DISPATCH_W(ltp_solve_generic_kernel, tiles, p->params, n, q_goal, q_0, v_0, a_0, ds,
+                   (const int*)nullptr, (const int*)nullptr);
+  } else {
+    if (p->d_work_capacity < n) {
+      if (p->d_work) LTP_CUDA(cudaFree(p->d_work));
+      p->d_work = nullptr;
+      p->d_work_capacity = 0;
+      LTP_CUDA(cudaMalloc(&p->d_work, sizeof(int) * (size_t)(n + 1)));
+      p->d_work_capacity = n;
+    }
+    LTP_CUDA(cudaMemsetAsync(p->d_work, 0, sizeof(int), st));
+    LTP_DISPATCH_W(ltp_solve_fast_kernel, tiles, p->params, n, q_goal, q_0, v_0, a_0, ds, p->d_work + 1,
+                   p->d_work);
+    // the work list is drained by a fixed-size grid-stride launch: its length never leaves
+    // the device
+    const unsigned g2 = tiles < (unsigned)(p->sm_count * 4) ? tiles : (unsigned)(p->sm_count * 4);
+    LTP_DISPATCH_W(ltp_solve_generic_kernel, g2, p->params, n, q_goal, q_0, v_0, a_0, ds,
+                   (const int*)(p->d_work + 1), (const int*)p->d_work);
+  }
+#undef LTP_DISPATCH_W
   LTP_CUDA(cudaGetLastError());
   return LTP_OK;
 }
@@ -577,25 +771,15 @@ int ltp_sample_batch(ltp_planner* p, int64_t n, const double* q_0, const double*
     return LTP_ERR_ARG;
   DeviceGuard g(p->device);
   const int dof = p->params.dof;
-  dim3 block(kTile, dof), grid((unsigned)((n + kTile - 1) / kTile));
-  const size_t smem = (size_t)dof * kTile;
+  const int ppb = 32 / dof > 0 ? 32 / dof : 1;  // whole problems per one-warp CTA (dof <= 32)
+  const unsigned grid = (unsigned)((n + ppb - 1) / ppb);
   const bool vec = (stride % 4 == 0) && aligned32(q) && aligned32(v) && aligned32(a) && aligned32(j);
-#define LTP_LAUNCH_SAMPLE(V, W)                                                 \
-  ltp_sample_kernel<V, W><<<grid, block, smem, (cudaStream_t)stream>>>(          \
-      p->params, n, q_0, v_0, a_0, to_dev(sol), horizon, stride, q, v, a, j, success)
-#define LTP_LAUNCH_SAMPLE_W(V)             \
-  do {                                     \
-    if (dof <= 1) LTP_LAUNCH_SAMPLE(V, 1); \
-    else if (dof <= 2) LTP_LAUNCH_SAMPLE(V, 2); \
-    else if (dof <= 4) LTP_LAUNCH_SAMPLE(V, 4); \
-    else if (dof <= 8) LTP_LAUNCH_SAMPLE(V, 8); \
-    else if (dof <= 16) LTP_LAUNCH_SAMPLE(V, 16); \
-    else LTP_LAUNCH_SAMPLE(V, 32);         \
-  } while (0)
-  if (vec) LTP_LAUNCH_SAMPLE_W(true);
-  else LTP_LAUNCH_SAMPLE_W(false);
-#undef LTP_LAUNCH_SAMPLE_W
-#undef LTP_LAUNCH_SAMPLE
+  if (vec)
+    ltp_sample_kernel<true><<<grid, 32, 0, (cudaStream_t)stream>>>(p->params, n, ppb, q_0, v_0, a_0, to_dev(sol),
+                                                                    horizon, stride, q, v, a, j, success);
+  else
+    ltp_sample_kernel<false><<<grid, 32, 0, (cudaStream_t)stream>>>(p->params, n, ppb, q_0, v_0, a_0, to_dev(sol),
+                                                                     horizon, stride, q, v, a, j, success);
   p->launches++;
   LTP_CUDA(cudaGetLastError());
   return LTP_OK;

@@ -496,8 +496,14 @@ LTP_HD_NOINLINE unsigned char ost_quartic_tail(const JointLimits& L, const Prolo
 
 // Body of optSwitchTimes for cruise speed V. t receives the cumulative switching times;
 // on the cc:340-344 failure it is left untouched, exactly like the reference.
-LTP_HD bool ost_body(const JointLimits& L, double Ts, const Prologue& P, double q_goal, double q_0,
-                     double V, double* t, unsigned char& mod, unsigned char& kase) {
+// Returns OST_FAIL (reference returns false), OST_OK (true) or -- only when ALLOW_TAIL is
+// false -- OST_DEFER: the joint needs the quartic tail (cc:245-337), nothing was written,
+// and the caller must hand the problem to the generic kernel.
+enum { OST_FAIL = 0, OST_OK = 1, OST_DEFER = 2 };
+
+template <bool ALLOW_TAIL>
+LTP_HD int ost_body_t(const JointLimits& L, double Ts, const Prologue& P, double q_goal, double q_0,
+                      double V, double* t, unsigned char& mod, unsigned char& kase) {
   const double A = L.a_max, J = L.j_max;
   const double eps = kEps;
   double T[7];
@@ -507,7 +513,7 @@ LTP_HD bool ost_body(const JointLimits& L, double Ts, const Prologue& P, double 
     T[0] = P.b0; T[1] = P.b1; T[2] = P.b2; T[3] = 0; T[4] = 0; T[5] = 0; T[6] = 0;
     cumsum7(T, t);
     kase = CASE_BRAKE_ONLY;
-    return true;
+    return OST_OK;
   }
   const double v_0 = P.v0m, a_0 = P.a0m;
   double q_brake = 0.0;
@@ -530,7 +536,7 @@ LTP_HD bool ost_body(const JointLimits& L, double Ts, const Prologue& P, double 
       } else {
         zero7(t);
         kase = CASE_DEGENERATE | flags;
-        return true;
+        return OST_OK;
       }
     }
   }
@@ -548,7 +554,7 @@ LTP_HD bool ost_body(const JointLimits& L, double Ts, const Prologue& P, double 
     } else {
       zero7(t);
       kase = CASE_DEGENERATE | flags;
-      return true;
+      return OST_OK;
     }
   }
   // cc:168-190
@@ -573,7 +579,7 @@ LTP_HD bool ost_body(const JointLimits& L, double Ts, const Prologue& P, double 
     if (mod == 1) {   // cc:195-199
       zero7(t);
       kase = CASE_FAIL | flags;
-      return false;
+      return OST_FAIL;
     }
     // cc:202-223
     double rad = (sq(J) * pow4(T[0])) / 2 - (sq(J) * pow4(T[2])) / 4 +
@@ -597,23 +603,31 @@ LTP_HD bool ost_body(const JointLimits& L, double Ts, const Prologue& P, double 
     } else {
       zero7(t);
       kase = CASE_DEGENERATE | flags;
-      return true;
+      return OST_OK;
     }
-    if (T[5] < -eps || T[1] < -eps) base = ost_quartic_tail(L, P, q_goal, q_0, T, flags);
+    if (T[5] < -eps || T[1] < -eps) {
+      if (!ALLOW_TAIL) return OST_DEFER;
+      base = ost_quartic_tail(L, P, q_goal, q_0, T, flags);
+    }
   }
   // cc:340-348
 #pragma unroll
   for (int i = 0; i < 7; ++i) {
     if (T[i] < -eps) {
       kase = CASE_FAIL | flags;
-      return false;
+      return OST_FAIL;
     } else if (T[i] < 0.0 && T[i] >= -eps) {
       T[i] = 0.0;
     }
   }
   cumsum7(T, t);  // cc:351
   kase = base | flags;
-  return true;
+  return OST_OK;
+}
+
+LTP_HD bool ost_body(const JointLimits& L, double Ts, const Prologue& P, double q_goal, double q_0,
+                     double V, double* t, unsigned char& mod, unsigned char& kase) {
+  return ost_body_t<true>(L, Ts, P, q_goal, q_0, V, t, mod, kase) == OST_OK;
 }
 
 // ------------------------------------------------------------------------------------
@@ -756,10 +770,61 @@ LTP_HD bool ts_try(const JointLimits& L, double Ts, const Prologue& P, const TsI
 
 // cc:358-645 from attempt `first` on (1 = whole search). P must be the prologue of this
 // joint's start state. Returns the accepted attempt (1..8) or 9 after the cc:641-644 reset.
+// A joint on the BRAKE_ONLY exit gets the same switching times from every nested solve,
+// whatever the cruise speed (cc:102-107), so the acceptance test of cc:402 has the same
+// outcome in all eight attempts. True when that outcome is "rejected": the search ends in
+// the cc:641-644 state without evaluating a single candidate (the reference grinds through
+// six eigen-solves to get there).
+LTP_HD bool ts_brake_only_rejects(const Prologue& P, double tr) {
+  if (!P.brake_only) return false;
+  const double t6 = ((((((P.b0 + P.b1) + P.b2) + 0.0) + 0.0) + 0.0) + 0.0);
+  return !(tr - t6 < kTol && tr - t6 > -kTol / 10);
+}
+
+LTP_HD void ts_fail_state(const JointLimits& L, double* scaled_t, double& v_drive, unsigned char& mod,
+                          unsigned char& final_case) {
+  mod = 0;
+  zero7(scaled_t);
+  v_drive = L.v_max;
+  final_case = CASE_FAIL;
+}
+
+// Closed-form part of the search (attempts 1 and 2) for the fast kernel. Returns the accepted
+// attempt (1, 2), 9 when the outcome is already known to be failure, or 0 when the joint
+// needs the root-solver attempts 3..8 or a quartic tail inside a nested solve: the caller
+// then defers the whole problem to the generic kernel.
+LTP_HD int time_scaling_closed_form(const JointLimits& L, double Ts, const Prologue& P, const TsInput& I,
+                                    double* scaled_t, double& v_drive, unsigned char& mod,
+                                    unsigned char& final_case) {
+  if (ts_brake_only_rejects(P, I.tr)) {
+    ts_fail_state(L, scaled_t, v_drive, mod, final_case);
+    return 9;
+  }
+  double V = ts_candidate1(L, I);
+  v_drive = V;
+  if (!isnan(V) && V > 0) {
+    const int st = ost_body_t<false>(L, Ts, P, I.q_goal, I.q_0, V, scaled_t, mod, final_case);
+    if (st == OST_DEFER) return 0;
+    if (st == OST_OK && I.tr - scaled_t[6] < kTol && I.tr - scaled_t[6] > -kTol / 10) return 1;
+  }
+  V = ts_candidate2(L, I);
+  v_drive = V;
+  if (!isnan(V) && V > 0) {
+    const int st = ost_body_t<false>(L, Ts, P, I.q_goal, I.q_0, V, scaled_t, mod, final_case);
+    if (st == OST_DEFER) return 0;
+    if (st == OST_OK && I.tr - scaled_t[6] < kTol && I.tr - scaled_t[6] > -kTol / 10) return 2;
+  }
+  return 0;
+}
+
 LTP_HD int time_scaling_from(int first, const JointLimits& L, double Ts, const Prologue& P,
                              const TsInput& I, double* scaled_t, double& v_drive,
                              unsigned char& mod, unsigned char& final_case) {
   double V;
+  if (ts_brake_only_rejects(P, I.tr)) {
+    ts_fail_state(L, scaled_t, v_drive, mod, final_case);
+    return 9;
+  }
   if (first <= 1) {
     V = ts_candidate1(L, I);
     v_drive = V;
@@ -775,10 +840,7 @@ LTP_HD int time_scaling_from(int first, const JointLimits& L, double Ts, const P
     v_drive = V;
     if (ts_try(L, Ts, P, I, V, scaled_t, mod, final_case)) return k;
   }
-  mod = 0;
-  zero7(scaled_t);
-  v_drive = L.v_max;
-  final_case = CASE_FAIL;
+  ts_fail_state(L, scaled_t, v_drive, mod, final_case);
   return 9;
 }
 
@@ -814,26 +876,35 @@ LTP_HD int samples_for(double t6, double Ts) {
 }
 
 // ------------------------------------------------------------------------------------
-// cc:729-831 for one (problem, joint) row, as a streaming state machine: init() derives the
-// sample indices, the piecewise-constant jerk and the (up to 8) fractional impulses;
-// step(i) returns sample i of j/a/v/q. Sample 0 is t = Ts (cc:810-812).
-// Impulses whose index falls outside [0, limit) are dropped (the reference writes them
-// out of bounds).
+// cc:729-831 for one (problem, joint) row.
+//
+// The reference materialises a jerk array (piecewise-constant fills, cc:759-766, plus up to
+// eight fractional impulses, cc:768-807) and then runs the forward-Euler recurrence
+// (cc:810-831). Here the jerk array is never stored: RowSampler::init derives the sample
+// indices and the impulses, build_segments cuts the row at every index where the jerk or
+// the update rule can change (at most 26 pieces), and the hot loop advances the reference's
+// own recurrence inside a piece with five FP64 operations per sample:
+//     a += Ts*j;  v = cruise ? v_drive*dir : v + Ts*a;  q += Ts*v
+// (multiply and add stay unfused; Ts*j is the same product the reference forms per sample).
+// Sample 0 is t = Ts (cc:810-812). Impulses whose index falls outside [0, limit) are dropped
+// (the reference writes them out of bounds).
 // ------------------------------------------------------------------------------------
+constexpr int kMaxSeg = 27;
+
 struct RowSampler {
   double Ts, jp0, jp2, jp4, jp6;  // jerk of the four non-zero phases (phases 2, 4, 6 are 0)
   double vcruise;                 // v_drive * dir (cc:823)
   int s[7];
-  int imp_idx[8];
-  double imp_a[8], imp_b[8], imp_c[8];  // value added = ((j + a) + b) + c, source order
-  unsigned char imp_n[8];               // how many of a,b,c are used (0 = slot unused)
+  int imp_idx[7];                 // -1 = slot unused
+  double imp_v[7];                // value added at imp_idx (first addend)
+  double imp0b, imp4b, imp4c;     // further addends of the two combined impulses (cc:781, 798)
+  unsigned char n0, n4;           // number of addends of slots 0 and 4
   bool phase4;
   double a, v, q;
 
-  LTP_HD void add_imp(int slot, int idx, int limit, double x, double y, double z, int n) {
-    imp_idx[slot] = idx;
-    imp_a[slot] = x; imp_b[slot] = y; imp_c[slot] = z;
-    imp_n[slot] = (idx >= 0 && idx < limit) ? (unsigned char)n : (unsigned char)0;
+  LTP_HD void set_imp(int slot, int idx, int limit, double x) {
+    imp_idx[slot] = (idx >= 0 && idx < limit) ? idx : -1;
+    imp_v[slot] = x;
   }
 
   LTP_HD void init(double Ts_, double J, const double* t, double dir, unsigned char mod,
@@ -851,34 +922,39 @@ struct RowSampler {
     for (int k = 0; k < 7; ++k) {
       double r = t[k] / Ts;
       double fl = floor(r);
-      fr[k] = t[k] - Ts * fl;  // cc:747
+      fr[k] = t[k] - Ts * fl;               // cc:747
       double idx = (k & 1) ? ceil(r) : fl;  // cc:751-757
       // clamp before the cast: NaN / huge values are undefined in the reference
       if (!(idx >= -2.0e9)) idx = -2.0e9;
       if (idx > 2.0e9) idx = 2.0e9;
       s[k] = (int)idx;
     }
+    n0 = 1;
+    n4 = 1;
+    imp0b = imp4b = imp4c = 0.0;
     // cc:768-807, source order
     if (s[2] >= s[1]) {
-      add_imp(0, s[0] + 1, limit, fr[0] / Ts * jp0, 0, 0, 1);
-      add_imp(1, s[1], (s[1] > 0) ? limit : 0, (1 - fr[1] / Ts) * jp2, 0, 0, 1);
-      add_imp(2, s[2] + 1, limit, fr[2] / Ts * jp2, 0, 0, 1);
+      set_imp(0, s[0] + 1, limit, fr[0] / Ts * jp0);
+      set_imp(1, s[1], (s[1] > 0) ? limit : 0, (1 - fr[1] / Ts) * jp2);
+      set_imp(2, s[2] + 1, limit, fr[2] / Ts * jp2);
     } else {
-      add_imp(0, s[1], (s[1] > 0) ? limit : 0, fr[0] / Ts * jp0, (fr[2] - fr[0]) / Ts * jp2, 0, 2);
-      add_imp(1, -1, 0, 0, 0, 0, 0);
-      add_imp(2, -1, 0, 0, 0, 0, 0);
+      set_imp(0, s[1], (s[1] > 0) ? limit : 0, fr[0] / Ts * jp0);
+      imp0b = (fr[2] - fr[0]) / Ts * jp2;
+      n0 = 2;
+      set_imp(1, -1, 0, 0.0);
+      set_imp(2, -1, 0, 0.0);
     }
-    add_imp(3, s[3], (s[3] > 0) ? limit : 0, (1 - fr[3] / Ts) * jp4, 0, 0, 1);
+    set_imp(3, s[3], (s[3] > 0) ? limit : 0, (1 - fr[3] / Ts) * jp4);
     if (s[2] - s[0] > 0) {
-      add_imp(4, s[4] + 1, limit, fr[4] / Ts * jp4, 0, 0, 1);
+      set_imp(4, s[4] + 1, limit, fr[4] / Ts * jp4);
     } else {
-      add_imp(4, s[4], (s[4] > 0) ? limit : 0, fr[4] / Ts * jp4, fr[0] / Ts * jp0,
-              (fr[2] - fr[0]) / Ts * jp2, 3);
+      set_imp(4, s[4], (s[4] > 0) ? limit : 0, fr[4] / Ts * jp4);
+      imp4b = fr[0] / Ts * jp0;
+      imp4c = (fr[2] - fr[0]) / Ts * jp2;
+      n4 = 3;
     }
-    add_imp(5, s[5], (s[5] > 0) ? limit : 0, (1 - fr[5] / Ts) * jp6, 0, 0, 1);
-    add_imp(6, s[6] + 1, limit, fr[6] / Ts * jp6, 0, 0, 1);
-    imp_n[7] = 0;
-    imp_idx[7] = -1;
+    set_imp(5, s[5], (s[5] > 0) ? limit : 0, (1 - fr[5] / Ts) * jp6);
+    set_imp(6, s[6] + 1, limit, fr[6] / Ts * jp6);
     phase4 = s[3] - s[2] > 2;  // cc:813
     a = a_0; v = v_0; q = q_0;
   }
@@ -900,24 +976,111 @@ struct RowSampler {
     double j = base_jerk(i);
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
-      if (imp_n[k] != 0 && imp_idx[k] == i) {
-        j = j + imp_a[k];
-        if (imp_n[k] > 1) j = j + imp_b[k];
-        if (imp_n[k] > 2) j = j + imp_c[k];
+      if (imp_idx[k] == i) {
+        j = j + imp_v[k];
+        if (k == 0 && n0 > 1) j = j + imp0b;
+        if (k == 4 && n4 > 1) {
+          j = j + imp4b;
+          j = j + imp4c;
+        }
       }
     }
     return j;
   }
 
-  // cc:810-831
+  // update rules of cc:815-829 at sample i (sample 0 uses the plain formulas, cc:810-812)
+  LTP_HD bool a_zero(int i) const { return i > 0 && i > s[6]; }
+  LTP_HD bool v_cruise(int i) const { return i > 0 && phase4 && i >= s[2] + 1 && i < s[3] - 1; }
+
+  // smallest index > i at which the jerk or an update rule can change
+  LTP_HD int next_break(int i) const {
+    int best = 0x7fffffff;
+#define LTP_CAND(c)                        \
+  do {                                     \
+    const int c_ = (c);                    \
+    if (c_ > i && c_ < best) best = c_;    \
+  } while (0)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) LTP_CAND(s[k]);
+    LTP_CAND(1);
+    LTP_CAND(s[6] + 1);
+    LTP_CAND(s[2] + 1);
+    LTP_CAND(s[3] - 1);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      LTP_CAND(imp_idx[k]);
+      LTP_CAND(imp_idx[k] + 1);
+    }
+#undef LTP_CAND
+    return best;
+  }
+
+  // one sample by the general rules; used by the host shadow and as the definition the
+  // segment machinery below must reproduce
   LTP_HD void step(int i, double& jo, double& ao, double& vo, double& qo) {
     const double j = jerk_at(i);
-    if (i == 0 || i <= s[6]) a = a + Ts * j; else a = 0.0;
-    if (i > 0 && phase4 && i >= s[2] + 1 && i < s[3] - 1) v = vcruise;
-    else if (i == 0 || i <= s[6]) v = v + Ts * a;
+    if (!a_zero(i)) a = a + Ts * j; else a = 0.0;
+    if (v_cruise(i)) v = vcruise;
+    else if (!a_zero(i)) v = v + Ts * a;
     else v = 0.0;
     q = q + Ts * v;
     jo = j; ao = a; vo = v; qo = q;
+  }
+};
+
+// The row cut into pieces of constant jerk and constant update rule.
+struct SegTable {
+  int start[kMaxSeg + 1];   // start[m] .. start[m+1]-1; unused entries are INT_MAX
+  double tsj[kMaxSeg];      // Ts * jerk (0 where the acceleration is pinned to 0)
+  double jv[kMaxSeg];       // jerk value that is emitted
+  unsigned char fl[kMaxSeg];  // bit0: a = v = 0 from here on (cc:817-829), bit1: v = v_drive*dir
+
+  LTP_HD void build(const RowSampler& R, int limit) {
+    int cur = 0;
+#pragma unroll 1
+    for (int m = 0; m < kMaxSeg; ++m) {
+      start[m] = cur;
+      const int at = cur < limit ? cur : 0;  // entries past the end are never entered
+      const double j = R.jerk_at(at);
+      const bool az = R.a_zero(at);
+      jv[m] = j;
+      tsj[m] = az ? 0.0 : R.Ts * j;
+      fl[m] = (unsigned char)((az ? 1 : 0) | (R.v_cruise(at) ? 2 : 0));
+      if (cur < limit) {
+        cur = R.next_break(cur);
+        if (cur >= limit) cur = 0x7fffffff;
+      }
+    }
+    start[kMaxSeg] = 0x7fffffff;
+  }
+};
+
+struct SegCursor {
+  int m, next;
+  double tsj, jv;
+  bool vc;
+
+  LTP_HD void enter(const SegTable& T, RowSampler& R, int m_) {
+    m = m_;
+    tsj = T.tsj[m];
+    jv = T.jv[m];
+    const unsigned f = T.fl[m];
+    vc = (f & 2u) != 0;
+    if (f & 1u) {  // past the last switching time: a and v are exactly 0 from here on
+      R.a = 0.0;
+      R.v = 0.0;
+    }
+    next = T.start[m + 1];
+  }
+
+  // sample i (called with i = 0, 1, 2, ... in order)
+  LTP_HD void step(const SegTable& T, RowSampler& R, int i, double& jo, double& ao, double& vo, double& qo) {
+    if (i == next) enter(T, R, m + 1);
+    R.a = R.a + tsj;
+    const double vn = R.v + R.Ts * R.a;
+    R.v = vc ? R.vcruise : vn;
+    R.q = R.q + R.Ts * R.v;
+    jo = jv; ao = R.a; vo = R.v; qo = R.q;
   }
 };
 

@@ -116,6 +116,10 @@ class LongTermPlanner:
         capi.check(capi.set_dof(self._h, int(dof)), "ltp_set_dof")
         self.dof_ = int(dof)
 
+    def setSolveMode(self, generic_only: bool) -> None:
+        """validation switch: run every problem through the generic kernel (same results)"""
+        capi.check(capi.set_solve_mode(self._h, 1 if generic_only else 0), "ltp_set_solve_mode")
+
     @property
     def launches(self) -> int:
         return int(capi.launch_count(self._h))

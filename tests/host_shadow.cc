@@ -147,9 +147,112 @@ void shadow_solve_batch(void* h, int64_t n, const double* q_goal, const double* 
   }
 }
 
+// Mirrors ltp_solve_fast_kernel + the work-list hand-over to the generic kernel: the
+// closed-form pass decides per problem whether it is complete or deferred; deferred problems
+// are recomputed by shadow_solve_batch (the generic sequence). Returns the number deferred.
+int64_t shadow_solve_batch_auto(void* h, int64_t n, const double* q_goal, const double* q_0, const double* v_0,
+                                const double* a_0, double* t_opt, double* t_scaled, double* dir, double* v_drive,
+                                unsigned char* mod, unsigned char* opt_case, unsigned char* ts_case,
+                                unsigned char* final_case, int* slowest, int* traj_len, unsigned char* reached, int) {
+  Shadow* s = static_cast<Shadow*>(h);
+  const int dof = s->dof;
+  std::vector<Prologue> pro(dof);
+  int64_t deferred = 0;
+  for (int64_t p = 0; p < n; ++p) {
+    const int64_t o = p * dof;
+    bool any_fail = false, defer = false;
+    for (int j = 0; j < dof; ++j) {
+      const JointLimits& L = s->lim[j];
+      bool in_ok = check_joint_input(L, q_0[o + j], v_0[o + j], a_0[o + j]);
+      pro[j] = ost_prologue(L, s->ts, q_goal[o + j], q_0[o + j], v_0[o + j], a_0[o + j]);
+      double* t = t_opt + 7 * (o + j);
+      zero7(t);
+      mod[o + j] = 0;
+      opt_case[o + j] = 255;
+      int st = ost_body_t<false>(L, s->ts, pro[j], q_goal[o + j], q_0[o + j], L.v_max, t, mod[o + j], opt_case[o + j]);
+      any_fail |= !(in_ok && st != OST_FAIL);
+      defer |= st == OST_DEFER;
+      dir[o + j] = pro[j].dir;
+    }
+    double t_req = -1;
+    int sl = -1;
+    for (int j = 0; j < dof; ++j)
+      if (t_opt[7 * (o + j) + 6] > t_req) { t_req = t_opt[7 * (o + j) + 6]; sl = j; }
+    const bool rch = !any_fail && sl != -1;
+    int len = 0;
+    bool bad = false;
+    for (int j = 0; j < dof && !defer; ++j) {
+      const JointLimits& L = s->lim[j];
+      double* t = t_scaled + 7 * (o + j);
+      zero7(t);
+      v_drive[o + j] = L.v_max;
+      ts_case[o + j] = 255;
+      final_case[o + j] = 255;
+      if (rch) {
+        if (j == sl) {
+          ts_case[o + j] = 0;
+          final_case[o + j] = opt_case[o + j];
+        } else {
+          TsInput I = make_ts_input(q_goal[o + j], q_0[o + j], v_0[o + j], a_0[o + j], pro[j].dir, t_req);
+          int c = time_scaling_closed_form(L, s->ts, pro[j], I, t, v_drive[o + j], mod[o + j], final_case[o + j]);
+          if (c == 0) { defer = true; break; }
+          ts_case[o + j] = (unsigned char)c;
+          if (c == 9) final_case[o + j] = opt_case[o + j];
+        }
+        double m = t[0];
+        for (int k = 1; k < 7; ++k)
+          if (m < t[k]) m = t[k];
+        if (m <= 0.0) std::memcpy(t, t_opt + 7 * (o + j), 56);
+        bool fin = true;
+        for (int k = 0; k < 7; ++k) fin &= (bool)std::isfinite(t[k]);
+        int li = (fin && t[6] / s->ts <= 2.0e9) ? samples_for(t[6], s->ts) : -1;
+        bad |= li < 0;
+        len = li > len ? li : len;
+      }
+    }
+    if (defer) {
+      ++deferred;
+      shadow_solve_batch(h, 1, q_goal + o, q_0 + o, v_0 + o, a_0 + o, t_opt + 7 * o, t_scaled + 7 * o, dir + o,
+                         v_drive + o, mod + o, opt_case + o, ts_case + o, final_case + o, slowest + p,
+                         traj_len + p, reached + p, 0);
+      continue;
+    }
+    slowest[p] = sl;
+    traj_len[p] = (rch && !bad) ? len : 0;
+    reached[p] = rch;
+  }
+  return deferred;
+}
+
 int shadow_get_trajectory(void* h, const double* t7, const double* dir, const unsigned char* mod,
                           const double* q_0, const double* v_0, const double* a_0, const double* v_drive,
                           int64_t stride, double* q, double* v, double* a, double* j) {
+  Shadow* s = static_cast<Shadow*>(h);
+  const int dof = s->dof;
+  int len = 0;
+  for (int i = 0; i < dof; ++i) {
+    int li = samples_for(t7[7 * i + 6], s->ts);
+    len = li > len ? li : len;
+  }
+  if (len > stride) return -len;
+  for (int jt = 0; jt < dof; ++jt) {
+    RowSampler R;
+    R.init(s->ts, s->lim[jt].j_max, t7 + 7 * jt, dir[jt], mod[jt], q_0[jt], v_0[jt], a_0[jt], v_drive[jt], len);
+    SegTable T;
+    T.build(R, len);
+    SegCursor C;
+    C.enter(T, R, 0);
+    for (int i = 0; i < len; ++i)
+      C.step(T, R, i, j[jt * stride + i], a[jt * stride + i], v[jt * stride + i], q[jt * stride + i]);
+  }
+  return len;
+}
+
+// same rows by the sample-by-sample general rules (RowSampler::step); the segment machinery
+// above must reproduce this bit for bit
+int shadow_get_trajectory_general(void* h, const double* t7, const double* dir, const unsigned char* mod,
+                                  const double* q_0, const double* v_0, const double* a_0, const double* v_drive,
+                                  int64_t stride, double* q, double* v, double* a, double* j) {
   Shadow* s = static_cast<Shadow*>(h);
   const int dof = s->dof;
   int len = 0;

@@ -31,6 +31,35 @@ class Shadow(OraclePort):
     libname = os.path.join("..", "..", "tests", "_build", "libltp_shadow.so")
 
 
+class ShadowAuto(Shadow):
+    """closed-form pass + deferral to the generic sequence (what LTP_SOLVE_AUTO does)"""
+
+    def _fn(self, name, restype=None):
+        if name == "solve_batch":
+            import ctypes
+            f = getattr(self.lib, "shadow_solve_batch_auto")
+            f.restype = ctypes.c_int64
+
+            def call(*a):
+                self.deferred = f(*a)
+            return call
+        return super()._fn(name, restype)
+
+
+@pytest.mark.parametrize("lim,n,seed", [(W.FRANKA7, 30_000, 221), (W.REF_RANDOM6, 30_000, 222), (W.REF_GRID, 50_000, 223)])
+def test_closed_form_pass_plus_deferral_equals_generic(lim, n, seed):
+    qg, q0, v0, a0 = W.random_states(lim, n, seed)
+    gen = Shadow.from_limits(lim).solve(qg, q0, v0, a0)
+    S = ShadowAuto.from_limits(lim)
+    auto = S.solve(qg, q0, v0, a0)
+    for k in gen:
+        a, b = gen[k], auto[k]
+        assert np.array_equal(a, b, equal_nan=True) if a.dtype.kind == "f" else np.array_equal(a, b), k
+    assert 0 <= S.deferred < n
+    if lim is W.FRANKA7:  # realistic limits: the root solver is essentially never needed
+        assert S.deferred < 0.01 * n
+
+
 @pytest.mark.parametrize("lim,n,seed", [(W.FRANKA7, 40_000, 201), (W.FRANKA12, 10_000, 202), (W.REF_RANDOM6, 40_000, 203)])
 def test_device_math_solve_matches_oracle(lim, n, seed):
     qg, q0, v0, a0 = W.random_states(lim, n, seed)
