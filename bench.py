@@ -264,29 +264,36 @@ def main():
             g2, s0, sv, sa = W.random_states(lim, n_env, W.SEEDS[3])
             d2 = [torch.from_numpy(W.to_joint_major(x)).to(dev) for x in (g2, s0, sv, sa)]
             sol2 = ltp.alloc_solution(n_env)
-            traj = ltp.alloc_trajectories(n_env, horizon)
             reps = 20
-            for _ in range(3):
-                ltp.solve(*d2, out=sol2)
-                ltp.sample(d2[1], d2[2], d2[3], sol2, horizon=horizon, out=traj)
-            torch.cuda.synchronize()
-            ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(reps)]
-            for r in range(reps):
-                ev[r][0].record()
-                ltp.solve(*d2, out=sol2)
-                ev[r][1].record()
-                ltp.sample(d2[1], d2[2], d2[3], sol2, horizon=horizon, out=traj)
-                ev[r][2].record()
-            torch.cuda.synchronize()
-            solve_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-            samp_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
             useful = n_env * lim.dof * horizon * 32
+            res = {}
+            for layout in ("rows", "time_major"):
+                traj = ltp.alloc_trajectories(n_env, horizon, layout)
+                for _ in range(3):
+                    ltp.solve(*d2, out=sol2)
+                    ltp.sample(d2[1], d2[2], d2[3], sol2, horizon=horizon, out=traj)
+                torch.cuda.synchronize()
+                ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(reps)]
+                for r in range(reps):
+                    ev[r][0].record()
+                    ltp.solve(*d2, out=sol2)
+                    ev[r][1].record()
+                    ltp.sample(d2[1], d2[2], d2[3], sol2, horizon=horizon, out=traj)
+                    ev[r][2].record()
+                torch.cuda.synchronize()
+                res[layout] = (float(np.mean([e[0].elapsed_time(e[1]) for e in ev])),
+                               float(np.mean([e[1].elapsed_time(e[2]) for e in ev])))
+                del traj
+            solve_ms, samp_ms = res["time_major"]
             gbs = useful / (samp_ms * 1e-3) / 1e9
             extra["sampler"] = {
                 "workload": "configs[2]: 4096 envs x 7 DoF, fixed horizon 2001 samples (2 s at 1 ms), "
                             "output 1.84 GB per replan (larger than L2)",
+                "layout": "time-major (samples, n, dof) f64 tensors q, v, a, j",
                 "replan_ms": solve_ms + samp_ms, "solve_ms": solve_ms, "sample_ms": samp_ms,
-                "roofline": {"kernel": "ltp_sample_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
+                "rows_layout_sample_ms": res["rows"][1],
+                "rows_layout_gbs": useful / (res["rows"][1] * 1e-3) / 1e9,
+                "roofline": {"kernel": "ltp_sample_tm_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
                              "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
                              "algorithmic_bytes_per_sample": 32, "bytes_per_launch": useful,
                              "write_only_probe_gbs": wgbs.value}}

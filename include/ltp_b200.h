@@ -117,15 +117,25 @@ int ltp_solve_batch(ltp_planner* p, int64_t n, const double* q_goal, const doubl
 
 /* replaces LongTermPlanner::getTrajectory + the final joint-limit check
  * (reference long_term_planner.cc:58-61, 706-841) for n problems.
- *   horizon == 0: every problem writes exactly traj_len[p] samples per row;
- *   horizon  > 0: every row holds exactly `horizon` samples (clipped, or continued with
- *                 the recurrence's own steady state q_last, 0, 0, 0).
- * stride (doubles per row) must be >= the samples written; rows are written with 32-byte
- * vector stores when stride % 4 == 0 and the four base pointers are 32-byte aligned.
+ *   horizon == 0: every problem writes exactly traj_len[p] samples;
+ *   horizon  > 0: every problem writes exactly `horizon` samples (clipped, or continued
+ *                 with the recurrence's own steady state q_last, 0, 0, 0).
+ * layout:
+ *   LTP_LAYOUT_ROWS        q[(problem * dof + joint) * stride + sample]  -- one row per
+ *                          (problem, joint) like Trajectory::q[joint][sample]; stride =
+ *                          doubles per row, >= the samples written. 32-byte vector stores
+ *                          when stride % 4 == 0 and the base pointers are 32-byte aligned.
+ *   LTP_LAYOUT_TIME_MAJOR  q[(sample * n + problem) * dof + joint]  -- a (stride, n, dof)
+ *                          tensor; stride = sample capacity. This is the layout a batched
+ *                          consumer steps through (all environments read sample k together)
+ *                          and the one that streams to HBM at full bandwidth.
  * success: [n], 1 iff reached and every joint ends inside [q_min, q_max]. */
+#define LTP_LAYOUT_ROWS 0
+#define LTP_LAYOUT_TIME_MAJOR 1
 int ltp_sample_batch(ltp_planner* p, int64_t n, const double* q_0, const double* v_0,
-                     const double* a_0, const ltp_solution* sol, int32_t horizon, int64_t stride,
-                     double* q, double* v, double* a, double* j, uint8_t* success, void* stream);
+                     const double* a_0, const ltp_solution* sol, int32_t horizon, int32_t layout,
+                     int64_t stride, double* q, double* v, double* a, double* j, uint8_t* success,
+                     void* stream);
 
 /* ---- host-buffer entry points (what a caller without device buffers uses) ------------ */
 

@@ -58,8 +58,9 @@ opt_switch_times_batch = _sig("ltp_opt_switch_times_batch", C.c_int, vp, i64, vp
 time_scaling_batch = _sig("ltp_time_scaling_batch", C.c_int, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                           vp, vp, vp)
 solve_batch = _sig("ltp_solve_batch", C.c_int, vp, i64, vp, vp, vp, vp, C.POINTER(Solution), vp)
-sample_batch = _sig("ltp_sample_batch", C.c_int, vp, i64, vp, vp, vp, C.POINTER(Solution), i32, i64, vp, vp,
-                    vp, vp, vp, vp)
+sample_batch = _sig("ltp_sample_batch", C.c_int, vp, i64, vp, vp, vp, C.POINTER(Solution), i32, i32, i64, vp,
+                    vp, vp, vp, vp, vp)
+LAYOUT_ROWS, LAYOUT_TIME_MAJOR = 0, 1
 solve_host = _sig("ltp_solve_host", C.c_int, vp, i64, vp, vp, vp, vp, C.POINTER(Solution))
 plan_host = _sig("ltp_plan_host", C.c_int, vp, i64, vp, vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, vp,
                  C.POINTER(i64))

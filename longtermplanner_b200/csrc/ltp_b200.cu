@@ -404,8 +404,13 @@ ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, int ppb, c
                   const double* __restrict__ v_0, const double* __restrict__ a_0, DeviceSolution S,
                   int horizon, int64_t stride, double* __restrict__ q, double* __restrict__ v,
                   double* __restrict__ a, double* __restrict__ j, uint8_t* success) {
+  // per-lane segment table, [entry][lane]
+  __shared__ double s_tsj[kMaxSeg][32];
+  __shared__ double s_jv[kMaxSeg][32];
+  __shared__ int2 s_nf[kMaxSeg][32];
   const int dof = P.dof;
   const int lane = threadIdx.x;
+  const SegTableT<32> T{&s_tsj[0][lane], &s_jv[0][lane], &s_nf[0][lane]};
   const int slot = lane / dof, jt = lane - slot * dof;   // problem slot within the CTA, joint
   const int64_t p = (int64_t)blockIdx.x * ppb + slot;
   const bool valid = slot < ppb && p < n;
@@ -420,12 +425,13 @@ ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, int ppb, c
       for (int k = 0; k < 7; ++k) t[k] = S.t_scaled[((int64_t)k * dof + jt) * n + p];
       const int n_out = horizon > 0 ? horizon : len;  // samples stored
       const int n_run = n_out > len ? n_out : len;    // samples computed
-      RowSampler R;
-      R.init(P.ts, L.j_max, t, S.dir[at], S.mod[at], q_0[at], v_0[at], a_0[at], S.v_drive[at], n_run);
-      SegTable T;
-      T.build(R, n_run);
-      SegCursor C;
-      C.enter(T, R, 0);
+      SegCursorT<32> C;
+      {
+        RowSampler R;
+        R.init(P.ts, L.j_max, t, S.dir[at], S.mod[at], q_0[at], v_0[at], a_0[at], S.v_drive[at], n_run);
+        T.build(R, n_run);
+        C.begin(R);
+      }
       const int64_t base = (p * dof + jt) * stride;
       double* qo = q + base; double* vo = v + base; double* ao = a + base; double* jo = j + base;
       double q_last = 0.0;
@@ -435,7 +441,7 @@ ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, int ppb, c
         for (; i < n_vec; i += 4) {
           double jj[4], aa[4], vv[4], qq[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) C.step(T, R, i + u, jj[u], aa[u], vv[u], qq[u]);
+          for (int u = 0; u < 4; ++u) C.step(T, i + u, jj[u], aa[u], vv[u], qq[u]);
           const unsigned k = (unsigned)(len - 1 - i);
           if (k < 4u) q_last = k == 0 ? qq[0] : k == 1 ? qq[1] : k == 2 ? qq[2] : qq[3];
           store4(qo + i, qq[0], qq[1], qq[2], qq[3]);
@@ -446,7 +452,7 @@ ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, int ppb, c
       }
       for (; i < n_run; ++i) {
         double jj, aa, vv, qq;
-        C.step(T, R, i, jj, aa, vv, qq);
+        C.step(T, i, jj, aa, vv, qq);
         if (i == len - 1) q_last = qq;
         if (i < n_out) {
           qo[i] = qq; vo[i] = vv; ao[i] = aa; jo[i] = jj;
@@ -461,6 +467,82 @@ ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, int ppb, c
     const unsigned want = ((dof >= 32) ? 0xffffffffu : ((1u << dof) - 1u)) << (slot * dof);
     success[p] = (uint8_t)((ok_mask & want) == want);
   }
+}
+
+// Time-major variant: q[(sample * n + problem) * dof + joint] (a torch tensor of shape
+// (samples, n, dof)). Lane l of CTA b owns row r = 32 b + l of the flattened (problem, joint)
+// index, so the 32 lanes of a warp write 32 consecutive doubles -- one aligned 256-byte
+// piece, two complete 128-byte lines -- per field and sample, and all rows advance through
+// the output in lockstep: HBM sees four long sequential write streams instead of n*dof*4
+// interleaved ones. Measured on B200 (tools/experiments/store_pattern_probe.cu,
+// store_parallelism_probe.cu): ~6.0 TB/s for this pattern against ~4.3 TB/s for one
+// 32-byte sector per row per store at a 16 KB row stride.
+// success[] must have been initialised with reached[]; a row that ends outside its joint
+// limits clears its problem's flag.
+__device__ __forceinline__ void clear_flag(uint8_t* flags, int64_t p) {
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(flags + p);
+  unsigned* word = reinterpret_cast<unsigned*>(addr & ~uintptr_t(3));
+  const unsigned shift = (unsigned)(addr & 3u) * 8u;
+  atomicAnd(word, ~(0xffu << shift));
+}
+
+__device__ __forceinline__ void store1(double* dst, double x) {
+  asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(dst), "d"(x) : "memory");
+}
+
+__global__ void __launch_bounds__(32)
+ltp_sample_tm_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_0,
+                     const double* __restrict__ v_0, const double* __restrict__ a_0, DeviceSolution S,
+                     int horizon, double* __restrict__ q, double* __restrict__ v, double* __restrict__ a,
+                     double* __restrict__ j, uint8_t* success) {
+  __shared__ double s_tsj[kMaxSeg][32];
+  __shared__ double s_jv[kMaxSeg][32];
+  __shared__ int2 s_nf[kMaxSeg][32];
+  const int dof = P.dof;
+  const int lane = threadIdx.x;
+  const SegTableT<32> T{&s_tsj[0][lane], &s_jv[0][lane], &s_nf[0][lane]};
+  const int64_t rows = n * dof;
+  const int64_t r = (int64_t)blockIdx.x * 32 + lane;
+  if (r >= rows) return;
+  const int64_t p = r / dof;
+  const int jt = (int)(r - p * dof);
+  if (!S.reached[p]) return;
+  const int len = S.traj_len[p];
+  if (len <= 0) {
+    clear_flag(success, p);
+    return;
+  }
+  const JointLimits L = P.lim[jt];
+  const int64_t at = (int64_t)jt * n + p;
+  double t[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) t[k] = S.t_scaled[((int64_t)k * dof + jt) * n + p];
+  const int n_out = horizon > 0 ? horizon : len;  // samples stored
+  const int n_run = n_out > len ? n_out : len;    // samples computed
+  SegCursorT<32> C;
+  {
+    RowSampler R;
+    R.init(P.ts, L.j_max, t, S.dir[at], S.mod[at], q_0[at], v_0[at], a_0[at], S.v_drive[at], n_run);
+    T.build(R, n_run);
+    C.begin(R);
+  }
+  double* qo = q + r; double* vo = v + r; double* ao = a + r; double* jo = j + r;
+  double q_last = 0.0;
+  int i = 0;
+#pragma unroll 4
+  for (; i < n_out; ++i) {
+    double jj, aa, vv, qq;
+    C.step(T, i, jj, aa, vv, qq);
+    if (i == len - 1) q_last = qq;
+    store1(qo, qq); store1(vo, vv); store1(ao, aa); store1(jo, jj);
+    qo += rows; vo += rows; ao += rows; jo += rows;
+  }
+  for (; i < n_run; ++i) {  // clipped horizon: run on to the true end for the limit check
+    double jj, aa, vv, qq;
+    C.step(T, i, jj, aa, vv, qq);
+    if (i == len - 1) q_last = qq;
+  }
+  if (q_last < L.q_min || q_last > L.q_max) clear_flag(success, p);  // cc:60
 }
 
 // [dof][7] host-style times -> [7][dof][1] is trivial on the host; nothing to do on device.
@@ -760,8 +842,9 @@ int ltp_solve_batch(ltp_planner* p, int64_t n, const double* q_goal, const doubl
 }
 
 int ltp_sample_batch(ltp_planner* p, int64_t n, const double* q_0, const double* v_0, const double* a_0,
-                     const ltp_solution* sol, int32_t horizon, int64_t stride, double* q, double* v,
-                     double* a, double* j, uint8_t* success, void* stream) {
+                     const ltp_solution* sol, int32_t horizon, int32_t layout, int64_t stride, double* q,
+                     double* v, double* a, double* j, uint8_t* success, void* stream) {
+  if (layout != LTP_LAYOUT_ROWS && layout != LTP_LAYOUT_TIME_MAJOR) return LTP_ERR_ARG;
   if (!p || n < 0 || p->params.dof < 1 || horizon < 0) return LTP_ERR_ARG;
   if (n == 0) return LTP_OK;
   if (!q_0 || !v_0 || !a_0 || !sol || !q || !v || !a || !j || !success || stride < 1 ||
@@ -771,6 +854,16 @@ int ltp_sample_batch(ltp_planner* p, int64_t n, const double* q_0, const double*
     return LTP_ERR_ARG;
   DeviceGuard g(p->device);
   const int dof = p->params.dof;
+  if (layout == LTP_LAYOUT_TIME_MAJOR) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LTP_CUDA(cudaMemcpyAsync(success, sol->reached, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    const int64_t rows = n * dof;
+    ltp_sample_tm_kernel<<<(unsigned)((rows + 31) / 32), 32, 0, st>>>(p->params, n, q_0, v_0, a_0, to_dev(sol),
+                                                                     horizon, q, v, a, j, success);
+    p->launches++;
+    LTP_CUDA(cudaGetLastError());
+    return LTP_OK;
+  }
   const int ppb = 32 / dof > 0 ? 32 / dof : 1;  // whole problems per one-warp CTA (dof <= 32)
   const unsigned grid = (unsigned)((n + ppb - 1) / ppb);
   const bool vec = (stride % 4 == 0) && aligned32(q) && aligned32(v) && aligned32(a) && aligned32(j);
@@ -875,7 +968,7 @@ int ltp_plan_host(ltp_planner* p, int64_t n, const double* q_goal, const double*
     for (int64_t i = 0; i < n; ++i) success[i] = 0;
     return need > capacity ? LTP_ERR_CAPACITY : LTP_ERR_ARG;
   }
-  rc = ltp_sample_batch(p, n, d_in[1], d_in[2], d_in[3], &ds, horizon, dstride, d_rows[0], d_rows[1],
+  rc = ltp_sample_batch(p, n, d_in[1], d_in[2], d_in[3], &ds, horizon, LTP_LAYOUT_ROWS, dstride, d_rows[0], d_rows[1],
                         d_rows[2], d_rows[3], d_succ, st);
   if (rc != LTP_OK) return rc;
   double* h_rows[4] = {q, v, a, j};
@@ -1016,7 +1109,7 @@ int ltp_get_trajectory_host(ltp_planner* p, const double* t7, const double* dir,
   const double* h_in[3] = {q_0, v_0, a_0};
   for (int i = 0; i < 3; ++i) LTP_CUDA(cudaMemcpyAsync(d_in[i], h_in[i], sizeof(double) * dof, cudaMemcpyHostToDevice, st));
   LTP_CUDA(cudaStreamSynchronize(st));  // the small host arrays above live on this stack frame
-  rc = ltp_sample_batch(p, 1, d_in[0], d_in[1], d_in[2], &ds, 0, dstride, d_rows[0], d_rows[1], d_rows[2],
+  rc = ltp_sample_batch(p, 1, d_in[0], d_in[1], d_in[2], &ds, 0, LTP_LAYOUT_ROWS, dstride, d_rows[0], d_rows[1], d_rows[2],
                         d_rows[3], d_succ, st);
   if (rc != LTP_OK) return rc;
   double* h_rows[4] = {q, v, a, j};

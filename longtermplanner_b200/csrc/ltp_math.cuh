@@ -26,6 +26,10 @@
 #include <math.h>
 #include <stdint.h>
 
+#ifndef __CUDACC__
+struct int2 { int x, y; };  // host build of the device math (tests/host_shadow.cc)
+#endif
+
 #ifdef __CUDACC__
 #define LTP_HD __host__ __device__ __forceinline__
 #define LTP_HD_NOINLINE __host__ __device__ __noinline__
@@ -1028,59 +1032,67 @@ struct RowSampler {
   }
 };
 
-// The row cut into pieces of constant jerk and constant update rule.
-struct SegTable {
-  int start[kMaxSeg + 1];   // start[m] .. start[m+1]-1; unused entries are INT_MAX
-  double tsj[kMaxSeg];      // Ts * jerk (0 where the acceleration is pinned to 0)
-  double jv[kMaxSeg];       // jerk value that is emitted
-  unsigned char fl[kMaxSeg];  // bit0: a = v = 0 from here on (cc:817-829), bit1: v = v_drive*dir
+// The row cut into pieces of constant jerk and constant update rule. The table is addressed
+// with a compile-time stride so that the kernel can keep one column per lane in shared
+// memory ([entry][lane], conflict-free for any mix of entry indices) while the host build
+// uses plain arrays (stride 1).
+template <int STRIDE>
+struct SegTableT {
+  double* tsj;   // Ts * jerk of the piece (0 where the acceleration is pinned to 0)
+  double* jv;    // jerk value that is emitted
+  int2* nf;      // .x = first sample index of the NEXT piece, .y = flags:
+                 //   bit0: a = v = 0 (past the last switching time, cc:817-829)
+                 //   bit1: v = v_drive*dir (cruise override, cc:822-823)
 
-  LTP_HD void build(const RowSampler& R, int limit) {
+  LTP_HD void build(const RowSampler& R, int limit) const {
     int cur = 0;
 #pragma unroll 1
     for (int m = 0; m < kMaxSeg; ++m) {
-      start[m] = cur;
       const int at = cur < limit ? cur : 0;  // entries past the end are never entered
       const double j = R.jerk_at(at);
       const bool az = R.a_zero(at);
-      jv[m] = j;
-      tsj[m] = az ? 0.0 : R.Ts * j;
-      fl[m] = (unsigned char)((az ? 1 : 0) | (R.v_cruise(at) ? 2 : 0));
+      const int fl = (az ? 1 : 0) | (R.v_cruise(at) ? 2 : 0);
       if (cur < limit) {
         cur = R.next_break(cur);
         if (cur >= limit) cur = 0x7fffffff;
       }
+      jv[m * STRIDE] = j;
+      tsj[m * STRIDE] = az ? 0.0 : R.Ts * j;
+      int2 e;
+      e.x = cur;
+      e.y = fl;
+      nf[m * STRIDE] = e;
     }
-    start[kMaxSeg] = 0x7fffffff;
   }
 };
 
-struct SegCursor {
+// Streaming state of one row. step() is branch-free: the piece index advances by a compare,
+// and the (three) table words of the current piece are re-read every sample.
+template <int STRIDE>
+struct SegCursorT {
+  double Ts, vcruise, a, v, q;
   int m, next;
-  double tsj, jv;
-  bool vc;
 
-  LTP_HD void enter(const SegTable& T, RowSampler& R, int m_) {
-    m = m_;
-    tsj = T.tsj[m];
-    jv = T.jv[m];
-    const unsigned f = T.fl[m];
-    vc = (f & 2u) != 0;
-    if (f & 1u) {  // past the last switching time: a and v are exactly 0 from here on
-      R.a = 0.0;
-      R.v = 0.0;
-    }
-    next = T.start[m + 1];
+  LTP_HD void begin(const RowSampler& R) {
+    Ts = R.Ts; vcruise = R.vcruise; a = R.a; v = R.v; q = R.q;
+    m = 0;
+    next = 0x7fffffff;  // replaced by entry 0 on the first step (i = 0 never equals it)
   }
 
-  // sample i (called with i = 0, 1, 2, ... in order)
-  LTP_HD void step(const SegTable& T, RowSampler& R, int i, double& jo, double& ao, double& vo, double& qo) {
-    if (i == next) enter(T, R, m + 1);
-    R.a = R.a + tsj;
-    const double vn = R.v + R.Ts * R.a;
-    R.v = vc ? R.vcruise : vn;
-    R.q = R.q + R.Ts * R.v;
-    jo = jv; ao = R.a; vo = R.v; qo = R.q;
+  LTP_HD void step(const SegTableT<STRIDE>& T, int i, double& jo, double& ao, double& vo, double& qo) {
+    m += (i == next) ? 1 : 0;
+    const double tsj = T.tsj[m * STRIDE];
+    const double jv = T.jv[m * STRIDE];
+    const int2 e = T.nf[m * STRIDE];
+    next = e.x;
+    const bool az = (e.y & 1) != 0, vc = (e.y & 2) != 0;
+    const double an = a + tsj;
+    a = az ? 0.0 : an;
+    const double vn = v + Ts * a;
+    const double vz = az ? 0.0 : vn;
+    v = vc ? vcruise : vz;
+    q = q + Ts * v;
+    jo = jv; ao = a; vo = v; qo = q;
   }
 };
 

@@ -61,7 +61,9 @@ class BatchSolution:
 
 @dataclasses.dataclass
 class BatchTrajectories:
-    """Device-resident sampled trajectories: rows [n, dof, stride], sample-contiguous."""
+    """Device-resident sampled trajectories. layout "time_major": tensors (stride, n, dof);
+    layout "rows": tensors (n, dof, stride), sample-contiguous like Trajectory::q[joint]."""
+    layout: str
     horizon: int
     stride: int
     q: torch.Tensor
@@ -98,7 +100,7 @@ class LongTermPlanner:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and capi is not None and getattr(capi, "destroy", None) is not None:  # interpreter shutdown
             capi.destroy(h)
             self._h = None
 
@@ -242,33 +244,44 @@ class LongTermPlanner:
                    "ltp_solve_batch")
         return sol
 
-    def alloc_trajectories(self, n: int, samples: int) -> BatchTrajectories:
+    def alloc_trajectories(self, n: int, samples: int, layout: str = "time_major") -> BatchTrajectories:
         dev = torch.device("cuda", self.device)
-        stride = (samples + 3) // 4 * 4
-        rows = [torch.empty(n, self.dof_, stride, dtype=torch.float64, device=dev) for _ in range(4)]
-        return BatchTrajectories(0, stride, *rows, torch.empty(n, dtype=torch.uint8, device=dev), None)
+        if layout == "time_major":
+            stride = samples
+            shape = (stride, n, self.dof_)
+        elif layout == "rows":
+            stride = (samples + 3) // 4 * 4
+            shape = (n, self.dof_, stride)
+        else:
+            raise ValueError(layout)
+        rows = [torch.empty(shape, dtype=torch.float64, device=dev) for _ in range(4)]
+        # 4-byte aligned, padded flag array (the kernel clears flags with word atomics)
+        succ = torch.empty((n + 3) // 4 * 4, dtype=torch.uint8, device=dev)[:n]
+        return BatchTrajectories(layout, 0, stride, *rows, succ, None)
 
     def sample(self, q_0, v_0, a_0, sol: BatchSolution, horizon: int = 0,
-               out: Optional[BatchTrajectories] = None) -> BatchTrajectories:
-        """stage 4. horizon = 0: exact length per problem (synchronises once to size the rows
-        unless `out` is given); horizon > 0: fixed number of samples per row."""
+               out: Optional[BatchTrajectories] = None, layout: str = "time_major") -> BatchTrajectories:
+        """stage 4. horizon = 0: exact length per problem (synchronises once to size the output
+        unless `out` is given); horizon > 0: fixed number of samples per problem."""
         n = sol.n
         ins = [self._chk(t, n, nm) for t, nm in zip((q_0, v_0, a_0), ("q_0", "v_0", "a_0"))]
         if out is None:
             samples = horizon if horizon > 0 else max(int(sol.traj_len.max().item()), 1)
-            out = self.alloc_trajectories(n, samples)
+            out = self.alloc_trajectories(n, samples, layout)
         out.horizon = horizon
         out.traj_len = sol.traj_len
         cs = sol.c_struct()
-        capi.check(capi.sample_batch(self._h, n, *[t.data_ptr() for t in ins], C.byref(cs), horizon, out.stride,
-                                     out.q.data_ptr(), out.v.data_ptr(), out.a.data_ptr(), out.j.data_ptr(),
-                                     out.success.data_ptr(), self._stream()), "ltp_sample_batch")
+        lay = capi.LAYOUT_TIME_MAJOR if out.layout == "time_major" else capi.LAYOUT_ROWS
+        capi.check(capi.sample_batch(self._h, n, *[t.data_ptr() for t in ins], C.byref(cs), horizon, lay,
+                                     out.stride, out.q.data_ptr(), out.v.data_ptr(), out.a.data_ptr(),
+                                     out.j.data_ptr(), out.success.data_ptr(), self._stream()),
+                   "ltp_sample_batch")
         return out
 
-    def planTrajectories(self, q_goal, q_0, v_0, a_0, horizon: int = 0):
+    def planTrajectories(self, q_goal, q_0, v_0, a_0, horizon: int = 0, layout: str = "time_major"):
         """Batched planTrajectory: -> (BatchSolution, BatchTrajectories)."""
         sol = self.solve(q_goal, q_0, v_0, a_0)
-        return sol, self.sample(q_0, v_0, a_0, sol, horizon)
+        return sol, self.sample(q_0, v_0, a_0, sol, horizon, layout=layout)
 
     # per-joint primitives, batched
     def optBrakingBatch(self, v_0, a_0):

@@ -238,12 +238,14 @@ int shadow_get_trajectory(void* h, const double* t7, const double* dir, const un
   for (int jt = 0; jt < dof; ++jt) {
     RowSampler R;
     R.init(s->ts, s->lim[jt].j_max, t7 + 7 * jt, dir[jt], mod[jt], q_0[jt], v_0[jt], a_0[jt], v_drive[jt], len);
-    SegTable T;
+    double tsj[kMaxSeg], jv[kMaxSeg];
+    int2 nf[kMaxSeg];
+    SegTableT<1> T{tsj, jv, nf};
     T.build(R, len);
-    SegCursor C;
-    C.enter(T, R, 0);
+    SegCursorT<1> C;
+    C.begin(R);
     for (int i = 0; i < len; ++i)
-      C.step(T, R, i, j[jt * stride + i], a[jt * stride + i], v[jt * stride + i], q[jt * stride + i]);
+      C.step(T, i, j[jt * stride + i], a[jt * stride + i], v[jt * stride + i], q[jt * stride + i]);
   }
   return len;
 }

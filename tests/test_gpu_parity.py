@@ -63,13 +63,23 @@ def test_solve_matches_reference_build():
     assert count_bad(pm(sol.v_drive.cpu().numpy()), ref["v_drive"]) == 0
 
 
+def _rows(traj):
+    """-> {field: array [n, dof, samples]} for either layout"""
+    out = {}
+    for k in "qvaj":
+        x = getattr(traj, k).cpu().numpy()
+        out[k] = x if traj.layout == "rows" else np.ascontiguousarray(x.transpose(1, 2, 0))
+    return out
+
+
+@pytest.mark.parametrize("layout", ["time_major", "rows"])
 @pytest.mark.parametrize("lim,n,seed", [(W.FRANKA7, 96, W.SEEDS[1]), (W.REF_RANDOM6, 300, 11), (W.FRANKA12, 40, 5)])
-def test_sampled_trajectories_match_oracle(lim, n, seed):
+def test_sampled_trajectories_match_oracle(lim, n, seed, layout):
     ltp, ins, sol, ref, (qg, q0, v0, a0) = _solve_both(lim, n, seed)
-    traj = ltp.sample(ins[1], ins[2], ins[3], sol)
+    traj = ltp.sample(ins[1], ins[2], ins[3], sol, layout=layout)
     torch.cuda.synchronize()
     P = OraclePort.from_limits(lim)
-    rows = {k: getattr(traj, k).cpu().numpy() for k in "qvaj"}
+    rows = _rows(traj)
     succ = traj.success.cpu().numpy()
     tl = sol.traj_len.cpu().numpy()
     bad = 0
@@ -82,19 +92,22 @@ def test_sampled_trajectories_match_oracle(lim, n, seed):
     assert bad == 0
 
 
-def test_fixed_horizon_mode():
+@pytest.mark.parametrize("layout", ["time_major", "rows"])
+def test_fixed_horizon_mode(layout):
     """horizon > traj_len continues with the recurrence's steady state (q_last, 0, 0, 0);
     horizon < traj_len clips; the first min(horizon, traj_len) samples equal the exact mode"""
     lim, n = W.FRANKA7, 64
     ltp, ins, sol, ref, _ = _solve_both(lim, n, 21)
-    exact = ltp.sample(ins[1], ins[2], ins[3], sol)
+    exact = ltp.sample(ins[1], ins[2], ins[3], sol, layout=layout)
     tl = sol.traj_len.cpu().numpy()
+    erows = _rows(exact)
     for H in (int(tl.max()) + 37, int(tl.min()) // 2):
-        fixed = ltp.sample(ins[1], ins[2], ins[3], sol, horizon=H)
+        fixed = ltp.sample(ins[1], ins[2], ins[3], sol, horizon=H, layout=layout)
         torch.cuda.synchronize()
         assert np.array_equal(fixed.success.cpu().numpy(), exact.success.cpu().numpy())
+        frows = _rows(fixed)
         for k in "qvaj":
-            e, f = getattr(exact, k).cpu().numpy(), getattr(fixed, k).cpu().numpy()
+            e, f = erows[k], frows[k]
             for i in range(n):
                 m = min(H, tl[i])
                 # sample index tl-1+1 may carry the late jerk impulse the exact mode drops
@@ -188,6 +201,30 @@ def test_host_entry_point_equals_device_entry_point():
               "ts_case", "final_case"):
         a, b = host[k], getattr(sol, k).cpu().numpy()
         assert np.array_equal(a, b, equal_nan=True) if a.dtype.kind == "f" else np.array_equal(a, b), k
+
+
+def test_layouts_agree_and_limit_violations_are_flagged():
+    """both layouts hold the same samples; a plan that ends outside [q_min, q_max] reports
+    success = 0 with the trajectory still written (reference cc:59-61)"""
+    lim = W.FRANKA7
+    ltp = _planner(lim)
+    qg, q0, v0, a0 = W.random_states(lim, 257, 41)
+    qg[5, 3] = lim.q_max[3] + 0.5    # goal outside the joint range: reached, but final check fails
+    qg[200, 0] = lim.q_min[0] - 0.5
+    ins = [_dev(jm(x)) for x in (qg, q0, v0, a0)]
+    sol = ltp.solve(*ins)
+    a = ltp.sample(ins[1], ins[2], ins[3], sol, layout="time_major")
+    b = ltp.sample(ins[1], ins[2], ins[3], sol, layout="rows")
+    torch.cuda.synchronize()
+    sa, sb = a.success.cpu().numpy(), b.success.cpu().numpy()
+    assert np.array_equal(sa, sb) and sa[5] == 0 and sa[200] == 0 and sa.sum() == 255
+    P = OraclePort.from_limits(lim)
+    assert P.plan(qg[5], q0[5], v0[5], a0[5])["success"] is False
+    tl = sol.traj_len.cpu().numpy()
+    ra, rb = _rows(a), _rows(b)
+    for k in "qvaj":
+        for i in (0, 5, 100, 200, 256):
+            assert np.array_equal(ra[k][i, :, :tl[i]], rb[k][i, :, :tl[i]])
 
 
 def test_rejected_inputs_and_empty_batch():

@@ -1,0 +1,59 @@
+"""Condense an .ncu-rep (read here, no GPU needed) into the handful of numbers the roofline
+discussion uses. Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [> profiles/xxx.txt]"""
+import csv
+import subprocess
+import sys
+
+KEYS = [
+    ("gpu__time_duration.sum", "duration"),
+    ("launch__grid_size", "grid"), ("launch__block_size", "block"),
+    ("launch__registers_per_thread", "regs/thread"),
+    ("launch__occupancy_limit_registers", "occ limit regs (blocks)"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
+    ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "FP64 pipe util % (inst)"),
+    ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "FP64 pipe cycles active %"),
+    ("smsp__thread_inst_executed_per_inst_executed.ratio", "active threads / instr"),
+    ("smsp__inst_executed.sum", "warp instructions"),
+    ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram throughput % of peak"),
+    ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram throughput %"),
+    ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+    ("l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "L1 global store sectors"),
+    ("smsp__sass_inst_executed_op_local_ld.sum", "local loads"),
+    ("smsp__sass_inst_executed_op_local_st.sum", "local stores"),
+    ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall barrier"),
+    ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall wait (fixed latency)"),
+    ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "stall no_instruction"),
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long_scoreboard"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall short_scoreboard"),
+    ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall math_pipe_throttle"),
+    ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "stall lg_throttle"),
+    ("smsp__average_warps_issue_stalled_drain_per_issue_active.ratio", "stall drain"),
+    ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "stall branch_resolving"),
+    ("smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "stall dispatch"),
+    ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall not_selected"),
+]
+
+
+def main(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    seen = {}
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void <unnamed>::", "")
+        seen.setdefault(name, []).append(r)
+    for name, rs in seen.items():
+        di = hdr.index("gpu__time_duration.sum")
+        r = max(rs, key=lambda x: float(x[di]))  # the largest launch of each kernel
+        print(f"=== {name}  ({len(rs)} launches captured; showing the longest)")
+        for k, label in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                print(f"  {label:34s} {r[i]:>16s} {units[i]}")
+        print()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

@@ -21,9 +21,10 @@ for _ in range(reps):
 n2, H = 4096, 2001
 ins2 = [torch.from_numpy(W.to_joint_major(x)).cuda() for x in W.random_states(lim, n2, W.SEEDS[3])]
 sol2 = ltp.alloc_solution(n2)
-traj = ltp.alloc_trajectories(n2, H)
-for _ in range(reps):
-    ltp.solve(*ins2, out=sol2)
-    ltp.sample(ins2[1], ins2[2], ins2[3], sol2, horizon=H, out=traj)
+for layout in ("time_major", "rows"):
+    traj = ltp.alloc_trajectories(n2, H, layout)
+    for _ in range(reps):
+        ltp.solve(*ins2, out=sol2)
+        ltp.sample(ins2[1], ins2[2], ins2[3], sol2, horizon=H, out=traj)
 torch.cuda.synchronize()
 print("done")
