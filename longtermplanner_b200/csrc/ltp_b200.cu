@@ -404,13 +404,10 @@ ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, int ppb, c
                   const double* __restrict__ v_0, const double* __restrict__ a_0, DeviceSolution S,
                   int horizon, int64_t stride, double* __restrict__ q, double* __restrict__ v,
                   double* __restrict__ a, double* __restrict__ j, uint8_t* success) {
-  // per-lane segment table, [entry][lane]
-  __shared__ double s_tsj[kMaxSeg][32];
-  __shared__ double s_jv[kMaxSeg][32];
-  __shared__ int2 s_nf[kMaxSeg][32];
+  __shared__ double s_tab[kMaxSeg][4][32];  // per-lane segment table, [entry][word][lane]
   const int dof = P.dof;
   const int lane = threadIdx.x;
-  const SegTableT<32> T{&s_tsj[0][lane], &s_jv[0][lane], &s_nf[0][lane]};
+  const SegTableT<32> T{&s_tab[0][0][lane]};
   const int slot = lane / dof, jt = lane - slot * dof;   // problem slot within the CTA, joint
   const int64_t p = (int64_t)blockIdx.x * ppb + slot;
   const bool valid = slot < ppb && p < n;
@@ -490,17 +487,18 @@ __device__ __forceinline__ void store1(double* dst, double x) {
   asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(dst), "d"(x) : "memory");
 }
 
+// OffT: byte offsets inside one field are kept in 32 bits when the field is smaller than
+// 4 GiB, which lets every store use the [uniform 64-bit base + 32-bit offset] address form.
+template <typename OffT>
 __global__ void __launch_bounds__(32)
 ltp_sample_tm_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_0,
                      const double* __restrict__ v_0, const double* __restrict__ a_0, DeviceSolution S,
                      int horizon, double* __restrict__ q, double* __restrict__ v, double* __restrict__ a,
                      double* __restrict__ j, uint8_t* success) {
-  __shared__ double s_tsj[kMaxSeg][32];
-  __shared__ double s_jv[kMaxSeg][32];
-  __shared__ int2 s_nf[kMaxSeg][32];
+  __shared__ double s_tab[kMaxSeg][4][32];  // per-lane segment table, [entry][word][lane]
   const int dof = P.dof;
   const int lane = threadIdx.x;
-  const SegTableT<32> T{&s_tsj[0][lane], &s_jv[0][lane], &s_nf[0][lane]};
+  const SegTableT<32> T{&s_tab[0][0][lane]};
   const int64_t rows = n * dof;
   const int64_t r = (int64_t)blockIdx.x * 32 + lane;
   if (r >= rows) return;
@@ -526,23 +524,30 @@ ltp_sample_tm_kernel(const __grid_constant__ PlannerParams P, int64_t n, const d
     T.build(R, n_run);
     C.begin(R);
   }
-  double* qo = q + r; double* vo = v + r; double* ao = a + r; double* jo = j + r;
-  double q_last = 0.0;
+  char* qb = reinterpret_cast<char*>(q);
+  char* vb = reinterpret_cast<char*>(v);
+  char* ab = reinterpret_cast<char*>(a);
+  char* jb = reinterpret_cast<char*>(j);
+  OffT off = (OffT)r * 8;
+  const OffT step = (OffT)rows * 8;
   int i = 0;
 #pragma unroll 4
   for (; i < n_out; ++i) {
     double jj, aa, vv, qq;
     C.step(T, i, jj, aa, vv, qq);
-    if (i == len - 1) q_last = qq;
-    store1(qo, qq); store1(vo, vv); store1(ao, aa); store1(jo, jj);
-    qo += rows; vo += rows; ao += rows; jo += rows;
+    store1(reinterpret_cast<double*>(qb + off), qq);
+    store1(reinterpret_cast<double*>(vb + off), vv);
+    store1(reinterpret_cast<double*>(ab + off), aa);
+    store1(reinterpret_cast<double*>(jb + off), jj);
+    off += step;
   }
   for (; i < n_run; ++i) {  // clipped horizon: run on to the true end for the limit check
     double jj, aa, vv, qq;
     C.step(T, i, jj, aa, vv, qq);
-    if (i == len - 1) q_last = qq;
   }
-  if (q_last < L.q_min || q_last > L.q_max) clear_flag(success, p);  // cc:60
+  // cc:60. The position is constant from the last switching sample on (v is pinned to 0), so
+  // the value after the last computed sample (index >= traj_len - 1) is q[traj_len - 1].
+  if (C.q < L.q_min || C.q > L.q_max) clear_flag(success, p);
 }
 
 // [dof][7] host-style times -> [7][dof][1] is trivial on the host; nothing to do on device.
@@ -858,8 +863,14 @@ int ltp_sample_batch(ltp_planner* p, int64_t n, const double* q_0, const double*
     cudaStream_t st = (cudaStream_t)stream;
     LTP_CUDA(cudaMemcpyAsync(success, sol->reached, (size_t)n, cudaMemcpyDeviceToDevice, st));
     const int64_t rows = n * dof;
-    ltp_sample_tm_kernel<<<(unsigned)((rows + 31) / 32), 32, 0, st>>>(p->params, n, q_0, v_0, a_0, to_dev(sol),
-                                                                     horizon, q, v, a, j, success);
+    const int64_t samples = horizon > 0 ? horizon : stride;
+    const unsigned grid = (unsigned)((rows + 31) / 32);
+    if ((double)rows * 8.0 * (double)(samples + 1) < 4294967296.0)
+      ltp_sample_tm_kernel<uint32_t><<<grid, 32, 0, st>>>(p->params, n, q_0, v_0, a_0, to_dev(sol), horizon, q,
+                                                           v, a, j, success);
+    else
+      ltp_sample_tm_kernel<uint64_t><<<grid, 32, 0, st>>>(p->params, n, q_0, v_0, a_0, to_dev(sol), horizon, q,
+                                                           v, a, j, success);
     p->launches++;
     LTP_CUDA(cudaGetLastError());
     return LTP_OK;

@@ -25,10 +25,7 @@
 
 #include <math.h>
 #include <stdint.h>
-
-#ifndef __CUDACC__
-struct int2 { int x, y; };  // host build of the device math (tests/host_shadow.cc)
-#endif
+#include <string.h>
 
 #ifdef __CUDACC__
 #define LTP_HD __host__ __device__ __forceinline__
@@ -1032,17 +1029,41 @@ struct RowSampler {
   }
 };
 
-// The row cut into pieces of constant jerk and constant update rule. The table is addressed
-// with a compile-time stride so that the kernel can keep one column per lane in shared
-// memory ([entry][lane], conflict-free for any mix of entry indices) while the host build
-// uses plain arrays (stride 1).
+// The row cut into pieces of constant jerk and constant update rule. Entry m holds four
+// 64-bit words; word w of entry m lives at base[(4*m + w) * STRIDE], so the kernel can keep
+// one column per lane in shared memory ([entry][word][lane], conflict-free for any mix of
+// entry indices) while the host build uses a plain array (STRIDE 1).
+//   word 0  Ts * jerk of the piece (0 where the acceleration is pinned to 0)
+//   word 1  jerk value that is emitted
+//   word 2  low 32 bits: first sample index of the NEXT piece; high 32 bits: 1 if the
+//           velocity is overridden with v_drive*dir (cc:822-823)
+//   word 3  1.0, or 0.0 from the sample after the last switching time on, where the
+//           reference pins a and v to exactly 0 (cc:817-829)
+LTP_HD double seg_pack(int next, int cruise) {
+  const long long b = (long long)(((unsigned long long)(unsigned)cruise << 32) | (unsigned)next);
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double(b);
+#else
+  double d;
+  memcpy(&d, &b, 8);
+  return d;
+#endif
+}
+LTP_HD void seg_unpack(double d, int& next, bool& cruise) {
+#ifdef __CUDA_ARCH__
+  next = __double2loint(d);
+  cruise = __double2hiint(d) != 0;
+#else
+  long long b;
+  memcpy(&b, &d, 8);
+  next = (int)(unsigned)(b & 0xffffffffll);
+  cruise = ((unsigned long long)b >> 32) != 0;
+#endif
+}
+
 template <int STRIDE>
 struct SegTableT {
-  double* tsj;   // Ts * jerk of the piece (0 where the acceleration is pinned to 0)
-  double* jv;    // jerk value that is emitted
-  int2* nf;      // .x = first sample index of the NEXT piece, .y = flags:
-                 //   bit0: a = v = 0 (past the last switching time, cc:817-829)
-                 //   bit1: v = v_drive*dir (cruise override, cc:822-823)
+  double* base;
 
   LTP_HD void build(const RowSampler& R, int limit) const {
     int cur = 0;
@@ -1051,23 +1072,24 @@ struct SegTableT {
       const int at = cur < limit ? cur : 0;  // entries past the end are never entered
       const double j = R.jerk_at(at);
       const bool az = R.a_zero(at);
-      const int fl = (az ? 1 : 0) | (R.v_cruise(at) ? 2 : 0);
+      const int vc = R.v_cruise(at) ? 1 : 0;
       if (cur < limit) {
         cur = R.next_break(cur);
         if (cur >= limit) cur = 0x7fffffff;
       }
-      jv[m * STRIDE] = j;
-      tsj[m * STRIDE] = az ? 0.0 : R.Ts * j;
-      int2 e;
-      e.x = cur;
-      e.y = fl;
-      nf[m * STRIDE] = e;
+      double* e = base + (4 * m) * STRIDE;
+      e[0] = az ? 0.0 : R.Ts * j;
+      e[STRIDE] = j;
+      e[2 * STRIDE] = seg_pack(cur, vc);
+      e[3 * STRIDE] = az ? 0.0 : 1.0;
     }
   }
 };
 
-// Streaming state of one row. step() is branch-free: the piece index advances by a compare,
-// and the (three) table words of the current piece are re-read every sample.
+// Streaming state of one row. step() is branch-free: the piece index advances by a compare
+// and the four table words of the current piece are re-read every sample. The two fma()
+// calls multiply by exactly 1.0 or 0.0, so they round exactly like the reference's plain
+// additions (and produce its exact +0.0 once a and v are pinned).
 template <int STRIDE>
 struct SegCursorT {
   double Ts, vcruise, a, v, q;
@@ -1081,15 +1103,15 @@ struct SegCursorT {
 
   LTP_HD void step(const SegTableT<STRIDE>& T, int i, double& jo, double& ao, double& vo, double& qo) {
     m += (i == next) ? 1 : 0;
-    const double tsj = T.tsj[m * STRIDE];
-    const double jv = T.jv[m * STRIDE];
-    const int2 e = T.nf[m * STRIDE];
-    next = e.x;
-    const bool az = (e.y & 1) != 0, vc = (e.y & 2) != 0;
-    const double an = a + tsj;
-    a = az ? 0.0 : an;
-    const double vn = v + Ts * a;
-    const double vz = az ? 0.0 : vn;
+    const double* e = T.base + (4 * m) * STRIDE;
+    const double tsj = e[0];
+    const double jv = e[STRIDE];
+    bool vc;
+    seg_unpack(e[2 * STRIDE], next, vc);
+    const double keep = e[3 * STRIDE];
+    a = fma(a, keep, tsj);          // a + Ts*j, or 0
+    const double ta = Ts * a;
+    const double vz = fma(v, keep, ta);  // v + Ts*a, or 0
     v = vc ? vcruise : vz;
     q = q + Ts * v;
     jo = jv; ao = a; vo = v; qo = q;

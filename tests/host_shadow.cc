@@ -238,9 +238,8 @@ int shadow_get_trajectory(void* h, const double* t7, const double* dir, const un
   for (int jt = 0; jt < dof; ++jt) {
     RowSampler R;
     R.init(s->ts, s->lim[jt].j_max, t7 + 7 * jt, dir[jt], mod[jt], q_0[jt], v_0[jt], a_0[jt], v_drive[jt], len);
-    double tsj[kMaxSeg], jv[kMaxSeg];
-    int2 nf[kMaxSeg];
-    SegTableT<1> T{tsj, jv, nf};
+    double table[4 * kMaxSeg];
+    SegTableT<1> T{table};
     T.build(R, len);
     SegCursorT<1> C;
     C.begin(R);
