@@ -40,7 +40,8 @@ typedef enum {
 /* case byte (the reference emits no case id; encoding documented in DESIGN.md):
  *  low nibble 0 brake-only | 1..4 cruise phase exists (1: P2,P6; 2: no P2; 3: no P6; 4: none)
  *  | 5 no cruise phase (closed form) | 6 quartic #1 | 7 quartic #1 + P2 | 8 quartic #2
- *  | 14 degenerate zero return | 15 failure;  0x10 modified jerk profile; 0x20 both
+ *  | 13 failure at the final safety check (reference leaves t unwritten) | 14 degenerate
+ *  zero return | 15 failure (t zeroed);  0x10 modified jerk profile; 0x20 both
  *  re-insertions fired; 0x40 / 0x80 no-P2 / no-P6 branch taken.
  * ts_case: 0 slowest joint, 1..8 accepted attempt, 9 search failed (optimal times kept),
  *  255 plan aborted before time scaling. */

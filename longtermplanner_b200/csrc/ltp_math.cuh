@@ -40,7 +40,7 @@ namespace ltp {
 // case byte, identical to oracle/ltp_oracle.h (the reference itself emits no case id)
 enum : unsigned char {
   CASE_BRAKE_ONLY = 0, CASE_NOP4 = 5, CASE_Q1 = 6, CASE_Q1_P2 = 7, CASE_Q2 = 8,
-  CASE_DEGENERATE = 14, CASE_FAIL = 15,
+  CASE_FAIL_UNTOUCHED = 13, CASE_DEGENERATE = 14, CASE_FAIL = 15,
   F_MOD = 0x10, F_BOTH = 0x20, F_NOP2 = 0x40, F_NOP6 = 0x80
 };
 
@@ -615,7 +615,7 @@ LTP_HD int ost_body_t(const JointLimits& L, double Ts, const Prologue& P, double
 #pragma unroll
   for (int i = 0; i < 7; ++i) {
     if (T[i] < -eps) {
-      kase = CASE_FAIL | flags;
+      kase = CASE_FAIL_UNTOUCHED | flags;
       return OST_FAIL;
     } else if (T[i] < 0.0 && T[i] >= -eps) {
       T[i] = 0.0;

@@ -559,7 +559,7 @@ int ltpo_opt_switch_times(const ltpo_planner* L, int joint, double q_goal, doubl
   /* cc:340-348 */
   for (int i = 0; i < 7; ++i) {
     if (T[i] < -eps) {
-      *kase = LTPO_CASE_FAIL | flags;
+      *kase = LTPO_CASE_FAIL_UNTOUCHED | flags;
       return 0; /* t is NOT written (cc:344) */
     } else if (T[i] < 0.0 && T[i] >= -eps) {
       T[i] = 0.0;

@@ -27,13 +27,14 @@ extern "C" {
  *   low nibble: 0 BRAKE_ONLY cc:102-107 | 1..4 cruise phase exists (1: P2,P6; 2: no P2;
  *               3: no P6; 4: neither) | 5 no cruise phase, closed form cc:202-236 |
  *               6 quartic #1 cc:246-270 | 7 quartic #1 then P2 re-inserted cc:273-296 |
- *               8 quartic #2 cc:299-333 | 14 "should never occur" zero return (true) |
- *               15 failure (false)
+ *               8 quartic #2 cc:299-333 | 13 failure at the final safety check, t NOT written
+ *               (false, cc:340-344) | 14 "should never occur" zero return (true) |
+ *               15 failure with t zeroed (false, cc:195-199; also the time-scaling reset)
  *   0x10 modified jerk profile (cc:119-122)   0x20 both cc:273 and cc:299 fired
  *   0x40 no-P2 branch cc:131-137 was taken    0x80 no-P6 branch cc:153-159 was taken */
 enum {
   LTPO_CASE_BRAKE_ONLY = 0, LTPO_CASE_NOP4 = 5, LTPO_CASE_Q1 = 6, LTPO_CASE_Q1_P2 = 7,
-  LTPO_CASE_Q2 = 8, LTPO_CASE_DEGENERATE = 14, LTPO_CASE_FAIL = 15,
+  LTPO_CASE_Q2 = 8, LTPO_CASE_FAIL_UNTOUCHED = 13, LTPO_CASE_DEGENERATE = 14, LTPO_CASE_FAIL = 15,
   LTPO_F_MOD = 0x10, LTPO_F_BOTH = 0x20, LTPO_F_NOP2 = 0x40, LTPO_F_NOP6 = 0x80
 };
 /* ts_case: 0 slowest joint (not scaled, cc:44-46); 1..8 accepted attempt; 9 all failed

@@ -1,0 +1,36 @@
+"""The reference's own gtest source (tests/src/long_term_planner_tests.cc, unmodified, compiled
+where it lies by tests/build_rehosted_reference_tests.sh) linked against this repository's
+drop-in C++ class: OptBraking / OptSwitchTimes / TimeScaling known answers, the 27 end-to-end
+planTrajectory scenarios and both grid sweeps (29 890 and 99 167 x 6 points), every call going
+through the C ABI to the GPU. SURVEY.md 8(f) rank 1."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+BIN = os.path.join(HERE, "_build", "ref_tests_rehosted")
+
+
+def _run(filter_):
+    env = dict(os.environ, LTP_GTEST_FILTER=filter_)
+    r = subprocess.run([BIN], capture_output=True, text=True, env=env, timeout=1500)
+    tail = "\n".join(r.stdout.splitlines()[-25:])
+    assert r.returncode == 0, tail + "\n" + r.stderr[-2000:]
+    assert "0 tests failed" in r.stdout, tail
+    return r.stdout
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="rehosted reference test binary not built")
+@pytest.mark.parametrize("name", ["OptBrakingTest", "OptSwitchTimesTest", "TrajectoryTestV0", "TrajectoryTestV1",
+                                  "TrajectoryTestV2", "TimeScalingTest", "gridTestOneJoint"])
+def test_reference_gtest_case(name):
+    out = _run(name)
+    assert f"[       OK ] LongTermPlannerTest1DoF.{name}" in out
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="rehosted reference test binary not built")
+def test_reference_grid_time_scaling():
+    out = _run("GridTimeScalingTest")
+    assert "[       OK ] LongTermPlannerTest1DoF.GridTimeScalingTest" in out
