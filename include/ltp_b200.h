@@ -118,7 +118,9 @@ int ltp_solve_batch(ltp_planner* p, int64_t n, const double* q_goal, const doubl
 
 /* replaces LongTermPlanner::getTrajectory + the final joint-limit check
  * (reference long_term_planner.cc:58-61, 706-841) for n problems.
- *   horizon == 0: every problem writes exactly traj_len[p] samples;
+ *   horizon == 0: every problem writes exactly traj_len[p] samples, clipped to the sample
+ *                 capacity `stride` (traj_len[p] > stride tells the caller a row was clipped;
+ *                 the success flag still refers to the complete trajectory);
  *   horizon  > 0: every problem writes exactly `horizon` samples (clipped, or continued
  *                 with the recurrence's own steady state q_last, 0, 0, 0).
  * layout:

@@ -60,6 +60,18 @@ def build_probe_library(force: bool = False) -> str:
     return PROBELIB
 
 
+WORKLOADLIB = os.path.join(LIBDIR, "libltp_workload.so")
+
+
+def build_workload_library(force: bool = False) -> str:
+    """bench/test tooling: device-side workload generator + trajectory row statistics"""
+    os.makedirs(LIBDIR, exist_ok=True)
+    src = os.path.join(CSRC, "ltp_workload.cu")
+    if force or _stale(WORKLOADLIB, [src]):
+        subprocess.run([_nvcc(), *NVCC_FLAGS, src, "-o", WORKLOADLIB], check=True)
+    return WORKLOADLIB
+
+
 def build_host_library(force: bool = False) -> str:
     """g++ -> lib/liblong_term_planner.so: the C++ drop-in class over the C ABI."""
     os.makedirs(LIBDIR, exist_ok=True)

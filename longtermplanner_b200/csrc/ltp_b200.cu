@@ -420,7 +420,8 @@ ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, int ppb, c
       double t[7];
 #pragma unroll
       for (int k = 0; k < 7; ++k) t[k] = S.t_scaled[((int64_t)k * dof + jt) * n + p];
-      const int n_out = horizon > 0 ? horizon : len;  // samples stored
+      // samples stored: the fixed horizon, or the exact length clipped to the row capacity
+      const int n_out = horizon > 0 ? horizon : (len < stride ? len : (int)stride);
       const int n_run = n_out > len ? n_out : len;    // samples computed
       SegCursorT<32> C;
       {
@@ -493,8 +494,8 @@ template <typename OffT>
 __global__ void __launch_bounds__(32)
 ltp_sample_tm_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_0,
                      const double* __restrict__ v_0, const double* __restrict__ a_0, DeviceSolution S,
-                     int horizon, double* __restrict__ q, double* __restrict__ v, double* __restrict__ a,
-                     double* __restrict__ j, uint8_t* success) {
+                     int horizon, int64_t capacity, double* __restrict__ q, double* __restrict__ v,
+                     double* __restrict__ a, double* __restrict__ j, uint8_t* success) {
   __shared__ double s_tab[kMaxSeg][4][32];  // per-lane segment table, [entry][word][lane]
   const int dof = P.dof;
   const int lane = threadIdx.x;
@@ -515,7 +516,8 @@ ltp_sample_tm_kernel(const __grid_constant__ PlannerParams P, int64_t n, const d
   double t[7];
 #pragma unroll
   for (int k = 0; k < 7; ++k) t[k] = S.t_scaled[((int64_t)k * dof + jt) * n + p];
-  const int n_out = horizon > 0 ? horizon : len;  // samples stored
+  // samples stored: the fixed horizon, or the exact length clipped to the sample capacity
+  const int n_out = horizon > 0 ? horizon : (len < capacity ? len : (int)capacity);
   const int n_run = n_out > len ? n_out : len;    // samples computed
   SegCursorT<32> C;
   {
@@ -570,6 +572,12 @@ struct ltp_planner {
   int64_t d_work_capacity;
   int solve_mode;  // LTP_SOLVE_AUTO / LTP_SOLVE_GENERIC
   int sm_count;
+  // chunk pipeline of ltp_solve_host: two slots, each with its own stream, device
+  // buffers and work list, so that the copy-in of chunk k+1 and the copy-out of chunk k
+  // run on the two DMA engines at the same time as the kernels of the chunk between them
+  cudaStream_t pipe_stream[2];
+  void* pipe_buf[2];
+  size_t pipe_bytes[2];
 };
 
 namespace {
@@ -695,6 +703,11 @@ int ltp_create(ltp_planner** out, int device, int dof, double t_sample, const do
   p->d_work_capacity = 0;
   p->solve_mode = LTP_SOLVE_AUTO;
   p->sm_count = 148;
+  for (int i = 0; i < 2; ++i) {
+    p->pipe_stream[i] = nullptr;
+    p->pipe_buf[i] = nullptr;
+    p->pipe_bytes[i] = 0;
+  }
   std::memset(p->params.lim, 0, sizeof p->params.lim);
   if (dof > 0) {
     int rc = fill_limits(p->params, q_min, q_max, v_max, a_max, j_max);
@@ -746,6 +759,10 @@ void ltp_destroy(ltp_planner* p) {
     if (p->d_scratch) cudaFree(p->d_scratch);
     if (p->d_work) cudaFree(p->d_work);
     if (p->stream) cudaStreamDestroy(p->stream);
+    for (int i = 0; i < 2; ++i) {
+      if (p->pipe_buf[i]) cudaFree(p->pipe_buf[i]);
+      if (p->pipe_stream[i]) cudaStreamDestroy(p->pipe_stream[i]);
+    }
   }
   delete p;
 }
@@ -795,18 +812,11 @@ int ltp_time_scaling_batch(ltp_planner* p, int64_t n, const double* q_goal, cons
   return LTP_OK;
 }
 
-int ltp_solve_batch(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
-                    const double* v_0, const double* a_0, const ltp_solution* sol, void* stream) {
-  if (!p || n < 0 || p->params.dof < 1) return LTP_ERR_ARG;
-  if (n == 0) return LTP_OK;
-  if (!q_goal || !q_0 || !v_0 || !a_0 || !sol) return LTP_ERR_ARG;
-  if (!sol->t_scaled || !sol->dir || !sol->v_drive || !sol->mod || !sol->slowest || !sol->traj_len ||
-      !sol->reached)
-    return LTP_ERR_ARG;
-  if (n > 0x7fffffff) return LTP_ERR_ARG;  // problem indices travel as int32 in the work list
-  DeviceGuard g(p->device);
+// launches of stages 1-3 on `st`. work: device buffer of n + 1 ints ([0] = count), only
+// touched in LTP_SOLVE_AUTO mode.
+static int solve_launch(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0, const double* v_0,
+                        const double* a_0, const ltp_solution* sol, int* work, cudaStream_t st) {
   const int dof = p->params.dof;
-  cudaStream_t st = (cudaStream_t)stream;
   const dim3 block(kTile, dof);
   const unsigned tiles = (unsigned)((n + kTile - 1) / kTile);
   const size_t smem = solve_smem_bytes(dof);
@@ -825,25 +835,37 @@ int ltp_solve_batch(ltp_planner* p, int64_t n, const double* q_goal, const doubl
     LTP_DISPATCH_W(ltp_solve_generic_kernel, tiles, p->params, n, q_goal, q_0, v_0, a_0, ds,
                    (const int*)nullptr, (const int*)nullptr);
   } else {
-    if (p->d_work_capacity < n) {
-      if (p->d_work) LTP_CUDA(cudaFree(p->d_work));
-      p->d_work = nullptr;
-      p->d_work_capacity = 0;
-      LTP_CUDA(cudaMalloc(&p->d_work, sizeof(int) * (size_t)(n + 1)));
-      p->d_work_capacity = n;
-    }
-    LTP_CUDA(cudaMemsetAsync(p->d_work, 0, sizeof(int), st));
-    LTP_DISPATCH_W(ltp_solve_fast_kernel, tiles, p->params, n, q_goal, q_0, v_0, a_0, ds, p->d_work + 1,
-                   p->d_work);
+    LTP_CUDA(cudaMemsetAsync(work, 0, sizeof(int), st));
+    LTP_DISPATCH_W(ltp_solve_fast_kernel, tiles, p->params, n, q_goal, q_0, v_0, a_0, ds, work + 1, work);
     // the work list is drained by a fixed-size grid-stride launch: its length never leaves
     // the device
     const unsigned g2 = tiles < (unsigned)(p->sm_count * 4) ? tiles : (unsigned)(p->sm_count * 4);
     LTP_DISPATCH_W(ltp_solve_generic_kernel, g2, p->params, n, q_goal, q_0, v_0, a_0, ds,
-                   (const int*)(p->d_work + 1), (const int*)p->d_work);
+                   (const int*)(work + 1), (const int*)work);
   }
 #undef LTP_DISPATCH_W
   LTP_CUDA(cudaGetLastError());
   return LTP_OK;
+}
+
+int ltp_solve_batch(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
+                    const double* v_0, const double* a_0, const ltp_solution* sol, void* stream) {
+  if (!p || n < 0 || p->params.dof < 1) return LTP_ERR_ARG;
+  if (n == 0) return LTP_OK;
+  if (!q_goal || !q_0 || !v_0 || !a_0 || !sol) return LTP_ERR_ARG;
+  if (!sol->t_scaled || !sol->dir || !sol->v_drive || !sol->mod || !sol->slowest || !sol->traj_len ||
+      !sol->reached)
+    return LTP_ERR_ARG;
+  if (n > 0x7fffffff) return LTP_ERR_ARG;  // problem indices travel as int32 in the work list
+  DeviceGuard g(p->device);
+  if (p->solve_mode != LTP_SOLVE_GENERIC && p->d_work_capacity < n) {
+    if (p->d_work) LTP_CUDA(cudaFree(p->d_work));
+    p->d_work = nullptr;
+    p->d_work_capacity = 0;
+    LTP_CUDA(cudaMalloc(&p->d_work, sizeof(int) * (size_t)(n + 1)));
+    p->d_work_capacity = n;
+  }
+  return solve_launch(p, n, q_goal, q_0, v_0, a_0, sol, p->d_work, (cudaStream_t)stream);
 }
 
 int ltp_sample_batch(ltp_planner* p, int64_t n, const double* q_0, const double* v_0, const double* a_0,
@@ -866,11 +888,11 @@ int ltp_sample_batch(ltp_planner* p, int64_t n, const double* q_0, const double*
     const int64_t samples = horizon > 0 ? horizon : stride;
     const unsigned grid = (unsigned)((rows + 31) / 32);
     if ((double)rows * 8.0 * (double)(samples + 1) < 4294967296.0)
-      ltp_sample_tm_kernel<uint32_t><<<grid, 32, 0, st>>>(p->params, n, q_0, v_0, a_0, to_dev(sol), horizon, q,
-                                                           v, a, j, success);
+      ltp_sample_tm_kernel<uint32_t><<<grid, 32, 0, st>>>(p->params, n, q_0, v_0, a_0, to_dev(sol), horizon, stride,
+                                                           q, v, a, j, success);
     else
-      ltp_sample_tm_kernel<uint64_t><<<grid, 32, 0, st>>>(p->params, n, q_0, v_0, a_0, to_dev(sol), horizon, q,
-                                                           v, a, j, success);
+      ltp_sample_tm_kernel<uint64_t><<<grid, 32, 0, st>>>(p->params, n, q_0, v_0, a_0, to_dev(sol), horizon, stride,
+                                                           q, v, a, j, success);
     p->launches++;
     LTP_CUDA(cudaGetLastError());
     return LTP_OK;
@@ -891,6 +913,11 @@ int ltp_sample_batch(ltp_planner* p, int64_t n, const double* q_0, const double*
 
 // ---- host-buffer entry points ---------------------------------------------------------
 
+// Problems per chunk of the host-buffer pipeline: 2^16 problems are 15 MB in and 34 MB out
+// for 7 joints -- long enough for full-rate DMA, short enough that the pipeline fills and
+// drains in a few percent of a 2^20-problem call.
+static const int64_t kHostChunk = 1 << 16;
+
 int ltp_solve_host(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
                    const double* v_0, const double* a_0, const ltp_solution* hs) {
   if (!p || n < 0 || !q_goal || !q_0 || !v_0 || !a_0 || !hs || p->params.dof < 1) return LTP_ERR_ARG;
@@ -898,39 +925,72 @@ int ltp_solve_host(ltp_planner* p, int64_t n, const double* q_goal, const double
       !hs->reached)
     return LTP_ERR_ARG;
   if (n == 0) return LTP_OK;
+  if (n > 0x7fffffff) return LTP_ERR_ARG;
   DeviceGuard g(p->device);
   const int dof = p->params.dof;
-  const size_t dn = (size_t)dof * (size_t)n;
-  ltp_solution ds;
-  const size_t sol_bytes = carve_solution(nullptr, dof, n, &ds);
-  const size_t in_bytes = up(dn * 8, 256);
-  int rc = ensure_scratch(p, sol_bytes + 4 * in_bytes);
-  if (rc != LTP_OK) return rc;
-  unsigned char* base = (unsigned char*)p->d_scratch;
-  double* d_in[4];
-  for (int i = 0; i < 4; ++i) d_in[i] = (double*)(base + i * in_bytes);
-  carve_solution(base + 4 * in_bytes, dof, n, &ds);
-  if (!hs->t_opt) ds.t_opt = nullptr;
-  if (!hs->opt_case) ds.opt_case = nullptr;
-  if (!hs->ts_case) ds.ts_case = nullptr;
-  if (!hs->final_case) ds.final_case = nullptr;
-  cudaStream_t st = p->stream;
+  // Chunks of problems go through two pipeline slots (own stream, own device buffers, own
+  // work list). Within a slot everything is stream-ordered: copy-in, the solve kernels,
+  // copy-out, then the slot's next chunk. The two slots overlap each other, so the
+  // host->device and device->host DMA engines and the SMs are busy at the same time and the
+  // call approaches the slower PCIe direction instead of the sum of the three stages.
+  // A joint-major host array x[row * n + problem] restricted to a chunk is `rows` pieces of
+  // c values at a pitch of n values: one 2-D copy per array.
+  const int64_t c_max = n < kHostChunk ? n : kHostChunk;
+  const int slots = n > c_max ? 2 : 1;
+  ltp_solution ds[2];
+  double* d_in[2][4];
+  int* d_work[2];
+  const size_t in_bytes = up((size_t)dof * (size_t)c_max * 8, 256);
+  const size_t sol_bytes = carve_solution(nullptr, dof, c_max, &ds[0]);
+  const size_t work_bytes = up(sizeof(int) * (size_t)(c_max + 1), 256);
+  const size_t need = 4 * in_bytes + sol_bytes + work_bytes;
+  for (int s = 0; s < slots; ++s) {
+    if (!p->pipe_stream[s]) LTP_CUDA(cudaStreamCreateWithFlags(&p->pipe_stream[s], cudaStreamNonBlocking));
+    if (p->pipe_bytes[s] < need) {
+      if (p->pipe_buf[s]) LTP_CUDA(cudaFree(p->pipe_buf[s]));
+      p->pipe_buf[s] = nullptr;
+      p->pipe_bytes[s] = 0;
+      LTP_CUDA(cudaMalloc(&p->pipe_buf[s], need));
+      p->pipe_bytes[s] = need;
+    }
+    unsigned char* base = (unsigned char*)p->pipe_buf[s];
+    for (int i = 0; i < 4; ++i) d_in[s][i] = (double*)(base + i * in_bytes);
+    carve_solution(base + 4 * in_bytes, dof, c_max, &ds[s]);
+    d_work[s] = (int*)(base + 4 * in_bytes + sol_bytes);
+    if (!hs->t_opt) ds[s].t_opt = nullptr;
+    if (!hs->opt_case) ds[s].opt_case = nullptr;
+    if (!hs->ts_case) ds[s].ts_case = nullptr;
+    if (!hs->final_case) ds[s].final_case = nullptr;
+  }
   const double* h_in[4] = {q_goal, q_0, v_0, a_0};
-  for (int i = 0; i < 4; ++i) LTP_CUDA(cudaMemcpyAsync(d_in[i], h_in[i], dn * 8, cudaMemcpyHostToDevice, st));
-  rc = ltp_solve_batch(p, n, d_in[0], d_in[1], d_in[2], d_in[3], &ds, st);
-  if (rc != LTP_OK) return rc;
-  LTP_CUDA(cudaMemcpyAsync(hs->t_scaled, ds.t_scaled, 7 * dn * 8, cudaMemcpyDeviceToHost, st));
-  LTP_CUDA(cudaMemcpyAsync(hs->dir, ds.dir, dn * 8, cudaMemcpyDeviceToHost, st));
-  LTP_CUDA(cudaMemcpyAsync(hs->v_drive, ds.v_drive, dn * 8, cudaMemcpyDeviceToHost, st));
-  LTP_CUDA(cudaMemcpyAsync(hs->mod, ds.mod, dn, cudaMemcpyDeviceToHost, st));
-  LTP_CUDA(cudaMemcpyAsync(hs->slowest, ds.slowest, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  LTP_CUDA(cudaMemcpyAsync(hs->traj_len, ds.traj_len, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  LTP_CUDA(cudaMemcpyAsync(hs->reached, ds.reached, (size_t)n, cudaMemcpyDeviceToHost, st));
-  if (hs->t_opt) LTP_CUDA(cudaMemcpyAsync(hs->t_opt, ds.t_opt, 7 * dn * 8, cudaMemcpyDeviceToHost, st));
-  if (hs->opt_case) LTP_CUDA(cudaMemcpyAsync(hs->opt_case, ds.opt_case, dn, cudaMemcpyDeviceToHost, st));
-  if (hs->ts_case) LTP_CUDA(cudaMemcpyAsync(hs->ts_case, ds.ts_case, dn, cudaMemcpyDeviceToHost, st));
-  if (hs->final_case) LTP_CUDA(cudaMemcpyAsync(hs->final_case, ds.final_case, dn, cudaMemcpyDeviceToHost, st));
-  LTP_CUDA(cudaStreamSynchronize(st));
+  int64_t k = 0;
+  for (int64_t p0 = 0; p0 < n; p0 += c_max, ++k) {
+    const int s = (int)(k % slots);
+    const int64_t c = (n - p0) < c_max ? (n - p0) : c_max;
+    cudaStream_t st = p->pipe_stream[s];
+    const ltp_solution& d = ds[s];
+    for (int i = 0; i < 4; ++i)
+      LTP_CUDA(cudaMemcpy2DAsync(d_in[s][i], (size_t)c * 8, h_in[i] + p0, (size_t)n * 8, (size_t)c * 8, dof,
+                                 cudaMemcpyHostToDevice, st));
+    int rc = solve_launch(p, c, d_in[s][0], d_in[s][1], d_in[s][2], d_in[s][3], &d, d_work[s], st);
+    if (rc != LTP_OK) return rc;
+#define LTP_OUT2D(FIELD, ROWS, ELEM)                                                                   \
+  LTP_CUDA(cudaMemcpy2DAsync(hs->FIELD + p0, (size_t)n * (ELEM), d.FIELD, (size_t)c * (ELEM),           \
+                             (size_t)c * (ELEM), (ROWS), cudaMemcpyDeviceToHost, st))
+    LTP_OUT2D(t_scaled, 7 * dof, 8);
+    LTP_OUT2D(dir, dof, 8);
+    LTP_OUT2D(v_drive, dof, 8);
+    LTP_OUT2D(mod, dof, 1);
+    LTP_OUT2D(slowest, 1, 4);
+    LTP_OUT2D(traj_len, 1, 4);
+    LTP_OUT2D(reached, 1, 1);
+    if (hs->t_opt) LTP_OUT2D(t_opt, 7 * dof, 8);
+    if (hs->opt_case) LTP_OUT2D(opt_case, dof, 1);
+    if (hs->ts_case) LTP_OUT2D(ts_case, dof, 1);
+    if (hs->final_case) LTP_OUT2D(final_case, dof, 1);
+#undef LTP_OUT2D
+  }
+  for (int s = 0; s < slots; ++s) LTP_CUDA(cudaStreamSynchronize(p->pipe_stream[s]));
   return LTP_OK;
 }
 

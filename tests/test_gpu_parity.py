@@ -203,6 +203,26 @@ def test_host_entry_point_equals_device_entry_point():
         assert np.array_equal(a, b, equal_nan=True) if a.dtype.kind == "f" else np.array_equal(a, b), k
 
 
+@pytest.mark.parametrize("lim,n", [(W.FRANKA7, 3 * 65536 + 777), (W.REF_RANDOM6, 65536 + 1), (W.FRANKA12, 65536)])
+def test_host_entry_point_chunk_pipeline(lim, n):
+    """ltp_solve_host above one chunk (2^16 problems) runs a two-slot copy/solve/copy pipeline
+    with 2-D copies into the joint-major host arrays; ragged last chunk; pinned and pageable"""
+    qg, q0, v0, a0 = W.random_states(lim, n, 78)
+    ltp = _planner(lim)
+    ins = [jm(x) for x in (qg, q0, v0, a0)]
+    host = ltp.solve_host(*ins, with_cases=True)  # pageable numpy buffers
+    pinned = [torch.from_numpy(x).pin_memory().numpy() for x in ins]
+    host2 = ltp.solve_host(*pinned)
+    sol = ltp.solve(*[_dev(x) for x in ins], with_cases=True)
+    torch.cuda.synchronize()
+    for k in ("t_scaled", "dir", "v_drive", "mod", "slowest", "traj_len", "reached", "opt_case", "ts_case",
+              "final_case"):
+        a, b = host[k], getattr(sol, k).cpu().numpy()
+        assert np.array_equal(a, b, equal_nan=(a.dtype.kind == "f")), k
+        if host2.get(k) is not None:
+            assert np.array_equal(host2[k], b, equal_nan=(a.dtype.kind == "f")), k
+
+
 def test_layouts_agree_and_limit_violations_are_flagged():
     """both layouts hold the same samples; a plan that ends outside [q_min, q_max] reports
     success = 0 with the trajectory still written (reference cc:59-61)"""
