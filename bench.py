@@ -131,6 +131,15 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_facts():
+    """per-launch facts read off the committed ncu --set full capture (profiles/ncu_facts.json,
+    written by tools/ncu_summary.py --json); {} if the capture has not been made"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_facts.json")))
+    except Exception:
+        return {}
+
+
 def load_probe():
     from longtermplanner_b200 import _build
     path = _build.PROBELIB
@@ -195,20 +204,26 @@ def main():
     if rank == 0:
         clocks.start()
     launches0 = ltp.launches
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e_start.record()
     for k in range(args.steps):
-        evs[k][0].record()
         ltp.solve(*dev_in, out=sol)
-        evs[k][1].record()
     e_stop.record()
     barrier()
     total_ms = max_over_ranks(e_start.elapsed_time(e_stop))
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     gpu_launches = ltp.launches - launches0
     value = world * n * args.steps / (total_ms * 1e-3)
+    # the dominant kernel's own launch duration: CUDA events recorded by the library on the
+    # launching stream directly around each launch (ltp_set_profiling), K more steps
+    ltp.setProfiling(True)
+    for k in range(args.steps):
+        ltp.solve(*dev_in, out=sol)
+    fast_ms, fast_cnt = ltp.kernelTime("solve_fast")
+    gen_ms, gen_cnt = ltp.kernelTime("solve_generic")
+    ltp.setProfiling(False)
+    kernel_ms = fast_ms / max(fast_cnt, 1)
+    generic_kernel_ms = gen_ms / max(gen_cnt, 1)
 
     # ---- end to end through the host-buffer C-ABI entry point ------------------------------
     host_np = [t.numpy() for t in host_in]
@@ -251,12 +266,20 @@ def main():
         probe.ltp_probe_hbm_write_gbs(local, 3, C.byref(wgbs))
         fp64_peak = tf.value if tf.value > 0 else 37.0
         achieved_tf = (n / (kernel_ms * 1e-3)) * FLOP_PER_PLAN_7DOF / 1e12
+        ncu = ncu_facts()
+        alg_gbs = (n * (224 + 534) / (kernel_ms * 1e-3)) / 1e9
         extra["roofline"] = {
-            "kernel": "ltp_solve_kernel", "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
-            "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak, "traffic": None,
+            "kernel": "ltp_solve_fast_kernel", "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
+            "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
+            "traffic": ncu.get("ltp_solve_fast_kernel", {}).get("dram_bytes_per_launch"),
             "peak_source": "live DFMA probe (csrc/ltp_probe.cu); no FP64 figure in MEASURED_PEAKS.json",
             "algorithmic_flop_per_plan": FLOP_PER_PLAN_7DOF, "kernel_ms": kernel_ms,
-            "hbm_gbs_algorithmic": (n * (224 + 534) / (kernel_ms * 1e-3)) / 1e9}
+            "kernel_share_of_step": kernel_ms / (total_ms / args.steps),
+            "work_list_kernel_ms": generic_kernel_ms,
+            "timing": "CUDA events on the launching stream around each launch, mean of K launches",
+            "ncu_fp64_pipe_pct": ncu.get("ltp_solve_fast_kernel", {}).get("fp64_pipe_pct"),
+            "hbm": {"achieved": alg_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": alg_gbs / hbm_peak,
+                    "algorithmic_bytes_per_plan": 224 + 534, "peak_source": hbm_src}}
 
         # ---- sampler: configs[2], 4096 envs x 7 DoF, dense sampling to 2 s at 1 ms ----------
         if not args.no_sampler:
@@ -274,6 +297,8 @@ def main():
                     ltp.sample(d2[1], d2[2], d2[3], sol2, horizon=horizon, out=traj)
                 torch.cuda.synchronize()
                 ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(reps)]
+                ltp.setProfiling(True)
+                ltp.kernelTime("sample_time_major"), ltp.kernelTime("sample_rows")
                 for r in range(reps):
                     ev[r][0].record()
                     ltp.solve(*d2, out=sol2)
@@ -281,20 +306,26 @@ def main():
                     ltp.sample(d2[1], d2[2], d2[3], sol2, horizon=horizon, out=traj)
                     ev[r][2].record()
                 torch.cuda.synchronize()
+                k_ms, k_cnt = ltp.kernelTime("sample_time_major" if layout == "time_major" else "sample_rows")
+                ltp.setProfiling(False)
                 res[layout] = (float(np.mean([e[0].elapsed_time(e[1]) for e in ev])),
-                               float(np.mean([e[1].elapsed_time(e[2]) for e in ev])))
+                               float(np.mean([e[1].elapsed_time(e[2]) for e in ev])), k_ms / max(k_cnt, 1))
                 del traj
-            solve_ms, samp_ms = res["time_major"]
-            gbs = useful / (samp_ms * 1e-3) / 1e9
+            solve_ms, samp_ms, samp_kernel_ms = res["time_major"]
+            gbs = useful / (samp_kernel_ms * 1e-3) / 1e9
             extra["sampler"] = {
                 "workload": "configs[2]: 4096 envs x 7 DoF, fixed horizon 2001 samples (2 s at 1 ms), "
                             "output 1.84 GB per replan (larger than L2)",
                 "layout": "time-major (samples, n, dof) f64 tensors q, v, a, j",
                 "replan_ms": solve_ms + samp_ms, "solve_ms": solve_ms, "sample_ms": samp_ms,
-                "rows_layout_sample_ms": res["rows"][1],
-                "rows_layout_gbs": useful / (res["rows"][1] * 1e-3) / 1e9,
+                "sample_call_gbs": useful / (samp_ms * 1e-3) / 1e9,
+                "rows_layout_sample_ms": res["rows"][1], "rows_layout_kernel_ms": res["rows"][2],
+                "rows_layout_gbs": useful / (res["rows"][2] * 1e-3) / 1e9,
                 "roofline": {"kernel": "ltp_sample_tm_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
-                             "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                             "unit": "GB/s", "frac": gbs / hbm_peak,
+                             "traffic": ncu.get("ltp_sample_tm_kernel", {}).get("dram_bytes_per_launch"),
+                             "peak_source": hbm_src, "kernel_ms": samp_kernel_ms,
+                             "timing": "CUDA events on the launching stream around each launch, mean of 20",
                              "algorithmic_bytes_per_sample": 32, "bytes_per_launch": useful,
                              "write_only_probe_gbs": wgbs.value}}
 

@@ -7,6 +7,9 @@ import os
 
 from ._build import LIB
 
+# a differently built copy of the same library (kernel experiments); never a fallback
+LIB = os.environ.get("LTP_B200_LIB", LIB)
+
 if not os.path.exists(LIB):
     raise ImportError(
         f"{LIB} is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -34,7 +37,7 @@ def _sig(name, restype, *argtypes):
 
 
 EXPORTS = [
-    "ltp_create", "ltp_set_limits", "ltp_set_sample_time", "ltp_set_dof", "ltp_set_solve_mode", "ltp_get_dof", "ltp_get_device",
+    "ltp_create", "ltp_set_limits", "ltp_set_sample_time", "ltp_set_dof", "ltp_set_solve_mode", "ltp_set_profiling", "ltp_profile_read", "ltp_get_dof", "ltp_get_device",
     "ltp_destroy", "ltp_status_string", "ltp_last_cuda_error", "ltp_launch_count",
     "ltp_opt_braking_batch", "ltp_opt_switch_times_batch", "ltp_time_scaling_batch", "ltp_solve_batch",
     "ltp_sample_batch", "ltp_solve_host", "ltp_plan_host", "ltp_opt_braking_host",
@@ -46,6 +49,8 @@ set_limits = _sig("ltp_set_limits", C.c_int, vp, vp, vp, vp, vp, vp)
 set_sample_time = _sig("ltp_set_sample_time", C.c_int, vp, f64)
 set_dof = _sig("ltp_set_dof", C.c_int, vp, C.c_int)
 set_solve_mode = _sig("ltp_set_solve_mode", C.c_int, vp, C.c_int)
+set_profiling = _sig("ltp_set_profiling", C.c_int, vp, C.c_int)
+profile_read = _sig("ltp_profile_read", C.c_int, vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64), C.c_int)
 get_dof = _sig("ltp_get_dof", C.c_int, vp)
 get_device = _sig("ltp_get_device", C.c_int, vp)
 destroy = _sig("ltp_destroy", None, vp)

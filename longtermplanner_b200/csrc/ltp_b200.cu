@@ -139,8 +139,18 @@ __device__ __forceinline__ bool finish_problem(const SolveShared& sh, const Devi
   return defer;
 }
 
+// Register budget: the kernel is bound by FP64 dependency latency, so it is compiled for
+// ~28 resident warps per SM (measured on B200, 2^20 Franka problems: 7 joints 1.12 ms at
+// 128 registers / 14 warps, 1.04 ms at 80 / 21, 0.95 ms at 72 / 28; 12 joints 2.10 ms at
+// 128 / 12, 1.51 ms at 80 / 24, 1.52 ms at 56 / 36, 1.88 ms at 40 / 48).
+#ifndef LTP_FAST_WARPS
+#define LTP_FAST_WARPS 28
+#endif
+constexpr int fast_min_blocks(int maxw) {
+  return (LTP_FAST_WARPS + maxw / 2) / maxw > 0 ? (LTP_FAST_WARPS + maxw / 2) / maxw : 1;
+}
 template <int MAXW>
-__global__ void __launch_bounds__(kTile * MAXW)
+__global__ void __launch_bounds__(kTile * MAXW, fast_min_blocks(MAXW))
 ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_goal,
                       const double* __restrict__ q_0, const double* __restrict__ v_0,
                       const double* __restrict__ a_0, DeviceSolution S, int* __restrict__ work_list,
@@ -404,10 +414,10 @@ ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, int ppb, c
                   const double* __restrict__ v_0, const double* __restrict__ a_0, DeviceSolution S,
                   int horizon, int64_t stride, double* __restrict__ q, double* __restrict__ v,
                   double* __restrict__ a, double* __restrict__ j, uint8_t* success) {
-  __shared__ double s_tab[kMaxSeg][4][32];  // per-lane segment table, [entry][word][lane]
+  __shared__ __align__(16) double s_tab[kMaxSeg][32][2];  // per-lane segment table, [entry][lane][word]
   const int dof = P.dof;
   const int lane = threadIdx.x;
-  const SegTableT<32> T{&s_tab[0][0][lane]};
+  const SegTableT<64> T{&s_tab[0][lane][0]};
   const int slot = lane / dof, jt = lane - slot * dof;   // problem slot within the CTA, joint
   const int64_t p = (int64_t)blockIdx.x * ppb + slot;
   const bool valid = slot < ppb && p < n;
@@ -423,7 +433,7 @@ ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, int ppb, c
       // samples stored: the fixed horizon, or the exact length clipped to the row capacity
       const int n_out = horizon > 0 ? horizon : (len < stride ? len : (int)stride);
       const int n_run = n_out > len ? n_out : len;    // samples computed
-      SegCursorT<32> C;
+      SegCursorT<64> C;
       {
         RowSampler R;
         R.init(P.ts, L.j_max, t, S.dir[at], S.mod[at], q_0[at], v_0[at], a_0[at], S.v_drive[at], n_run);
@@ -475,6 +485,11 @@ ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, int ppb, c
 // interleaved ones. Measured on B200 (tools/experiments/store_pattern_probe.cu,
 // store_parallelism_probe.cu): ~6.0 TB/s for this pattern against ~4.3 TB/s for one
 // 32-byte sector per row per store at a 16 KB row stride.
+//
+// More warps per row tile (splitting the sample axis for the stores, with a compute-only
+// run-up per chunk) do not help: the pure-store kernel of this pattern tops out at
+// 5.9-6.05 TB/s with 1, 2, 4 or 8 warps per tile, and this kernel reaches 96 % of that with
+// one (tools/experiments/sampler_variants.cu).
 // success[] must have been initialised with reached[]; a row that ends outside its joint
 // limits clears its problem's flag.
 __device__ __forceinline__ void clear_flag(uint8_t* flags, int64_t p) {
@@ -496,10 +511,10 @@ ltp_sample_tm_kernel(const __grid_constant__ PlannerParams P, int64_t n, const d
                      const double* __restrict__ v_0, const double* __restrict__ a_0, DeviceSolution S,
                      int horizon, int64_t capacity, double* __restrict__ q, double* __restrict__ v,
                      double* __restrict__ a, double* __restrict__ j, uint8_t* success) {
-  __shared__ double s_tab[kMaxSeg][4][32];  // per-lane segment table, [entry][word][lane]
+  __shared__ __align__(16) double s_tab[kMaxSeg][32][2];  // per-lane segment table, [entry][lane][word]
   const int dof = P.dof;
   const int lane = threadIdx.x;
-  const SegTableT<32> T{&s_tab[0][0][lane]};
+  const SegTableT<64> T{&s_tab[0][lane][0]};
   const int64_t rows = n * dof;
   const int64_t r = (int64_t)blockIdx.x * 32 + lane;
   if (r >= rows) return;
@@ -519,7 +534,7 @@ ltp_sample_tm_kernel(const __grid_constant__ PlannerParams P, int64_t n, const d
   // samples stored: the fixed horizon, or the exact length clipped to the sample capacity
   const int n_out = horizon > 0 ? horizon : (len < capacity ? len : (int)capacity);
   const int n_run = n_out > len ? n_out : len;    // samples computed
-  SegCursorT<32> C;
+  SegCursorT<64> C;
   {
     RowSampler R;
     R.init(P.ts, L.j_max, t, S.dir[at], S.mod[at], q_0[at], v_0[at], a_0[at], S.v_drive[at], n_run);
@@ -532,10 +547,10 @@ ltp_sample_tm_kernel(const __grid_constant__ PlannerParams P, int64_t n, const d
   char* jb = reinterpret_cast<char*>(j);
   OffT off = (OffT)r * 8;
   const OffT step = (OffT)rows * 8;
+  double jj, aa, vv, qq;
   int i = 0;
 #pragma unroll 4
   for (; i < n_out; ++i) {
-    double jj, aa, vv, qq;
     C.step(T, i, jj, aa, vv, qq);
     store1(reinterpret_cast<double*>(qb + off), qq);
     store1(reinterpret_cast<double*>(vb + off), vv);
@@ -543,13 +558,21 @@ ltp_sample_tm_kernel(const __grid_constant__ PlannerParams P, int64_t n, const d
     store1(reinterpret_cast<double*>(jb + off), jj);
     off += step;
   }
-  for (; i < n_run; ++i) {  // clipped horizon: run on to the true end for the limit check
-    double jj, aa, vv, qq;
-    C.step(T, i, jj, aa, vv, qq);
-  }
   // cc:60. The position is constant from the last switching sample on (v is pinned to 0), so
   // the value after the last computed sample (index >= traj_len - 1) is q[traj_len - 1].
-  if (C.q < L.q_min || C.q > L.q_max) clear_flag(success, p);
+  double q_end = C.q;
+  if (i < n_run) {
+    // Clipped row: the check still refers to the complete trajectory. Jump to the end with
+    // the per-piece closed form; only if that lands within 1e-9 of a limit (it is accurate
+    // to ~1e-12) step through the remaining samples to get the reference's exact value.
+    q_end = C.peek_position(T, i, n_run);
+    const double band = 1e-9;
+    if (!(fabs(q_end - L.q_min) > band && fabs(q_end - L.q_max) > band)) {
+      for (; i < n_run; ++i) C.step(T, i, jj, aa, vv, qq);
+      q_end = C.q;
+    }
+  }
+  if (q_end < L.q_min || q_end > L.q_max) clear_flag(success, p);
 }
 
 // [dof][7] host-style times -> [7][dof][1] is trivial on the host; nothing to do on device.
@@ -559,6 +582,8 @@ ltp_sample_tm_kernel(const __grid_constant__ PlannerParams P, int64_t n, const d
 // ======================================================================================
 // C ABI
 // ======================================================================================
+constexpr int kProfRing = 64;  // timed launches kept between two ltp_profile_read calls
+
 struct ltp_planner {
   int device;
   PlannerParams params;
@@ -572,6 +597,15 @@ struct ltp_planner {
   int64_t d_work_capacity;
   int solve_mode;  // LTP_SOLVE_AUTO / LTP_SOLVE_GENERIC
   int sm_count;
+  // optional per-kernel timing (ltp_set_profiling): CUDA events recorded on the launching
+  // stream directly around the hot kernels, read back by ltp_profile_read
+  bool profiling;
+  struct Timed {
+    cudaEvent_t ev[kProfRing][2];
+    int head, pending;
+    double ms_sum;
+    int64_t count;
+  } timed[LTP_PROFILE_KERNELS];
   // chunk pipeline of ltp_solve_host: two slots, each with its own stream, device
   // buffers and work list, so that the copy-in of chunk k+1 and the copy-out of chunk k
   // run on the two DMA engines at the same time as the kernels of the chunk between them
@@ -643,6 +677,44 @@ int ensure_scratch(ltp_planner* p, size_t bytes) {
 
 size_t up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// fold the finished event pairs of one kernel slot into its sum (synchronises on them)
+void prof_drain(ltp_planner::Timed& t) {
+  for (int k = 0; k < t.pending; ++k) {
+    const int slot = (t.head - t.pending + k + 2 * kProfRing) % kProfRing;
+    float ms = 0.f;
+    if (cudaEventSynchronize(t.ev[slot][1]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, t.ev[slot][0], t.ev[slot][1]) == cudaSuccess) {
+      t.ms_sum += ms;
+      t.count++;
+    }
+  }
+  t.pending = 0;
+}
+
+// RAII bracket around one kernel launch: records an event pair on `st` when profiling is on
+struct ProfScope {
+  ltp_planner::Timed* t;
+  cudaStream_t st;
+  int slot;
+  ProfScope(ltp_planner* p, int which, cudaStream_t s) : t(nullptr), st(s), slot(0) {
+    if (!p->profiling) return;
+    t = &p->timed[which];
+    if (t->pending == kProfRing) prof_drain(*t);
+    slot = t->head;
+    if (!t->ev[slot][0]) {
+      cudaEventCreate(&t->ev[slot][0]);
+      cudaEventCreate(&t->ev[slot][1]);
+    }
+    cudaEventRecord(t->ev[slot][0], st);
+  }
+  ~ProfScope() {
+    if (!t) return;
+    cudaEventRecord(t->ev[slot][1], st);
+    t->head = (t->head + 1) % kProfRing;
+    t->pending++;
+  }
+};
+
 // carve a solution (all fields) out of a scratch block; returns bytes used
 size_t carve_solution(unsigned char* base, int dof, int64_t n, ltp_solution* s) {
   size_t off = 0;
@@ -703,6 +775,8 @@ int ltp_create(ltp_planner** out, int device, int dof, double t_sample, const do
   p->d_work_capacity = 0;
   p->solve_mode = LTP_SOLVE_AUTO;
   p->sm_count = 148;
+  p->profiling = false;
+  std::memset(p->timed, 0, sizeof p->timed);
   for (int i = 0; i < 2; ++i) {
     p->pipe_stream[i] = nullptr;
     p->pipe_buf[i] = nullptr;
@@ -748,6 +822,26 @@ int ltp_set_solve_mode(ltp_planner* p, int mode) {
   return LTP_OK;
 }
 
+int ltp_set_profiling(ltp_planner* p, int on) {
+  if (!p) return LTP_ERR_ARG;
+  p->profiling = on != 0;
+  return LTP_OK;
+}
+
+int ltp_profile_read(ltp_planner* p, int kernel, double* ms_sum, int64_t* launches, int reset) {
+  if (!p || kernel < 0 || kernel >= LTP_PROFILE_KERNELS) return LTP_ERR_ARG;
+  DeviceGuard g(p->device);
+  ltp_planner::Timed& t = p->timed[kernel];
+  prof_drain(t);
+  if (ms_sum) *ms_sum = t.ms_sum;
+  if (launches) *launches = t.count;
+  if (reset) {
+    t.ms_sum = 0.0;
+    t.count = 0;
+  }
+  return LTP_OK;
+}
+
 int ltp_get_dof(const ltp_planner* p) { return p ? p->params.dof : LTP_ERR_ARG; }
 int ltp_get_device(const ltp_planner* p) { return p ? p->device : LTP_ERR_ARG; }
 int64_t ltp_launch_count(const ltp_planner* p) { return p ? p->launches.load() : 0; }
@@ -759,6 +853,10 @@ void ltp_destroy(ltp_planner* p) {
     if (p->d_scratch) cudaFree(p->d_scratch);
     if (p->d_work) cudaFree(p->d_work);
     if (p->stream) cudaStreamDestroy(p->stream);
+    for (auto& t : p->timed)
+      for (auto& e : t.ev)
+        for (auto& x : e)
+          if (x) cudaEventDestroy(x);
     for (int i = 0; i < 2; ++i) {
       if (p->pipe_buf[i]) cudaFree(p->pipe_buf[i]);
       if (p->pipe_stream[i]) cudaStreamDestroy(p->pipe_stream[i]);
@@ -831,18 +929,34 @@ static int solve_launch(ltp_planner* p, int64_t n, const double* q_goal, const d
     else KERNEL<32><<<GRID, block, smem, st>>>(__VA_ARGS__);                                \
     p->launches++;                                                                          \
   } while (0)
+  // the closed-form kernel is compiled for the exact CTA size of the common arm sizes so that
+  // its register budget is the largest that still fits the intended number of CTAs per SM
+#define LTP_DISPATCH_FAST(GRID, ...)                                                        \
+  do {                                                                                      \
+    if (dof == 6) ltp_solve_fast_kernel<6><<<GRID, block, smem, st>>>(__VA_ARGS__);         \
+    else if (dof == 7) ltp_solve_fast_kernel<7><<<GRID, block, smem, st>>>(__VA_ARGS__);    \
+    else if (dof == 12) ltp_solve_fast_kernel<12><<<GRID, block, smem, st>>>(__VA_ARGS__);  \
+    else { LTP_DISPATCH_W(ltp_solve_fast_kernel, GRID, __VA_ARGS__); break; }               \
+    p->launches++;                                                                          \
+  } while (0)
   if (p->solve_mode == LTP_SOLVE_GENERIC) {
+    ProfScope ps(p, LTP_PROFILE_SOLVE_GENERIC, st);
     LTP_DISPATCH_W(ltp_solve_generic_kernel, tiles, p->params, n, q_goal, q_0, v_0, a_0, ds,
                    (const int*)nullptr, (const int*)nullptr);
   } else {
     LTP_CUDA(cudaMemsetAsync(work, 0, sizeof(int), st));
-    LTP_DISPATCH_W(ltp_solve_fast_kernel, tiles, p->params, n, q_goal, q_0, v_0, a_0, ds, work + 1, work);
+    {
+      ProfScope ps(p, LTP_PROFILE_SOLVE_FAST, st);
+      LTP_DISPATCH_FAST(tiles, p->params, n, q_goal, q_0, v_0, a_0, ds, work + 1, work);
+    }
     // the work list is drained by a fixed-size grid-stride launch: its length never leaves
     // the device
     const unsigned g2 = tiles < (unsigned)(p->sm_count * 4) ? tiles : (unsigned)(p->sm_count * 4);
+    ProfScope ps(p, LTP_PROFILE_SOLVE_GENERIC, st);
     LTP_DISPATCH_W(ltp_solve_generic_kernel, g2, p->params, n, q_goal, q_0, v_0, a_0, ds,
                    (const int*)(work + 1), (const int*)work);
   }
+#undef LTP_DISPATCH_FAST
 #undef LTP_DISPATCH_W
   LTP_CUDA(cudaGetLastError());
   return LTP_OK;
@@ -887,6 +1001,7 @@ int ltp_sample_batch(ltp_planner* p, int64_t n, const double* q_0, const double*
     const int64_t rows = n * dof;
     const int64_t samples = horizon > 0 ? horizon : stride;
     const unsigned grid = (unsigned)((rows + 31) / 32);
+    ProfScope ps(p, LTP_PROFILE_SAMPLE_TIME_MAJOR, st);
     if ((double)rows * 8.0 * (double)(samples + 1) < 4294967296.0)
       ltp_sample_tm_kernel<uint32_t><<<grid, 32, 0, st>>>(p->params, n, q_0, v_0, a_0, to_dev(sol), horizon, stride,
                                                            q, v, a, j, success);
@@ -900,6 +1015,7 @@ int ltp_sample_batch(ltp_planner* p, int64_t n, const double* q_0, const double*
   const int ppb = 32 / dof > 0 ? 32 / dof : 1;  // whole problems per one-warp CTA (dof <= 32)
   const unsigned grid = (unsigned)((n + ppb - 1) / ppb);
   const bool vec = (stride % 4 == 0) && aligned32(q) && aligned32(v) && aligned32(a) && aligned32(j);
+  ProfScope ps(p, LTP_PROFILE_SAMPLE_ROWS, (cudaStream_t)stream);
   if (vec)
     ltp_sample_kernel<true><<<grid, 32, 0, (cudaStream_t)stream>>>(p->params, n, ppb, q_0, v_0, a_0, to_dev(sol),
                                                                     horizon, stride, q, v, a, j, success);

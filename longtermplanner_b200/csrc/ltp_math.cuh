@@ -1029,18 +1029,19 @@ struct RowSampler {
   }
 };
 
-// The row cut into pieces of constant jerk and constant update rule. Entry m holds four
-// 64-bit words; word w of entry m lives at base[(4*m + w) * STRIDE], so the kernel can keep
-// one column per lane in shared memory ([entry][word][lane], conflict-free for any mix of
-// entry indices) while the host build uses a plain array (STRIDE 1).
-//   word 0  Ts * jerk of the piece (0 where the acceleration is pinned to 0)
-//   word 1  jerk value that is emitted
-//   word 2  low 32 bits: first sample index of the NEXT piece; high 32 bits: 1 if the
-//           velocity is overridden with v_drive*dir (cc:822-823)
-//   word 3  1.0, or 0.0 from the sample after the last switching time on, where the
-//           reference pins a and v to exactly 0 (cc:817-829)
-LTP_HD double seg_pack(int next, int cruise) {
-  const long long b = (long long)(((unsigned long long)(unsigned)cruise << 32) | (unsigned)next);
+// The row cut into pieces of constant jerk and constant update rule. Entry m of a row holds
+// two 64-bit words, adjacent and 16-byte aligned (one 128-bit load per sample); consecutive
+// entries of a row are ENTRY_STRIDE doubles apart, so the kernels keep one column per lane in
+// shared memory ([entry][lane][2], conflict-free per quarter-warp for any mix of entry
+// indices) while the host build uses a plain array (ENTRY_STRIDE 2).
+//   word 0  jerk of the piece (the value that is emitted)
+//   word 1  low 32 bits: first sample index of the NEXT piece; bit 32: the velocity is
+//           overridden with v_drive*dir (cc:822-823); bit 33: "live", cleared from the sample
+//           after the last switching time on, where the reference pins a and v to exactly 0
+//           (cc:817-829)
+LTP_HD double seg_pack(int next, int cruise, int live) {
+  const unsigned hi = (unsigned)cruise | ((unsigned)live << 1);
+  const long long b = (long long)(((unsigned long long)hi << 32) | (unsigned)next);
 #ifdef __CUDA_ARCH__
   return __longlong_as_double(b);
 #else
@@ -1049,21 +1050,23 @@ LTP_HD double seg_pack(int next, int cruise) {
   return d;
 #endif
 }
-LTP_HD void seg_unpack(double d, int& next, bool& cruise) {
+LTP_HD void seg_unpack(double d, int& next, bool& cruise, bool& live) {
 #ifdef __CUDA_ARCH__
   next = __double2loint(d);
-  cruise = __double2hiint(d) != 0;
+  const int hi = __double2hiint(d);
 #else
   long long b;
   memcpy(&b, &d, 8);
   next = (int)(unsigned)(b & 0xffffffffll);
-  cruise = ((unsigned long long)b >> 32) != 0;
+  const int hi = (int)((unsigned long long)b >> 32);
 #endif
+  cruise = (hi & 1) != 0;
+  live = (hi & 2) != 0;
 }
 
-template <int STRIDE>
+template <int ENTRY_STRIDE>
 struct SegTableT {
-  double* base;
+  double* base;  // entry 0 of this row
 
   LTP_HD void build(const RowSampler& R, int limit) const {
     int cur = 0;
@@ -1071,26 +1074,24 @@ struct SegTableT {
     for (int m = 0; m < kMaxSeg; ++m) {
       const int at = cur < limit ? cur : 0;  // entries past the end are never entered
       const double j = R.jerk_at(at);
-      const bool az = R.a_zero(at);
+      const int live = R.a_zero(at) ? 0 : 1;
       const int vc = R.v_cruise(at) ? 1 : 0;
       if (cur < limit) {
         cur = R.next_break(cur);
         if (cur >= limit) cur = 0x7fffffff;
       }
-      double* e = base + (4 * m) * STRIDE;
-      e[0] = az ? 0.0 : R.Ts * j;
-      e[STRIDE] = j;
-      e[2 * STRIDE] = seg_pack(cur, vc);
-      e[3 * STRIDE] = az ? 0.0 : 1.0;
+      double* e = base + m * ENTRY_STRIDE;
+      e[0] = j;
+      e[1] = seg_pack(cur, vc, live);
     }
   }
 };
 
 // Streaming state of one row. step() is branch-free: the piece index advances by a compare
-// and the four table words of the current piece are re-read every sample. The two fma()
-// calls multiply by exactly 1.0 or 0.0, so they round exactly like the reference's plain
-// additions (and produce its exact +0.0 once a and v are pinned).
-template <int STRIDE>
+// and the two table words of the current piece are re-read every sample. Arithmetic per
+// sample is exactly the reference's (cc:810-831): a + Ts*j, v + Ts*a, q + Ts*v with multiply
+// and add unfused, and the pinned values (0, 0 and v_drive*dir) selected, not computed.
+template <int ENTRY_STRIDE>
 struct SegCursorT {
   double Ts, vcruise, a, v, q;
   int m, next;
@@ -1101,20 +1102,56 @@ struct SegCursorT {
     next = 0x7fffffff;  // replaced by entry 0 on the first step (i = 0 never equals it)
   }
 
-  LTP_HD void step(const SegTableT<STRIDE>& T, int i, double& jo, double& ao, double& vo, double& qo) {
+  LTP_HD void step(const SegTableT<ENTRY_STRIDE>& T, int i, double& jo, double& ao, double& vo, double& qo) {
     m += (i == next) ? 1 : 0;
-    const double* e = T.base + (4 * m) * STRIDE;
-    const double tsj = e[0];
-    const double jv = e[STRIDE];
-    bool vc;
-    seg_unpack(e[2 * STRIDE], next, vc);
-    const double keep = e[3 * STRIDE];
-    a = fma(a, keep, tsj);          // a + Ts*j, or 0
-    const double ta = Ts * a;
-    const double vz = fma(v, keep, ta);  // v + Ts*a, or 0
-    v = vc ? vcruise : vz;
+    const double* e = T.base + m * ENTRY_STRIDE;
+#ifdef __CUDA_ARCH__
+    const double2 w = *reinterpret_cast<const double2*>(e);
+    const double jv = w.x, pk = w.y;
+#else
+    const double jv = e[0], pk = e[1];
+#endif
+    bool vc, live;
+    seg_unpack(pk, next, vc, live);
+    const double a1 = a + Ts * jv;
+    a = live ? a1 : 0.0;
+    const double v1 = v + Ts * a;
+    v = vc ? vcruise : (live ? v1 : 0.0);
     q = q + Ts * v;
     jo = jv; ao = a; vo = v; qo = q;
+  }
+
+  // Position after sample `end - 1`, starting from the state after sample `i - 1`, WITHOUT
+  // stepping: inside a piece the recurrence has the closed form
+  //   a_k = a + c k,  v_k = v + Ts (a k + c k(k+1)/2),  q_n = q + Ts (v n + Ts (a n(n+1)/2 + c n(n+1)(n+2)/6))
+  // (c = Ts * jerk; discrete sums, not the continuous polynomials). The result differs from
+  // the sequentially rounded one by ~1e-12, so it may only be used for decisions with a guard
+  // band (the final joint-limit check of a clipped row); the cursor itself is not advanced.
+  LTP_HD double peek_position(const SegTableT<ENTRY_STRIDE>& T, int i, int end) const {
+    double pa = a, pv = v, pq = q;
+    int pm = m, pnext = next;
+    while (i < end) {
+      pm += (i == pnext) ? 1 : 0;
+      const double* e = T.base + pm * ENTRY_STRIDE;
+      bool vc, live;
+      seg_unpack(e[1], pnext, vc, live);
+      const int stop = pnext < end ? pnext : end;
+      const double k = (double)(stop - i);
+      const double c = live ? Ts * e[0] : 0.0;
+      if (!live) pa = 0.0;
+      if (vc) {
+        pv = vcruise;
+        pq = pq + Ts * pv * k;
+      } else if (live) {
+        pq = pq + Ts * (pv * k + Ts * (pa * (k * (k + 1.0) * 0.5) + c * (k * (k + 1.0) * (k + 2.0) / 6.0)));
+        pv = pv + Ts * (pa * k + c * (k * (k + 1.0) * 0.5));
+      } else {
+        pv = 0.0;
+      }
+      pa = pa + c * k;
+      i = stop;
+    }
+    return pq;
   }
 };
 

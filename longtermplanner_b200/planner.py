@@ -122,6 +122,19 @@ class LongTermPlanner:
         """validation switch: run every problem through the generic kernel (same results)"""
         capi.check(capi.set_solve_mode(self._h, 1 if generic_only else 0), "ltp_set_solve_mode")
 
+    KERNELS = {"solve_fast": 0, "solve_generic": 1, "sample_time_major": 2, "sample_rows": 3}
+
+    def setProfiling(self, on: bool) -> None:
+        """bracket every launch of the hot kernels with CUDA events on the launching stream"""
+        capi.check(capi.set_profiling(self._h, 1 if on else 0), "ltp_set_profiling")
+
+    def kernelTime(self, kernel: str, reset: bool = True):
+        """-> (sum of launch durations in ms, number of launches) since the last reset"""
+        ms, cnt = C.c_double(0), capi.i64(0)
+        capi.check(capi.profile_read(self._h, self.KERNELS[kernel], C.byref(ms), C.byref(cnt), 1 if reset else 0),
+                   "ltp_profile_read")
+        return ms.value, int(cnt.value)
+
     @property
     def launches(self) -> int:
         return int(capi.launch_count(self._h))

@@ -5,6 +5,7 @@
 // GPU run costs minutes, and a formula typo should be caught before spending them.
 // Build: g++ -O2 -ffp-contract=off (no FMA contraction; explicit fma() stays exact).
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -238,15 +239,50 @@ int shadow_get_trajectory(void* h, const double* t7, const double* dir, const un
   for (int jt = 0; jt < dof; ++jt) {
     RowSampler R;
     R.init(s->ts, s->lim[jt].j_max, t7 + 7 * jt, dir[jt], mod[jt], q_0[jt], v_0[jt], a_0[jt], v_drive[jt], len);
-    double table[4 * kMaxSeg];
-    SegTableT<1> T{table};
+    alignas(16) double table[2 * kMaxSeg];
+    SegTableT<2> T{table};
     T.build(R, len);
-    SegCursorT<1> C;
+    SegCursorT<2> C;
     C.begin(R);
     for (int i = 0; i < len; ++i)
       C.step(T, i, j[jt * stride + i], a[jt * stride + i], v[jt * stride + i], q[jt * stride + i]);
   }
   return len;
+}
+
+// largest |peek_position(i -> len) - q[len-1]| over all joints and a set of start samples i:
+// the closed-form jump the time-major kernel uses for the limit check of clipped rows
+double shadow_peek_error(void* h, const double* t7, const double* dir, const unsigned char* mod,
+                         const double* q_0, const double* v_0, const double* a_0, const double* v_drive) {
+  Shadow* s = static_cast<Shadow*>(h);
+  const int dof = s->dof;
+  int len = 0;
+  for (int i = 0; i < dof; ++i) {
+    int li = samples_for(t7[7 * i + 6], s->ts);
+    len = li > len ? li : len;
+  }
+  double worst = 0.0;
+  for (int jt = 0; jt < dof; ++jt) {
+    RowSampler R;
+    R.init(s->ts, s->lim[jt].j_max, t7 + 7 * jt, dir[jt], mod[jt], q_0[jt], v_0[jt], a_0[jt], v_drive[jt], len);
+    alignas(16) double table[2 * kMaxSeg];
+    SegTableT<2> T{table};
+    T.build(R, len);
+    SegCursorT<2> C;
+    C.begin(R);
+    std::vector<double> peek(len + 1);
+    double jj, aa, vv, qq = q_0[jt];
+    for (int i = 0; i < len; ++i) {
+      if (i % 7 == 0 || i + 3 >= len) peek[i] = C.peek_position(T, i, len); else peek[i] = NAN;
+      C.step(T, i, jj, aa, vv, qq);
+    }
+    for (int i = 0; i < len; ++i)
+      if (peek[i] == peek[i]) {
+        const double e = std::fabs(peek[i] - qq);
+        worst = e > worst ? e : worst;
+      }
+  }
+  return worst;
 }
 
 // same rows by the sample-by-sample general rules (RowSampler::step); the segment machinery

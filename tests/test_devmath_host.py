@@ -87,6 +87,30 @@ def test_device_math_sampler_is_bit_exact():
                 assert bitdiff(b[k], a[k]) == 0, (lim.name, i, k)
 
 
+def test_closed_form_jump_to_the_end_of_a_row():
+    """peek_position (used for the limit check of clipped rows, with a 1e-9 guard band) agrees
+    with the stepped recurrence to 1e-11 from any start sample"""
+    import ctypes
+    f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
+    u8p = np.ctypeslib.ndpointer(np.uint8, flags="C")
+    for lim, n, seed in ((W.FRANKA7, 60, 231), (W.REF_RANDOM6, 200, 232)):
+        qg, q0, v0, a0 = W.random_states(lim, n, seed)
+        P, S = OraclePort.from_limits(lim), Shadow.from_limits(lim)
+        fn = S.lib.shadow_peek_error
+        fn.restype = ctypes.c_double
+        fn.argtypes = [ctypes.c_void_p, f64p, f64p, u8p, f64p, f64p, f64p, f64p]
+        s = P.solve(qg, q0, v0, a0)
+        worst = 0.0
+        for i in range(n):
+            if not s["reached"][i]:
+                continue
+            worst = max(worst, fn(S.h, np.ascontiguousarray(s["t_scaled"][i]), np.ascontiguousarray(s["dir"][i]),
+                                  np.ascontiguousarray(s["mod"][i]), np.ascontiguousarray(q0[i]),
+                                  np.ascontiguousarray(v0[i]), np.ascontiguousarray(a0[i]),
+                                  np.ascontiguousarray(s["v_drive"][i])))
+        assert worst < 1e-11, (lim.name, worst)
+
+
 def test_device_math_on_reference_time_scaling_grid():
     lim = W.REF_GRID
     P, S = OraclePort.from_limits(lim), Shadow.from_limits(lim)

@@ -1,5 +1,5 @@
 """Condense an .ncu-rep (read here, no GPU needed) into the handful of numbers the roofline
-discussion uses. Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [> profiles/xxx.txt]"""
+discussion uses. Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--json profiles/ncu_facts.json] [> profiles/xxx.txt]"""
 import csv
 import subprocess
 import sys
@@ -36,7 +36,12 @@ KEYS = [
 ]
 
 
-def main(path):
+def to_bytes(value, unit):
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    return float(value.replace(",", "")) * scale.get(unit, 1)
+
+
+def main(path, json_out=None):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -44,6 +49,7 @@ def main(path):
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")].split("(")[0].replace("void <unnamed>::", "")
         seen.setdefault(name, []).append(r)
+    facts = {}
     for name, rs in seen.items():
         di = hdr.index("gpu__time_duration.sum")
         r = max(rs, key=lambda x: float(x[di]))  # the largest launch of each kernel
@@ -53,7 +59,21 @@ def main(path):
                 i = hdr.index(k)
                 print(f"  {label:34s} {r[i]:>16s} {units[i]}")
         print()
+        if json_out:
+            g = lambda k: (r[hdr.index(k)], units[hdr.index(k)])
+            facts[name.split("<")[0]] = {
+                "dram_bytes_per_launch": to_bytes(*g("dram__bytes_read.sum")) + to_bytes(*g("dram__bytes_write.sum")),
+                "dram_read_bytes": to_bytes(*g("dram__bytes_read.sum")),
+                "dram_write_bytes": to_bytes(*g("dram__bytes_write.sum")),
+                "duration": " ".join(g("gpu__time_duration.sum")),
+                "fp64_pipe_pct": float(g("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active")[0]),
+                "grid": r[hdr.index("launch__grid_size")], "block": r[hdr.index("launch__block_size")],
+                "registers": r[hdr.index("launch__registers_per_thread")],
+                "source": "ncu --set full --clock-control none, " + path.split("/")[-1] + " (longest launch of the kernel)"}
+    if json_out:
+        import json
+        json.dump(facts, open(json_out, "w"), indent=1)
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], sys.argv[3] if len(sys.argv) > 3 and sys.argv[2] == "--json" else None)

@@ -1,0 +1,39 @@
+"""Kernel-level timing of the solve (configs[1], 2^20 Franka problems) and of the time-major
+sampler (configs[2]) through the library's own event hooks. Used to compare builds:
+  LTP_B200_LIB=/path/to/variant.so python tools/solve_timing.py"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from longtermplanner_b200 import LongTermPlanner, workloads as W  # noqa: E402
+
+lim = W.FRANKA7 if len(sys.argv) < 2 or sys.argv[1] != "12" else W.FRANKA12
+n = 1 << 20
+ltp = LongTermPlanner(lim.dof, lim.t_sample, *lim.arrays(), device=0)
+ins = [torch.from_numpy(W.to_joint_major(x)).cuda() for x in W.random_states(lim, n, W.SEEDS[2])]
+sol = ltp.alloc_solution(n)
+for _ in range(3):
+    ltp.solve(*ins, out=sol)
+ltp.setProfiling(True)
+for _ in range(20):
+    ltp.solve(*ins, out=sol)
+ms, cnt = ltp.kernelTime("solve_fast")
+ms2, cnt2 = ltp.kernelTime("solve_generic")
+chk = int(sol.traj_len.sum().item())
+print(f"{os.environ.get('LTP_B200_LIB', 'default')}: dof {lim.dof} solve_fast {ms / cnt:.4f} ms -> {n / (ms / cnt) / 1e3:.1f} M plans/s; "
+      f"generic {ms2 / cnt2:.4f} ms; traj_len checksum {chk}", flush=True)
+if lim.dof == 7:
+    n2, H = 4096, 2001
+    ins2 = [torch.from_numpy(W.to_joint_major(x)).cuda() for x in W.random_states(lim, n2, W.SEEDS[3])]
+    sol2 = ltp.solve(*ins2)
+    traj = ltp.alloc_trajectories(n2, H, "time_major")
+    ltp.setProfiling(False)
+    for _ in range(3):
+        ltp.sample(ins2[1], ins2[2], ins2[3], sol2, horizon=H, out=traj)
+    ltp.setProfiling(True)
+    for _ in range(20):
+        ltp.sample(ins2[1], ins2[2], ins2[3], sol2, horizon=H, out=traj)
+    ms, cnt = ltp.kernelTime("sample_time_major")
+    print(f"   sampler time-major {ms / cnt:.4f} ms -> {n2 * 7 * H * 32 / (ms / cnt) / 1e6:.0f} GB/s", flush=True)
