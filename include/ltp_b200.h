@@ -151,6 +151,59 @@ int ltp_sample_batch(ltp_planner* p, int64_t n, const double* q_0, const double*
                      int64_t stride, double* q, double* v, double* a, double* j, uint8_t* success,
                      void* stream);
 
+/* ---- streaming: more trajectories than fit in memory -------------------------------- */
+
+/* One chunk of a streamed run, as seen by the consumer. Everything is a DEVICE pointer into
+ * a slot of the planner's ring and stays valid until work enqueued on `stream` by the
+ * consumer has run (the slot is reused by the chunk after next, on the same stream). Inputs
+ * and solution are joint-major over `count` problems; q, v, a, j are time-major
+ * (capacity, count, dof). */
+typedef struct {
+  int64_t first, count;        /* problems first .. first + count - 1 of the run */
+  int64_t capacity;            /* sample capacity of the trajectory tensors */
+  int32_t horizon;
+  ltp_solution solution;
+  const double *q_goal, *q_0, *v_0, *a_0;
+  const double *q, *v, *a, *j;
+  const uint8_t* success;
+} ltp_chunk;
+
+/* called on the host right after a chunk's kernels were enqueued; enqueue the consuming work
+ * on `stream` (do not synchronise). Non-zero return aborts the run. */
+typedef int (*ltp_chunk_consumer)(void* user, const ltp_chunk* chunk, void* stream);
+
+typedef struct {
+  int64_t problems, chunks;
+  int64_t reached, success;    /* problems that were planned / ended inside the joint limits */
+  int64_t clipped;             /* problems whose trajectory is longer than what was written */
+  int64_t samples;             /* (problem, joint, sample) triples written */
+  int64_t bytes;               /* samples * 32 (q, v, a, j as f64) */
+  int64_t max_traj_len;
+} ltp_stream_stats;
+
+/* planTrajectory for n problems whose trajectories do not fit in memory at once (reference
+ * long_term_planner.cc:7-63 per problem). Inputs: device, joint-major [dof][n]. The run is cut
+ * into chunks of `chunk` problems; each chunk is solved and sampled (time-major, `horizon`
+ * and `capacity` as in ltp_sample_batch) into one of two ring slots on its own stream, handed
+ * to `consume` (may be NULL), and the slot is recycled. Synchronises before returning;
+ * `stats` (may be NULL) receives the totals, accumulated on the device. */
+int ltp_plan_stream(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
+                    const double* v_0, const double* a_0, int64_t chunk, int32_t horizon,
+                    int64_t capacity, ltp_chunk_consumer consume, void* user,
+                    ltp_stream_stats* stats);
+
+/* Receding-horizon replanning (the reference's stated use, README.md:10-13: a new target
+ * arrives before the previous one is reached): the state `tick` samples into the current
+ * time-major trajectories (sample index tick, i.e. time (tick + 1) * t_sample, reference
+ * cc:810-812) becomes the next start state, joint-major [dof][n]. traj_len (may be NULL for
+ * fixed-horizon trajectories, which hold every sample up to the horizon): [n], the tick is
+ * limited to traj_len - 1 per problem. valid (may be NULL): [n], problems with 0 keep their
+ * q_0/v_0/a_0. clamp != 0 pulls a state that overshoots a limit by
+ * the recurrence's rounding back inside what checkInputs accepts (reference cc:68-77). */
+int ltp_advance_batch(ltp_planner* p, int64_t n, int32_t tick, int32_t clamp, const int32_t* traj_len,
+                      const uint8_t* valid, const double* q, const double* v, const double* a,
+                      double* q_0, double* v_0, double* a_0, void* stream);
+
 /* ---- host-buffer entry points (what a caller without device buffers uses) ------------ */
 
 /* Stages 1-3 with HOST buffers: copies the four inputs in, solves, copies the requested

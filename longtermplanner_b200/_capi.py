@@ -40,9 +40,24 @@ EXPORTS = [
     "ltp_create", "ltp_set_limits", "ltp_set_sample_time", "ltp_set_dof", "ltp_set_solve_mode", "ltp_set_profiling", "ltp_profile_read", "ltp_get_dof", "ltp_get_device",
     "ltp_destroy", "ltp_status_string", "ltp_last_cuda_error", "ltp_launch_count",
     "ltp_opt_braking_batch", "ltp_opt_switch_times_batch", "ltp_time_scaling_batch", "ltp_solve_batch",
-    "ltp_sample_batch", "ltp_solve_host", "ltp_plan_host", "ltp_opt_braking_host",
+    "ltp_sample_batch", "ltp_plan_stream", "ltp_advance_batch", "ltp_solve_host", "ltp_plan_host", "ltp_opt_braking_host",
     "ltp_opt_switch_times_host", "ltp_time_scaling_host", "ltp_get_trajectory_host",
 ]
+
+class Chunk(C.Structure):
+    """ltp_chunk"""
+    _fields_ = [("first", i64), ("count", i64), ("capacity", i64), ("horizon", i32), ("solution", Solution),
+                ("q_goal", vp), ("q_0", vp), ("v_0", vp), ("a_0", vp), ("q", vp), ("v", vp), ("a", vp), ("j", vp),
+                ("success", vp)]
+
+
+class StreamStats(C.Structure):
+    """ltp_stream_stats"""
+    _fields_ = [(k, i64) for k in ("problems", "chunks", "reached", "success", "clipped", "samples", "bytes",
+                                   "max_traj_len")]
+
+
+CHUNK_CONSUMER = C.CFUNCTYPE(C.c_int, vp, C.POINTER(Chunk), vp)
 
 create = _sig("ltp_create", C.c_int, C.POINTER(vp), C.c_int, C.c_int, f64, vp, vp, vp, vp, vp)
 set_limits = _sig("ltp_set_limits", C.c_int, vp, vp, vp, vp, vp, vp)
@@ -66,6 +81,9 @@ solve_batch = _sig("ltp_solve_batch", C.c_int, vp, i64, vp, vp, vp, vp, C.POINTE
 sample_batch = _sig("ltp_sample_batch", C.c_int, vp, i64, vp, vp, vp, C.POINTER(Solution), i32, i32, i64, vp,
                     vp, vp, vp, vp, vp)
 LAYOUT_ROWS, LAYOUT_TIME_MAJOR = 0, 1
+plan_stream = _sig("ltp_plan_stream", C.c_int, vp, i64, vp, vp, vp, vp, i64, i32, i64, CHUNK_CONSUMER, vp,
+                   C.POINTER(StreamStats))
+advance_batch = _sig("ltp_advance_batch", C.c_int, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp)
 solve_host = _sig("ltp_solve_host", C.c_int, vp, i64, vp, vp, vp, vp, C.POINTER(Solution))
 plan_host = _sig("ltp_plan_host", C.c_int, vp, i64, vp, vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, vp,
                  C.POINTER(i64))

@@ -575,7 +575,94 @@ ltp_sample_tm_kernel(const __grid_constant__ PlannerParams P, int64_t n, const d
   if (q_end < L.q_min || q_end > L.q_max) clear_flag(success, p);
 }
 
-// [dof][7] host-style times -> [7][dof][1] is trivial on the host; nothing to do on device.
+// ------------------------------------------------------------------------------------
+// streaming driver: totals of one chunk, accumulated in device memory across chunks
+// ------------------------------------------------------------------------------------
+struct StreamTotals {  // mirrors ltp_stream_stats
+  long long problems, reached, success, clipped, samples, max_len;
+};
+
+__global__ void __launch_bounds__(256)
+ltp_chunk_totals_kernel(int64_t n, int dof, int horizon, int64_t capacity, const int32_t* __restrict__ traj_len,
+                        const uint8_t* __restrict__ reached, const uint8_t* __restrict__ success,
+                        StreamTotals* totals) {
+  long long rch = 0, suc = 0, clip = 0, smp = 0, mx = 0;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int len = traj_len[p];
+    const bool r = reached[p] != 0 && len > 0;
+    rch += reached[p] != 0;
+    suc += success[p] != 0;
+    if (r) {
+      const long long out = horizon > 0 ? horizon : (len < capacity ? len : capacity);
+      clip += (horizon > 0 ? len > horizon : len > capacity);
+      smp += out * dof;
+      mx = len > mx ? len : mx;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    rch += __shfl_down_sync(0xffffffffu, rch, o);
+    suc += __shfl_down_sync(0xffffffffu, suc, o);
+    clip += __shfl_down_sync(0xffffffffu, clip, o);
+    smp += __shfl_down_sync(0xffffffffu, smp, o);
+    const long long other = __shfl_down_sync(0xffffffffu, mx, o);
+    mx = other > mx ? other : mx;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd((unsigned long long*)&totals->reached, (unsigned long long)rch);
+    atomicAdd((unsigned long long*)&totals->success, (unsigned long long)suc);
+    atomicAdd((unsigned long long*)&totals->clipped, (unsigned long long)clip);
+    atomicAdd((unsigned long long*)&totals->samples, (unsigned long long)smp);
+    atomicMax(&totals->max_len, mx);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&totals->problems, (unsigned long long)n);
+}
+
+// ------------------------------------------------------------------------------------
+// receding-horizon replanning: the state reached `tick` samples into the current plans
+// becomes the start state of the next solve. Time-major trajectories (samples, n, dof) ->
+// joint-major [dof][n]. The forward-Euler samples may overshoot a limit by a few ulps (or by
+// the discretisation error of a sample); with clamp != 0 the state is pulled back inside what
+// checkInputs accepts (reference cc:68-77) so that the next plan is not rejected for it.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ltp_advance_kernel(const __grid_constant__ PlannerParams P, int64_t n, int tick, int clamp,
+                   const int32_t* __restrict__ traj_len, const uint8_t* __restrict__ valid,
+                   const double* __restrict__ q, const double* __restrict__ v, const double* __restrict__ a,
+                   double* __restrict__ q_0, double* __restrict__ v_0, double* __restrict__ a_0) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int jt = blockIdx.y;
+  if (p >= n) return;
+  const int64_t at = (int64_t)jt * n + p;
+  if (valid && !valid[p]) return;  // no plan: the environment keeps its state
+  const int dof = P.dof;
+  const JointLimits L = P.lim[jt];
+  // exact-length trajectories end at traj_len - 1; from there on the state is the final one
+  int at_sample = tick;
+  if (traj_len) {
+    const int len = traj_len[p];
+    if (len <= 0) return;
+    at_sample = tick < len ? tick : len - 1;
+  }
+  const int64_t src = ((int64_t)at_sample * n + p) * dof + jt;
+  double qq = q[src], vv = v[src], aa = a[src];
+  if (clamp) {
+    aa = fmin(fmax(aa, -L.a_max), L.a_max);
+    vv = fmin(fmax(vv, -L.v_max), L.v_max);
+    qq = fmin(fmax(qq, L.q_min), L.q_max);
+    // |v + a|a|/(2 j)| <= v_max (cc:74): shrink the acceleration towards the largest one
+    // from which the joint can still be stopped below v_max
+    const double room = L.v_max - fabs(vv);
+    if (fabs(vv + 0.5 * aa * fabs(aa) / L.j_max) > L.v_max && vv * aa > 0) {
+      double lim_a = sqrt(2.0 * L.j_max * (room > 0 ? room : 0.0));
+      lim_a = lim_a * (1.0 - 4.0 * kDblEps);
+      aa = aa > 0 ? fmin(aa, lim_a) : fmax(aa, -lim_a);
+    }
+  }
+  q_0[at] = qq;
+  v_0[at] = vv;
+  a_0[at] = aa;
+}
+
 
 }  // namespace
 
@@ -612,6 +699,10 @@ struct ltp_planner {
   cudaStream_t pipe_stream[2];
   void* pipe_buf[2];
   size_t pipe_bytes[2];
+  // ltp_plan_stream: ring of trajectory slots (grown on demand) and the device totals
+  void* ring_buf[2];
+  size_t ring_bytes[2];
+  StreamTotals* d_totals;
 };
 
 namespace {
@@ -781,7 +872,10 @@ int ltp_create(ltp_planner** out, int device, int dof, double t_sample, const do
     p->pipe_stream[i] = nullptr;
     p->pipe_buf[i] = nullptr;
     p->pipe_bytes[i] = 0;
+    p->ring_buf[i] = nullptr;
+    p->ring_bytes[i] = 0;
   }
+  p->d_totals = nullptr;
   std::memset(p->params.lim, 0, sizeof p->params.lim);
   if (dof > 0) {
     int rc = fill_limits(p->params, q_min, q_max, v_max, a_max, j_max);
@@ -852,6 +946,7 @@ void ltp_destroy(ltp_planner* p) {
     DeviceGuard g(p->device);
     if (p->d_scratch) cudaFree(p->d_scratch);
     if (p->d_work) cudaFree(p->d_work);
+    if (p->d_totals) cudaFree(p->d_totals);
     if (p->stream) cudaStreamDestroy(p->stream);
     for (auto& t : p->timed)
       for (auto& e : t.ev)
@@ -859,6 +954,7 @@ void ltp_destroy(ltp_planner* p) {
           if (x) cudaEventDestroy(x);
     for (int i = 0; i < 2; ++i) {
       if (p->pipe_buf[i]) cudaFree(p->pipe_buf[i]);
+      if (p->ring_buf[i]) cudaFree(p->ring_buf[i]);
       if (p->pipe_stream[i]) cudaStreamDestroy(p->pipe_stream[i]);
     }
   }
@@ -1107,6 +1203,123 @@ int ltp_solve_host(ltp_planner* p, int64_t n, const double* q_goal, const double
 #undef LTP_OUT2D
   }
   for (int s = 0; s < slots; ++s) LTP_CUDA(cudaStreamSynchronize(p->pipe_stream[s]));
+  return LTP_OK;
+}
+
+static int grow(void** buf, size_t* have, size_t need) {
+  if (*have >= need) return LTP_OK;
+  if (*buf) LTP_CUDA(cudaFree(*buf));
+  *buf = nullptr;
+  *have = 0;
+  LTP_CUDA(cudaMalloc(buf, need));
+  *have = need;
+  return LTP_OK;
+}
+
+int ltp_plan_stream(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0, const double* v_0,
+                    const double* a_0, int64_t chunk, int32_t horizon, int64_t capacity,
+                    ltp_chunk_consumer consume, void* user, ltp_stream_stats* stats) {
+  if (!p || n < 0 || chunk < 1 || chunk > 0x7fffffff || horizon < 0 || capacity < 1 ||
+      (horizon > 0 && capacity < horizon) || p->params.dof < 1)
+    return LTP_ERR_ARG;
+  if (stats) std::memset(stats, 0, sizeof *stats);
+  if (n == 0) return LTP_OK;
+  if (!q_goal || !q_0 || !v_0 || !a_0) return LTP_ERR_ARG;
+  DeviceGuard g(p->device);
+  const int dof = p->params.dof;
+  const int64_t c_max = n < chunk ? n : chunk;
+  const int slots = n > c_max ? 2 : 1;
+  // per slot: compact chunk inputs, solution, work list (pipe_buf) and the four trajectory
+  // fields + success flags (ring_buf), all reused by every second chunk
+  ltp_solution ds[2];
+  double* d_in[2][4];
+  int* d_work[2];
+  double* d_traj[2][4];
+  uint8_t* d_succ[2];
+  const size_t in_bytes = up((size_t)dof * (size_t)c_max * 8, 256);
+  const size_t sol_bytes = carve_solution(nullptr, dof, c_max, &ds[0]);
+  const size_t work_bytes = up(sizeof(int) * (size_t)(c_max + 1), 256);
+  const size_t field_bytes = up((size_t)capacity * (size_t)c_max * (size_t)dof * 8, 256);
+  const size_t succ_bytes = up((size_t)c_max, 256);
+  for (int s = 0; s < slots; ++s) {
+    if (!p->pipe_stream[s]) LTP_CUDA(cudaStreamCreateWithFlags(&p->pipe_stream[s], cudaStreamNonBlocking));
+    int rc = grow(&p->pipe_buf[s], &p->pipe_bytes[s], 4 * in_bytes + sol_bytes + work_bytes);
+    if (rc != LTP_OK) return rc;
+    rc = grow(&p->ring_buf[s], &p->ring_bytes[s], 4 * field_bytes + succ_bytes);
+    if (rc != LTP_OK) return rc;
+    unsigned char* base = (unsigned char*)p->pipe_buf[s];
+    for (int i = 0; i < 4; ++i) d_in[s][i] = (double*)(base + i * in_bytes);
+    carve_solution(base + 4 * in_bytes, dof, c_max, &ds[s]);
+    ds[s].t_opt = nullptr; ds[s].opt_case = nullptr; ds[s].ts_case = nullptr; ds[s].final_case = nullptr;
+    d_work[s] = (int*)(base + 4 * in_bytes + sol_bytes);
+    unsigned char* ring = (unsigned char*)p->ring_buf[s];
+    for (int i = 0; i < 4; ++i) d_traj[s][i] = (double*)(ring + i * field_bytes);
+    d_succ[s] = ring + 4 * field_bytes;
+  }
+  if (!p->d_totals) LTP_CUDA(cudaMalloc(&p->d_totals, sizeof(StreamTotals)));
+  LTP_CUDA(cudaMemsetAsync(p->d_totals, 0, sizeof(StreamTotals), p->pipe_stream[0]));
+  LTP_CUDA(cudaStreamSynchronize(p->pipe_stream[0]));
+  const double* src[4] = {q_goal, q_0, v_0, a_0};
+  int64_t k = 0;
+  for (int64_t p0 = 0; p0 < n; p0 += c_max, ++k) {
+    const int s = (int)(k % slots);
+    const int64_t c = (n - p0) < c_max ? (n - p0) : c_max;
+    cudaStream_t st = p->pipe_stream[s];
+    // a chunk of a joint-major array is dof pieces of c values at a pitch of n values
+    for (int i = 0; i < 4; ++i)
+      LTP_CUDA(cudaMemcpy2DAsync(d_in[s][i], (size_t)c * 8, src[i] + p0, (size_t)n * 8, (size_t)c * 8, dof,
+                                 cudaMemcpyDeviceToDevice, st));
+    int rc = solve_launch(p, c, d_in[s][0], d_in[s][1], d_in[s][2], d_in[s][3], &ds[s], d_work[s], st);
+    if (rc != LTP_OK) return rc;
+    rc = ltp_sample_batch(p, c, d_in[s][1], d_in[s][2], d_in[s][3], &ds[s], horizon, LTP_LAYOUT_TIME_MAJOR, capacity,
+                          d_traj[s][0], d_traj[s][1], d_traj[s][2], d_traj[s][3], d_succ[s], st);
+    if (rc != LTP_OK) return rc;
+    const unsigned tg = (unsigned)((c + 255) / 256);
+    ltp_chunk_totals_kernel<<<tg < 1024u ? tg : 1024u, 256, 0, st>>>(c, dof, horizon, capacity, ds[s].traj_len,
+                                                                     ds[s].reached, d_succ[s], p->d_totals);
+    p->launches++;
+    LTP_CUDA(cudaGetLastError());
+    if (consume) {
+      ltp_chunk view;
+      view.first = p0;
+      view.count = c;
+      view.capacity = capacity;
+      view.horizon = horizon;
+      view.solution = ds[s];
+      view.q_goal = d_in[s][0]; view.q_0 = d_in[s][1]; view.v_0 = d_in[s][2]; view.a_0 = d_in[s][3];
+      view.q = d_traj[s][0]; view.v = d_traj[s][1]; view.a = d_traj[s][2]; view.j = d_traj[s][3];
+      view.success = d_succ[s];
+      const int crc = consume(user, &view, (void*)st);
+      if (crc != 0) {
+        for (int t = 0; t < slots; ++t) cudaStreamSynchronize(p->pipe_stream[t]);
+        return crc < 0 ? crc : LTP_ERR_ARG;
+      }
+    }
+  }
+  for (int s = 0; s < slots; ++s) LTP_CUDA(cudaStreamSynchronize(p->pipe_stream[s]));
+  if (stats) {
+    StreamTotals h;
+    LTP_CUDA(cudaMemcpy(&h, p->d_totals, sizeof h, cudaMemcpyDeviceToHost));
+    stats->problems = h.problems; stats->reached = h.reached; stats->success = h.success;
+    stats->clipped = h.clipped; stats->samples = h.samples; stats->max_traj_len = h.max_len;
+    stats->chunks = k;
+    stats->bytes = h.samples * 32;
+  }
+  return LTP_OK;
+}
+
+int ltp_advance_batch(ltp_planner* p, int64_t n, int32_t tick, int32_t clamp, const int32_t* traj_len,
+                      const uint8_t* valid, const double* q, const double* v, const double* a, double* q_0,
+                      double* v_0, double* a_0, void* stream) {
+  if (!p || n < 0 || tick < 0 || p->params.dof < 1) return LTP_ERR_ARG;
+  if (n == 0) return LTP_OK;
+  if (!q || !v || !a || !q_0 || !v_0 || !a_0) return LTP_ERR_ARG;
+  DeviceGuard g(p->device);
+  dim3 grid((unsigned)((n + 255) / 256), p->params.dof);
+  ltp_advance_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p->params, n, tick, clamp, traj_len, valid, q, v, a,
+                                                             q_0, v_0, a_0);
+  p->launches++;
+  LTP_CUDA(cudaGetLastError());
   return LTP_OK;
 }
 

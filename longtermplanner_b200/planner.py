@@ -74,6 +74,16 @@ class BatchTrajectories:
     traj_len: torch.Tensor  # [n] i32
 
 
+class _DevMem:
+    """a device allocation owned by someone else, exposed through __cuda_array_interface__ so that
+    torch.as_tensor can alias it without copying"""
+
+    def __init__(self, ptr: int, nbytes: int, shape, dtype):
+        typestr = {torch.float64: "<f8", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2, "strides": None}
+
+
 def _vec(x: Sequence[float], dof: int) -> np.ndarray:
     a = np.ascontiguousarray(x, dtype=np.float64)
     if a.shape != (dof,):
@@ -295,6 +305,75 @@ class LongTermPlanner:
         """Batched planTrajectory: -> (BatchSolution, BatchTrajectories)."""
         sol = self.solve(q_goal, q_0, v_0, a_0)
         return sol, self.sample(q_0, v_0, a_0, sol, horizon, layout=layout)
+
+    def planStream(self, q_goal, q_0, v_0, a_0, chunk: int, horizon: int = 0, capacity: int = 4096,
+                   consumer=None) -> dict:
+        """planTrajectories for more problems than fit in memory at once (ltp_plan_stream): chunks
+        of `chunk` problems are solved and sampled (time-major) into a two-slot ring; `consumer`,
+        if given, is called per chunk as consumer(view, stream) with view a dict of CUDA tensors
+        that alias the ring slot (valid for work enqueued on `stream` = a torch ExternalStream).
+        Returns the totals accumulated on the device."""
+        n = q_goal.shape[1]
+        ins = [self._chk(t, n, nm) for t, nm in zip((q_goal, q_0, v_0, a_0), ("q_goal", "q_0", "v_0", "a_0"))]
+        dof, dev = self.dof_, torch.device("cuda", self.device)
+        err = []
+
+        def _alias(ptr, shape, dtype):
+            n_el = int(np.prod(shape))
+            if n_el == 0 or not ptr:
+                return torch.empty(shape, dtype=dtype, device=dev)
+            itemsize = torch.empty((), dtype=dtype).element_size()
+            arr = _DevMem(ptr, n_el * itemsize, shape, dtype)
+            return torch.as_tensor(arr, device=dev)
+
+        def _cb(user, chunk_p, stream):
+            try:
+                c = chunk_p.contents
+                cnt, cap = int(c.count), int(c.capacity)
+                sol = c.solution
+                view = dict(
+                    first=int(c.first), count=cnt, capacity=cap, horizon=int(c.horizon),
+                    q_goal=_alias(c.q_goal, (dof, cnt), torch.float64), q_0=_alias(c.q_0, (dof, cnt), torch.float64),
+                    v_0=_alias(c.v_0, (dof, cnt), torch.float64), a_0=_alias(c.a_0, (dof, cnt), torch.float64),
+                    t_scaled=_alias(sol.t_scaled, (7, dof, cnt), torch.float64),
+                    traj_len=_alias(sol.traj_len, (cnt,), torch.int32),
+                    reached=_alias(sol.reached, (cnt,), torch.uint8),
+                    success=_alias(c.success, (cnt,), torch.uint8),
+                    q=_alias(c.q, (cap, cnt, dof), torch.float64), v=_alias(c.v, (cap, cnt, dof), torch.float64),
+                    a=_alias(c.a, (cap, cnt, dof), torch.float64), j=_alias(c.j, (cap, cnt, dof), torch.float64))
+                ext = torch.cuda.ExternalStream(int(stream), device=dev)
+                with torch.cuda.stream(ext):
+                    consumer(view, ext)
+                return 0
+            except Exception as e:  # never unwind through the C frame
+                err.append(e)
+                return 1
+
+        cb = capi.CHUNK_CONSUMER(_cb) if consumer is not None else capi.CHUNK_CONSUMER()
+        stats = capi.StreamStats()
+        rc = capi.plan_stream(self._h, n, *[t.data_ptr() for t in ins], int(chunk), int(horizon), int(capacity),
+                              cb, None, C.byref(stats))
+        if err:
+            raise err[0]
+        capi.check(rc, "ltp_plan_stream")
+        return {k: int(getattr(stats, k)) for k, _ in capi.StreamStats._fields_}
+
+    def advance(self, traj: BatchTrajectories, tick: int, q_0, v_0, a_0, valid: Optional[torch.Tensor] = None,
+                clamp: bool = True) -> None:
+        """receding horizon: the state at sample index `tick` of time-major trajectories becomes
+        the next start state (written into q_0, v_0, a_0 in place), ltp_advance_batch"""
+        if traj.layout != "time_major":
+            raise ValueError("advance needs time-major trajectories")
+        n = q_0.shape[1]
+        for t in (q_0, v_0, a_0):
+            self._chk(t, n, "state")
+        if not (0 <= tick < traj.stride):
+            raise ValueError("tick outside the sampled range")
+        tl = None if traj.horizon > 0 else traj.traj_len.data_ptr()
+        capi.check(capi.advance_batch(self._h, n, int(tick), 1 if clamp else 0, tl,
+                                      None if valid is None else valid.data_ptr(), traj.q.data_ptr(),
+                                      traj.v.data_ptr(), traj.a.data_ptr(), q_0.data_ptr(), v_0.data_ptr(),
+                                      a_0.data_ptr(), self._stream()), "ltp_advance_batch")
 
     # per-joint primitives, batched
     def optBrakingBatch(self, v_0, a_0):

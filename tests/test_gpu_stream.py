@@ -1,0 +1,188 @@
+"""GPU tests of the streaming driver (BASELINE.json configs[4] shape: more trajectories than fit
+in memory, recycled ring) and of the receding-horizon step (configs[2]: replanning every 10 ms
+from the state the previous plan has reached)."""
+import numpy as np
+import pytest
+
+from helpers import count_bad, jm
+from longtermplanner_b200 import workloads as W
+from oracle.bindings import OraclePort
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _planner(lim):
+    from longtermplanner_b200 import LongTermPlanner
+    return LongTermPlanner(lim.dof, lim.t_sample, *lim.arrays(), device=0)
+
+
+def _view_as_traj(view):
+    from longtermplanner_b200.planner import BatchTrajectories
+    return BatchTrajectories("time_major", view["horizon"], view["capacity"], view["q"], view["v"], view["a"],
+                             view["j"], view["success"], view["traj_len"])
+
+
+@pytest.mark.parametrize("lim,n,chunk", [(W.FRANKA12, 5000, 1536), (W.FRANKA7, 3000, 3000), (W.FRANKA7, 1000, 4096)])
+def test_streamed_run_equals_one_shot(lim, n, chunk):
+    """per-row checksums, lengths and flags gathered chunk by chunk from the ring equal those
+    of one planTrajectories call over the whole batch, bit for bit"""
+    from longtermplanner_b200 import devtools
+    ltp = _planner(lim)
+    ins = devtools.random_states_device(lim, n, W.SEEDS[5], start=77)
+    sol, traj = ltp.planTrajectories(*ins)
+    want = devtools.row_stats(traj, sol.traj_len)
+    got = torch.zeros_like(want)
+    succ = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    tl = torch.zeros(n, dtype=torch.int32, device="cuda")
+    seen = []
+
+    def consumer(view, stream):
+        a, c = view["first"], view["count"]
+        seen.append((a, c))
+        got[a:a + c] = devtools.row_stats(_view_as_traj(view), view["traj_len"])
+        succ[a:a + c] = view["success"]
+        tl[a:a + c] = view["traj_len"]
+
+    stats = ltp.planStream(*ins, chunk=chunk, capacity=4096, consumer=consumer)
+    torch.cuda.synchronize()
+    assert seen == [(a, min(chunk, n - a)) for a in range(0, n, chunk)]
+    assert torch.equal(got.view(torch.int64), want.view(torch.int64))
+    assert torch.equal(succ, traj.success) and torch.equal(tl, sol.traj_len)
+    assert stats["problems"] == n and stats["chunks"] == len(seen)
+    assert stats["reached"] == int(sol.reached.sum()) and stats["success"] == int(traj.success.sum())
+    assert stats["samples"] == int(sol.traj_len.long().sum()) * lim.dof and stats["bytes"] == stats["samples"] * 32
+    assert stats["clipped"] == 0 and stats["max_traj_len"] == int(sol.traj_len.max())
+
+
+def test_streamed_run_fixed_horizon_and_clipping():
+    from longtermplanner_b200 import devtools
+    lim, n, H = W.FRANKA7, 2500, 600
+    ltp = _planner(lim)
+    ins = devtools.random_states_device(lim, n, 99)
+    sol = ltp.solve(*ins)
+    stats = ltp.planStream(*ins, chunk=1024, horizon=H, capacity=H)
+    tl = sol.traj_len.cpu().numpy()
+    assert stats["samples"] == n * lim.dof * H
+    assert stats["clipped"] == int((tl > H).sum()) > 0
+    # exact-length mode with a capacity below the longest trajectory
+    cap = int(np.median(tl))
+    stats = ltp.planStream(*ins, chunk=1024, horizon=0, capacity=cap)
+    assert stats["clipped"] == int((tl > cap).sum())
+    assert stats["samples"] == int(np.minimum(tl, cap).sum()) * lim.dof
+
+
+def test_streamed_run_without_consumer_and_empty_batch():
+    from longtermplanner_b200 import devtools
+    lim = W.FRANKA7
+    ltp = _planner(lim)
+    ins = devtools.random_states_device(lim, 300, 5)
+    stats = ltp.planStream(*ins, chunk=128)
+    assert stats["problems"] == 300 and stats["chunks"] == 3
+    empty = [t[:, :0].contiguous() for t in ins]
+    assert ltp.planStream(*empty, chunk=128)["problems"] == 0
+
+
+def test_consumer_exception_propagates():
+    from longtermplanner_b200 import devtools
+    lim = W.FRANKA7
+    ltp = _planner(lim)
+    ins = devtools.random_states_device(lim, 300, 5)
+
+    def consumer(view, stream):
+        raise KeyError("boom")
+
+    with pytest.raises(KeyError):
+        ltp.planStream(*ins, chunk=128, consumer=consumer)
+    torch.cuda.synchronize()
+    assert ltp.planStream(*ins, chunk=128)["problems"] == 300  # the planner is still usable
+
+
+def test_advance_takes_the_sample_at_the_tick():
+    lim, n, H, tick = W.FRANKA7, 777, 64, 9
+    ltp = _planner(lim)
+    qg, q0, v0, a0 = W.random_states(lim, n, 17)
+    ins = [torch.from_numpy(jm(x)).cuda() for x in (qg, q0, v0, a0)]
+    sol = ltp.solve(*ins)
+    traj = ltp.sample(ins[1], ins[2], ins[3], sol, horizon=H)
+    nq, nv, na = (t.clone() for t in ins[1:])
+    ltp.advance(traj, tick, nq, nv, na, clamp=False)
+    torch.cuda.synchronize()
+    assert torch.equal(nq, traj.q[tick].T.contiguous()) and torch.equal(nv, traj.v[tick].T.contiguous())
+    assert torch.equal(na, traj.a[tick].T.contiguous())
+    # exact-length trajectories: a tick past the end gives the final state
+    exact = ltp.sample(ins[1], ins[2], ins[3], sol)
+    big = exact.stride - 1
+    ltp.advance(exact, big, nq, nv, na, clamp=False)
+    tl = sol.traj_len.long() - 1
+    idx = torch.minimum(tl, torch.tensor(big, device="cuda"))
+    want = exact.q[idx, torch.arange(n, device="cuda"), :].T.contiguous()
+    assert torch.equal(nq, want)
+    assert bool((nv == 0).all()) and bool((na == 0).all())
+
+
+def test_receding_horizon_loop_matches_oracle_and_never_rejects_its_own_state():
+    """configs[2] in small: replan every 10 samples towards a fresh goal from the state the
+    previous plan reached; every replan is accepted (clamped Euler drift), and the solve from
+    that state agrees with the oracle on the same numbers"""
+    lim, n, H, tick = W.FRANKA7, 256, 200, 9
+    ltp = _planner(lim)
+    P = OraclePort.from_limits(lim)
+    qg, q0, v0, a0 = W.random_states(lim, n, 23)
+    state = [torch.from_numpy(jm(x)).cuda() for x in (q0, v0, a0)]
+    for step in range(12):
+        goal = torch.from_numpy(jm(W.random_states(lim, n, 100 + step)[0])).cuda()
+        sol = ltp.solve(goal, *state, with_cases=True)
+        traj = ltp.sample(*state, sol, horizon=H)
+        torch.cuda.synchronize()
+        assert bool(sol.reached.all()), step
+        if step % 4 == 0:
+            ref = P.solve(goal.cpu().numpy().T.copy(), *[s.cpu().numpy().T.copy() for s in state], threads=4)
+            assert np.array_equal(sol.traj_len.cpu().numpy(), ref["traj_len"])
+            assert np.array_equal(sol.final_case.cpu().numpy().T, ref["final_case"])
+            assert count_bad(sol.t_scaled.cpu().numpy().transpose(2, 1, 0), ref["t_scaled"]) == 0
+        ltp.advance(traj, tick, *state)
+    # states stay physically plausible
+    q_min, q_max, v_max, a_max, _ = (torch.from_numpy(x).cuda()[:, None] for x in lim.arrays())
+    assert bool((state[0] >= q_min).all() and (state[0] <= q_max).all())
+    assert bool((state[1].abs() <= v_max).all() and (state[2].abs() <= a_max).all())
+
+
+def test_replanning_step_can_be_captured_in_a_cuda_graph():
+    lim, n, H, tick = W.FRANKA7, 512, 128, 9
+    ltp = _planner(lim)
+    qg, q0, v0, a0 = W.random_states(lim, n, 31)
+    goal = torch.from_numpy(jm(qg)).cuda()
+
+    def fresh():
+        return [torch.from_numpy(jm(x)).cuda() for x in (q0, v0, a0)]
+
+    def run(state, sol, traj, steps):
+        for _ in range(steps):
+            ltp.solve(goal, *state, out=sol)
+            ltp.sample(*state, sol, horizon=H, out=traj)
+            ltp.advance(traj, tick, *state)
+
+    eager_state = fresh()
+    sol_e, traj_e = ltp.alloc_solution(n), ltp.alloc_trajectories(n, H)
+    run(eager_state, sol_e, traj_e, 3)
+    torch.cuda.synchronize()
+
+    state = fresh()
+    sol, traj = ltp.alloc_solution(n), ltp.alloc_trajectories(n, H)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        run(state, sol, traj, 1)  # warm-up on the capture stream: allocates the work list
+        for a, b in zip(state, fresh()):
+            a.copy_(b)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            run(state, sol, traj, 1)
+        for a, b in zip(state, fresh()):  # capture does not execute
+            a.copy_(b)
+        for _ in range(3):
+            g.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(state, eager_state):
+        assert torch.equal(a, b)
+    assert torch.equal(traj.q, traj_e.q) and torch.equal(sol.traj_len, sol_e.traj_len)
