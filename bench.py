@@ -140,6 +140,63 @@ def ncu_facts():
         return {}
 
 
+def replan_loop(ltp, lim, dev, hbm_peak, n_env=4096, horizon=2001, tick=9, ticks=50):
+    """4096 environments, every control period (10 samples = 10 ms): new goals arrive from the
+    host, every environment is re-solved from the state its previous plan has reached by then and
+    re-sampled to the 2 s horizon; the next 10 samples go back to the host. Solve + sample +
+    state gather are one CUDA graph."""
+    import torch
+    g0, q0, v0, a0 = W.random_states(lim, n_env, W.SEEDS[3])
+    state = [torch.from_numpy(W.to_joint_major(x)).to(dev) for x in (q0, v0, a0)]
+    goal = torch.from_numpy(W.to_joint_major(g0)).to(dev)
+    pool = [torch.from_numpy(W.to_joint_major(W.random_states(lim, n_env, 1000 + k)[0])).pin_memory()
+            for k in range(8)]
+    sol = ltp.alloc_solution(n_env)
+    traj = ltp.alloc_trajectories(n_env, horizon, "time_major")
+    head = torch.empty(3, tick + 1, n_env, lim.dof, dtype=torch.float64).pin_memory()
+
+    def step():
+        ltp.solve(goal, *state, out=sol)
+        ltp.sample(*state, sol, horizon=horizon, out=traj)
+        ltp.advance(traj, tick, *state)
+
+    s = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(s):
+        step()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            step()
+        for _ in range(3):
+            graph.replay()
+        s.synchronize()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        e[0].record()
+        for k in range(ticks):
+            graph.replay()
+        e[1].record()
+        s.synchronize()
+        graph_ms = e[0].elapsed_time(e[1]) / ticks
+        # end to end: goals from pinned host memory in, the next control period's samples out
+        t0 = time.perf_counter()
+        for k in range(ticks):
+            goal.copy_(pool[k % len(pool)], non_blocking=True)
+            graph.replay()
+            head[0].copy_(traj.q[:tick + 1], non_blocking=True)
+            head[1].copy_(traj.v[:tick + 1], non_blocking=True)
+            head[2].copy_(traj.a[:tick + 1], non_blocking=True)
+            s.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / ticks
+    reached = float(sol.reached.double().mean().item())
+    useful = n_env * lim.dof * horizon * 32
+    return {"workload": f"configs[2] loop: {n_env} envs x {lim.dof} DoF, replanned every {tick + 1} samples towards new "
+                        f"goals, dense sampling to {horizon} samples, {ticks} consecutive replans",
+            "graph_replan_ms": graph_ms, "budget_ms": (tick + 1) * lim.t_sample * 1e3,
+            "e2e_replan_ms": e2e_ms, "e2e_h2d_bytes": int(pool[0].numel() * 8), "e2e_d2h_bytes": int(head.numel() * 8),
+            "write_gbs": useful / (graph_ms * 1e-3) / 1e9, "frac_of_hbm_peak": useful / (graph_ms * 1e-3) / 1e9 / hbm_peak,
+            "reached_frac": reached, "kernels_per_replan": 4,
+            "timing": "CUDA events around 50 graph replays (solve fast + work-list kernel + sampler + state gather)"}
+
+
 def load_probe():
     from longtermplanner_b200 import _build
     path = _build.PROBELIB
@@ -157,6 +214,9 @@ def main():
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="problems per GPU")
     ap.add_argument("--no-sampler", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-stream", action="store_true")
+    ap.add_argument("--no-replan", action="store_true")
+    ap.add_argument("--stream-log2n", type=int, default=26, help="configs[4]: total problems = 2^k over all GPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -251,7 +311,47 @@ def main():
     assert np.array_equal(host_out["traj_len"], sol.traj_len.cpu().numpy())
 
     extra = {}
+    # free the configs[1] buffers before the memory-hungry sections
+    del dev_in, host_in, host_np, host_out
+    torch.cuda.empty_cache()
+
+    # ---- configs[4]: 2^26 random 12-DoF problems, full dense sampling, sharded over the ranks --
+    if not args.no_stream:
+        from longtermplanner_b200 import devtools
+        lim12 = W.FRANKA12
+        n_total = 1 << args.stream_log2n
+        n_rank = n_total // world
+        chunk, cap = 8192, 4096
+        ltp12 = LongTermPlanner(lim12.dof, lim12.t_sample, *lim12.arrays(), device=local)
+        ins12 = devtools.random_states_device(lim12, n_rank, W.SEEDS[5], start=rank * n_rank, device=local)
+        ltp12.planStream(*[t[:, :2 * chunk + 7].contiguous() for t in ins12], chunk=chunk, capacity=cap)  # warm-up
+        launches12 = ltp12.launches
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        s0.record()
+        st12 = ltp12.planStream(*ins12, chunk=chunk, capacity=cap)  # synchronises before returning
+        s1.record()
+        barrier()
+        stream_ms = max_over_ranks(s0.elapsed_time(s1))
+        tot = torch.tensor([st12["problems"], st12["bytes"], st12["success"], st12["clipped"], st12["reached"]],
+                           dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot)
+        tot = tot.tolist()
+        extra_stream = {
+            "workload": f"configs[4]: 2^{args.stream_log2n} random 12-DoF dual-arm problems (FRANKA12), solve + "
+                        "exact-length dense q/v/a/j sampling, contiguous problem-index shards, each rank streams its "
+                        f"shard through a two-slot ring of {chunk}-problem chunks (time-major, capacity {cap} samples)",
+            "scaling": "strong", "seconds": stream_ms * 1e-3, "plans_per_s": tot[0] / (stream_ms * 1e-3),
+            "write_gbs": tot[1] / (stream_ms * 1e-3) / 1e9, "write_gbs_per_gpu": tot[1] / (stream_ms * 1e-3) / 1e9 / world,
+            "bytes_written": tot[1], "problems": tot[0], "reached": tot[4], "success": tot[2], "clipped": tot[3],
+            "gpu_launches": int(ltp12.launches - launches12),
+            "timing": "CUDA events around the call (it synchronises its two streams), max over ranks"}
+        del ins12, ltp12
+        torch.cuda.empty_cache()
     if rank == 0:
+        if not args.no_stream:
+            extra["stream"] = extra_stream
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -328,6 +428,10 @@ def main():
                              "timing": "CUDA events on the launching stream around each launch, mean of 20",
                              "algorithmic_bytes_per_sample": 32, "bytes_per_launch": useful,
                              "write_only_probe_gbs": wgbs.value}}
+
+        # ---- configs[2] as a loop: replan every 10 ms from the state the previous plan reached ----
+        if not args.no_replan and not args.no_sampler:
+            extra["replan"] = replan_loop(ltp, lim, dev, hbm_peak)
 
         # ---- CPU baseline: the reference's code on this box's host cores ---------------------
         if not args.no_cpu and world == 1:
