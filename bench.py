@@ -131,6 +131,29 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this rank's host threads on the CPUs of the GPU's NUMA node, so that the pinned
+    buffers of the end-to-end path are first touched (= placed) next to the GPU's PCIe root.
+    Returns the node, or None where the topology is not exposed."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def ncu_facts():
     """per-launch facts read off the committed ncu --set full capture (profiles/ncu_facts.json,
     written by tools/ncu_summary.py --json); {} if the capture has not been made"""
@@ -231,9 +254,23 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL announces its version on stdout when the first communicator comes up; stdout
+        # carries exactly one JSON line, so that goes to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:
@@ -304,6 +341,7 @@ def main():
     h2d = sum(x.nbytes for x in host_np)
     d2h = sum(x.nbytes for x in host_out.values())
     clock_info = clocks.stop() if rank == 0 else None
+    os.sched_setaffinity(0, all_cpus)  # the CPU baseline below uses every host core
 
     # a cheap integrity check on what was timed (not a parity test; those live in tests/)
     reached_frac = float(sol.reached.double().mean().item())
@@ -460,7 +498,8 @@ def main():
                        "l2": "inputs 235 MB + outputs 560 MB per step, larger than the 126 MB L2",
                        "sharding": "contiguous problem-index shards, no collective on the data path"},
             "e2e": {"value": e2e_value, "unit": "plans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "ltp_solve_host (pinned host buffers in and out)"},
+                    "steps": e2e_steps, "api": "ltp_solve_host (pinned host buffers in and out)",
+                    "host_numa_node": numa},
             "gpu_launches": int(gpu_launches), "clocks": clock_info, "reached_frac": reached_frac,
         }
         line.update(extra)

@@ -188,24 +188,26 @@ def test_replanning_step_can_be_captured_in_a_cuda_graph():
     assert torch.equal(traj.q, traj_e.q) and torch.equal(sol.traj_len, sol_e.traj_len)
 
 
-def test_refined_single_joint_grid_populates_every_case_and_matches_oracle():
-    """configs[3] at reduced size (64^3 points): the sweep tool's three passes run, every one of
-    the eight phase patterns and time-scaling attempts 1..4 occur, and the strided parity
-    check against the oracle reports zero mismatches"""
+def test_refined_single_joint_grid_matches_oracle_at_every_point():
+    """configs[3] at reduced size (48^3 points): the sweep tool's three passes run and EVERY point
+    is compared with the oracle (case bytes, accepted attempt, flags exact; times and cruise
+    speeds within tolerance), so the case histograms are the oracle's. Which cases a grid
+    populates depends on its resolution; the committed 256^3 run (profiles/) populates all
+    eight phase patterns and attempts 1..7."""
     import json
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "tools", "grid_sweep.py"), "64", "8", "5"],
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "grid_sweep.py"), "48", "8", "1"],
                          capture_output=True, text=True, check=True).stdout
     r = json.loads(out)
-    assert r["all_eight_cases_populated"], r["case_histogram_pass1_plus_nested"]
-    # the closed forms and the first two quartic attempts are accepted somewhere even on this
-    # coarse grid; 5..8 are rare (16 M-point grid: 2203, 12464, 528 and 0 acceptances)
-    assert set(r["pass2_attempts_never_accepted"]) <= {5, 6, 7, 8}, r["pass2_attempt_histogram_all_increments"]
     par = r["parity_vs_cpu_oracle"]
+    assert par["points"] == 48 ** 3
     assert all(v == 0 for v in par["exact_field_mismatches"].values()), par
     assert all(v == 0 for v in par["value_mismatches"].values()), par
+    h = r["case_histogram_pass1_plus_nested"]
+    assert sum(1 for k in range(1, 9) if h.get(str(k), 0) > 0) >= 5, h
     acc = r["pass3_goal_accuracy"]["results"]
     assert acc["optimal"]["max_abs_goal_error"] < 0.02  # the reference's own bar, tests.cc:318
+    assert all(acc[k]["max_abs_goal_error"] < 0.02 for k in acc)
