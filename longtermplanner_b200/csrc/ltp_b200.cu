@@ -64,44 +64,69 @@ constexpr int kTile = 32;  // problems per CTA
 // The split changes no result: a deferred problem is recomputed from its inputs by exactly
 // the code that handles it in generic-only mode.
 // ------------------------------------------------------------------------------------
+struct Attempt2Item {  // a joint whose first cruise-speed candidate was rejected (fast kernel)
+  double q_goal, q_0, v_0, a_0, t_req;
+  int lane, jt;
+};
+
 struct SolveShared {
   double* t6;            // [dof][32]
+  Attempt2Item* item;    // [dof * 32]  work items of the second closed-form attempt
   int* len;              // [dof][32]
-  unsigned char* flag;   // [dof][32]  bit0 fail, bit1 defer
   int* arrived;          // [32]
+  int* slowest;          // [32]
+  int* warp_items;       // [dof + 1]   items per warp, then their total
+  unsigned char* flag;   // [dof][32]  bit0 fail, bit1 defer
 };
+
+__host__ __device__ inline size_t solve_smem_bytes(int dof) {
+  return (size_t)dof * kTile * (sizeof(double) + sizeof(Attempt2Item) + sizeof(int) + 1) +
+         (2 * kTile + dof + 1) * sizeof(int) + 16;
+}
 
 __device__ __forceinline__ SolveShared carve_shared(unsigned char* raw, int dof) {
   SolveShared s;
   s.t6 = reinterpret_cast<double*>(raw);
-  s.len = reinterpret_cast<int*>(s.t6 + dof * kTile);
+  s.item = reinterpret_cast<Attempt2Item*>(s.t6 + dof * kTile);
+  s.len = reinterpret_cast<int*>(s.item + dof * kTile);
   s.arrived = s.len + dof * kTile;
-  s.flag = reinterpret_cast<unsigned char*>(s.arrived + kTile);
+  s.slowest = s.arrived + kTile;
+  s.warp_items = s.slowest + kTile;
+  s.flag = reinterpret_cast<unsigned char*>(s.warp_items + dof + 1);
   return s;
 }
 
-static size_t solve_smem_bytes(int dof) {
-  return (size_t)dof * kTile * (sizeof(double) + sizeof(int) + 1) + kTile * sizeof(int);
-}
-
-// per-joint stores shared by both kernels
-__device__ __forceinline__ void store_joint(const DeviceSolution& S, int dof, int jt, int64_t n, int64_t p,
-                                            const double* t_sc, const double* t_opt, double dir,
-                                            double v_drive, unsigned char mod, unsigned char opt_case,
-                                            unsigned char ts_case, unsigned char final_case) {
+// per-joint stores shared by both kernels: the part known after the time-optimal solve ...
+__device__ __forceinline__ void store_joint_opt(const DeviceSolution& S, int dof, int jt, int64_t n, int64_t p,
+                                                const double* t_opt, double dir, unsigned char opt_case) {
   const int64_t at = (int64_t)jt * n + p;
-#pragma unroll
-  for (int k = 0; k < 7; ++k) S.t_scaled[((int64_t)k * dof + jt) * n + p] = t_sc[k];
   S.dir[at] = dir;
-  S.v_drive[at] = v_drive;
-  S.mod[at] = mod;
   if (S.t_opt) {
 #pragma unroll
     for (int k = 0; k < 7; ++k) S.t_opt[((int64_t)k * dof + jt) * n + p] = t_opt[k];
   }
   if (S.opt_case) S.opt_case[at] = opt_case;
+}
+
+// ... and the part that the time-scaling search decides
+__device__ __forceinline__ void store_joint_scaled(const DeviceSolution& S, int dof, int jt, int64_t n, int64_t p,
+                                                   const double* t_sc, double v_drive, unsigned char mod,
+                                                   unsigned char ts_case, unsigned char final_case) {
+  const int64_t at = (int64_t)jt * n + p;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) S.t_scaled[((int64_t)k * dof + jt) * n + p] = t_sc[k];
+  S.v_drive[at] = v_drive;
+  S.mod[at] = mod;
   if (S.ts_case) S.ts_case[at] = ts_case;
   if (S.final_case) S.final_case[at] = final_case;
+}
+
+__device__ __forceinline__ void store_joint(const DeviceSolution& S, int dof, int jt, int64_t n, int64_t p,
+                                            const double* t_sc, const double* t_opt, double dir,
+                                            double v_drive, unsigned char mod, unsigned char opt_case,
+                                            unsigned char ts_case, unsigned char final_case) {
+  store_joint_scaled(S, dof, jt, n, p, t_sc, v_drive, mod, ts_case, final_case);
+  store_joint_opt(S, dof, jt, n, p, t_opt, dir, opt_case);
 }
 
 // cc:718 for one joint, -1 when a switching time is not finite / not representable
@@ -195,39 +220,90 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
   // a joint that needs the quartic tail has no t_opt yet: the whole problem is deferred
   const bool defer1 = (any & 2) != 0;
   const bool reached = !(any & 1) && slowest != -1;
-  // stage 3 (cc:42-55), closed-form attempts only
+  if (jt == 0) sh.slowest[lane] = slowest;
+  // stage 3 (cc:42-55), closed-form attempts only. Attempt 1 runs here; the joints it does
+  // not settle (about a third) are compacted over the CTA and attempt 2 runs on full warps.
   double t_sc[7];
   zero7(t_sc);
   double v_drive = L.v_max;
   unsigned char ts_case = 255, final_case = 255;
-  bool my_defer = false;
+  bool my_defer = false, need2 = false;
   if (reached && !defer1) {
     if (jt == slowest) {
       ts_case = 0;
       final_case = opt_case;
     } else {
       const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
-      const int c = time_scaling_closed_form(L, Ts, pro, I, t_sc, v_drive, mod, final_case);
+      const int c = time_scaling_attempt1(L, Ts, pro, I, t_sc, v_drive, mod, final_case);
       my_defer = (c == 0);
+      need2 = (c == -1) && valid;
       ts_case = (unsigned char)c;
       if (c == 9) final_case = opt_case;
     }
-    double m = t_sc[0];
+    if (!need2) {
+      double m = t_sc[0];
 #pragma unroll
-    for (int k = 1; k < 7; ++k)
-      if (m < t_sc[k]) m = t_sc[k];
-    if (m <= 0.0) {
+      for (int k = 1; k < 7; ++k)
+        if (m < t_sc[k]) m = t_sc[k];
+      if (m <= 0.0) {
 #pragma unroll
-      for (int k = 0; k < 7; ++k) t_sc[k] = t_opt[k];
+        for (int k = 0; k < 7; ++k) t_sc[k] = t_opt[k];
+      }
     }
   }
-  const int my_len = (reached && !defer1 && !my_defer) ? joint_samples(t_sc, Ts) : 0;
-  if (!valid) return;
-  if (finish_problem(sh, S, dof, lane, jt, p, my_len, my_defer, reached, slowest)) {
-    const int slot = atomicAdd(work_count, 1);
-    work_list[slot] = (int)p;
+  // compaction: slot = (items of the warps before mine) + (items of the lanes before mine)
+  const unsigned need_mask = __ballot_sync(0xffffffffu, need2);
+  if (lane == 0) sh.warp_items[jt] = __popc(need_mask);
+  __syncthreads();
+  int before = 0, total = 0;
+  for (int w = 0; w < dof; ++w) {
+    const int c = sh.warp_items[w];
+    before += (w < jt) ? c : 0;
+    total += c;
   }
-  store_joint(S, dof, jt, n, p, t_sc, t_opt, pro.dir, v_drive, mod, opt_case, ts_case, final_case);
+  if (need2) {
+    Attempt2Item& it = sh.item[before + __popc(need_mask & ((1u << lane) - 1u))];
+    it.q_goal = qg; it.q_0 = q0; it.v_0 = v0; it.a_0 = a0; it.t_req = t_req;
+    it.lane = lane; it.jt = jt;
+  }
+  __syncthreads();
+  if (valid) {
+    store_joint_opt(S, dof, jt, n, p, t_opt, pro.dir, opt_case);
+    if (!need2) {
+      const int my_len = (reached && !defer1 && !my_defer) ? joint_samples(t_sc, Ts) : 0;
+      if (finish_problem(sh, S, dof, lane, jt, p, my_len, my_defer, reached, slowest)) {
+        const int slot = atomicAdd(work_count, 1);
+        work_list[slot] = (int)p;
+      }
+      store_joint_scaled(S, dof, jt, n, p, t_sc, v_drive, mod, ts_case, final_case);
+    }
+  }
+  // attempt 2 on the compacted items (thread t takes item t; total <= blockDim)
+  const int tid = jt * kTile + lane;
+  if (tid >= total) return;
+  const Attempt2Item it = sh.item[tid];
+  const JointLimits L2 = P.lim[it.jt];
+  const Prologue pro2 = ost_prologue(L2, Ts, it.q_goal, it.q_0, it.v_0, it.a_0);
+  const TsInput I2 = make_ts_input(it.q_goal, it.q_0, it.v_0, it.a_0, pro2.dir, it.t_req);
+  double t2[7];
+  zero7(t2);
+  double v2 = L2.v_max;
+  unsigned char mod2 = 0, fc2 = 255;
+  const int c2 = time_scaling_attempt2(L2, Ts, pro2, I2, t2, v2, mod2, fc2);
+  double m2 = t2[0];
+#pragma unroll
+  for (int k = 1; k < 7; ++k)
+    if (m2 < t2[k]) m2 = t2[k];
+  // an accepted solve with no positive time falls back to the time-optimal times (cc:50-55),
+  // which this thread does not hold: leave that (degenerate) problem to the generic kernel
+  const bool defer2 = (c2 == 0) || (m2 <= 0.0);
+  const int64_t p2 = (int64_t)blockIdx.x * kTile + it.lane;
+  const int len2 = defer2 ? 0 : joint_samples(t2, Ts);
+  if (finish_problem(sh, S, dof, it.lane, it.jt, p2, len2, defer2, true, sh.slowest[it.lane])) {
+    const int slot = atomicAdd(work_count, 1);
+    work_list[slot] = (int)p2;
+  }
+  store_joint_scaled(S, dof, it.jt, n, p2, t2, v2, mod2, (unsigned char)c2, fc2);
 }
 
 // every branch evaluated in-thread. work_list == nullptr: problem = tile index (generic-only

@@ -790,25 +790,33 @@ LTP_HD void ts_fail_state(const JointLimits& L, double* scaled_t, double& v_driv
   final_case = CASE_FAIL;
 }
 
-// Closed-form part of the search (attempts 1 and 2) for the fast kernel. Returns the accepted
-// attempt (1, 2), 9 when the outcome is already known to be failure, or 0 when the joint
-// needs the root-solver attempts 3..8 or a quartic tail inside a nested solve: the caller
-// then defers the whole problem to the generic kernel.
-LTP_HD int time_scaling_closed_form(const JointLimits& L, double Ts, const Prologue& P, const TsInput& I,
-                                    double* scaled_t, double& v_drive, unsigned char& mod,
-                                    unsigned char& final_case) {
+// Closed-form part of the search (attempts 1 and 2) for the fast kernel, one function per
+// attempt so that the joints attempt 1 does not settle can be regrouped in between.
+// attempt1 returns 1 (accepted), 9 (the outcome is already known to be failure), 0 (a nested
+// solve needs the quartic tail: the caller defers the whole problem to the generic kernel) or
+// -1 (rejected: go on with attempt 2). attempt2 returns 2 (accepted) or 0 (the joint needs the
+// root-solver attempts 3..8 or a quartic tail: defer).
+LTP_HD int time_scaling_attempt1(const JointLimits& L, double Ts, const Prologue& P, const TsInput& I,
+                                 double* scaled_t, double& v_drive, unsigned char& mod,
+                                 unsigned char& final_case) {
   if (ts_brake_only_rejects(P, I.tr)) {
     ts_fail_state(L, scaled_t, v_drive, mod, final_case);
     return 9;
   }
-  double V = ts_candidate1(L, I);
+  const double V = ts_candidate1(L, I);
   v_drive = V;
   if (!isnan(V) && V > 0) {
     const int st = ost_body_t<false>(L, Ts, P, I.q_goal, I.q_0, V, scaled_t, mod, final_case);
     if (st == OST_DEFER) return 0;
     if (st == OST_OK && I.tr - scaled_t[6] < kTol && I.tr - scaled_t[6] > -kTol / 10) return 1;
   }
-  V = ts_candidate2(L, I);
+  return -1;
+}
+
+LTP_HD int time_scaling_attempt2(const JointLimits& L, double Ts, const Prologue& P, const TsInput& I,
+                                 double* scaled_t, double& v_drive, unsigned char& mod,
+                                 unsigned char& final_case) {
+  const double V = ts_candidate2(L, I);
   v_drive = V;
   if (!isnan(V) && V > 0) {
     const int st = ost_body_t<false>(L, Ts, P, I.q_goal, I.q_0, V, scaled_t, mod, final_case);
@@ -816,6 +824,13 @@ LTP_HD int time_scaling_closed_form(const JointLimits& L, double Ts, const Prolo
     if (st == OST_OK && I.tr - scaled_t[6] < kTol && I.tr - scaled_t[6] > -kTol / 10) return 2;
   }
   return 0;
+}
+
+LTP_HD int time_scaling_closed_form(const JointLimits& L, double Ts, const Prologue& P, const TsInput& I,
+                                    double* scaled_t, double& v_drive, unsigned char& mod,
+                                    unsigned char& final_case) {
+  const int c = time_scaling_attempt1(L, Ts, P, I, scaled_t, v_drive, mod, final_case);
+  return c >= 0 ? c : time_scaling_attempt2(L, Ts, P, I, scaled_t, v_drive, mod, final_case);
 }
 
 LTP_HD int time_scaling_from(int first, const JointLimits& L, double Ts, const Prologue& P,
