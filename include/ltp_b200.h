@@ -64,7 +64,7 @@ int ltp_set_dof(ltp_planner* p, int dof);
 #define LTP_SOLVE_AUTO 0
 #define LTP_SOLVE_GENERIC 1
 int ltp_set_solve_mode(ltp_planner* p, int mode);
-/* Per-kernel timing for benchmarks. While on, every launch of the four hot kernels is
+/* Per-kernel timing for benchmarks. While on, every launch of the hot kernels is
  * bracketed by a CUDA event pair on the launching stream. ltp_profile_read waits for the
  * recorded launches of one kernel, returns the sum of their durations in ms and their number
  * since the last reset. Off by default; results do not depend on it. */
@@ -72,7 +72,8 @@ int ltp_set_solve_mode(ltp_planner* p, int mode);
 #define LTP_PROFILE_SOLVE_GENERIC 1
 #define LTP_PROFILE_SAMPLE_TIME_MAJOR 2
 #define LTP_PROFILE_SAMPLE_ROWS 3
-#define LTP_PROFILE_KERNELS 4
+#define LTP_PROFILE_SOLVE_ATTEMPT2 4
+#define LTP_PROFILE_KERNELS 5
 int ltp_set_profiling(ltp_planner* p, int on);
 int ltp_profile_read(ltp_planner* p, int kernel, double* ms_sum, int64_t* launches, int reset);
 int ltp_get_dof(const ltp_planner* p);

@@ -64,35 +64,66 @@ constexpr int kTile = 32;  // problems per CTA
 // The split changes no result: a deferred problem is recomputed from its inputs by exactly
 // the code that handles it in generic-only mode.
 // ------------------------------------------------------------------------------------
-struct Attempt2Item {  // a joint whose first cruise-speed candidate was rejected (fast kernel)
-  double q_goal, q_0, v_0, a_0, t_req;
-  int lane, jt;
+// Queue of the joints whose first cruise-speed candidate was rejected: filled by the
+// closed-form kernel, drained (regrouped into full warps) by ltp_solve_attempt2_kernel.
+// Structure of arrays, so that both sides access it fully coalesced; the start state travels
+// with the entry (the producer has it in registers, a gather in the consumer costs more).
+struct Attempt2Queue {
+  double *t_req, *q_goal, *q_0, *v_0, *a_0;
+  int2* where;  // (problem, joint)
 };
+
+constexpr int kDeferredMark = 0x7fffffff;  // traj_len of a problem that sits in the work list
 
 struct SolveShared {
   double* t6;            // [dof][32]
-  Attempt2Item* item;    // [dof * 32]  work items of the second closed-form attempt
   int* len;              // [dof][32]
   int* arrived;          // [32]
-  int* slowest;          // [32]
-  int* warp_items;       // [dof + 1]   items per warp, then their total
+  int* warp_items;       // [dof + 2]   queued joints per warp, then their total and queue base
   unsigned char* flag;   // [dof][32]  bit0 fail, bit1 defer
 };
 
 __host__ __device__ inline size_t solve_smem_bytes(int dof) {
-  return (size_t)dof * kTile * (sizeof(double) + sizeof(Attempt2Item) + sizeof(int) + 1) +
-         (2 * kTile + dof + 1) * sizeof(int) + 16;
+  return (size_t)dof * kTile * (sizeof(double) + sizeof(int) + 1) + (kTile + dof + 2) * sizeof(int);
 }
 
 __device__ __forceinline__ SolveShared carve_shared(unsigned char* raw, int dof) {
   SolveShared s;
   s.t6 = reinterpret_cast<double*>(raw);
-  s.item = reinterpret_cast<Attempt2Item*>(s.t6 + dof * kTile);
-  s.len = reinterpret_cast<int*>(s.item + dof * kTile);
+  s.len = reinterpret_cast<int*>(s.t6 + dof * kTile);
   s.arrived = s.len + dof * kTile;
-  s.slowest = s.arrived + kTile;
-  s.warp_items = s.slowest + kTile;
-  s.flag = reinterpret_cast<unsigned char*>(s.warp_items + dof + 1);
+  s.warp_items = s.arrived + kTile;
+  s.flag = reinterpret_cast<unsigned char*>(s.warp_items + dof + 2);
+  return s;
+}
+
+// Device scratch of one solve: [0] work-list length, [1] attempt-2 queue length, then the
+// work list (n problem indices) and the queue (at most (dof - 1) * n entries).
+struct SolveScratch {
+  int* counters;
+  int* work_list;
+  Attempt2Queue queue;
+};
+
+inline size_t solve_scratch_bytes(int dof, int64_t n) {
+  const size_t lists = 16 + (((size_t)n * sizeof(int) + 15) / 16) * 16;
+  const size_t cap = (size_t)(dof > 1 ? dof - 1 : 0) * (size_t)n;
+  return lists + cap * (5 * sizeof(double) + sizeof(int2));
+}
+
+inline SolveScratch carve_scratch(void* base, int dof, int64_t n) {
+  SolveScratch s;
+  unsigned char* b = static_cast<unsigned char*>(base);
+  s.counters = reinterpret_cast<int*>(b);
+  s.work_list = reinterpret_cast<int*>(b + 16);
+  const size_t cap = (size_t)(dof > 1 ? dof - 1 : 0) * (size_t)n;
+  double* q = reinterpret_cast<double*>(b + 16 + (((size_t)n * sizeof(int) + 15) / 16) * 16);
+  s.queue.t_req = q;
+  s.queue.q_goal = q + cap;
+  s.queue.q_0 = q + 2 * cap;
+  s.queue.v_0 = q + 3 * cap;
+  s.queue.a_0 = q + 4 * cap;
+  s.queue.where = reinterpret_cast<int2*>(q + 5 * cap);
   return s;
 }
 
@@ -159,7 +190,7 @@ __device__ __forceinline__ bool finish_problem(const SolveShared& sh, const Devi
     defer |= (sh.flag[i * kTile + lane] & 2) != 0;
   }
   S.slowest[p] = slowest;
-  S.traj_len[p] = (reached && !bad) ? len : 0;
+  S.traj_len[p] = defer ? kDeferredMark : ((reached && !bad) ? len : 0);
   S.reached[p] = (uint8_t)reached;
   return defer;
 }
@@ -178,11 +209,12 @@ template <int MAXW>
 __global__ void __launch_bounds__(kTile * MAXW, fast_min_blocks(MAXW))
 ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_goal,
                       const double* __restrict__ q_0, const double* __restrict__ v_0,
-                      const double* __restrict__ a_0, DeviceSolution S, int* __restrict__ work_list,
-                      int* __restrict__ work_count) {
+                      const double* __restrict__ a_0, DeviceSolution S, SolveScratch X) {
   extern __shared__ unsigned char smem_raw[];
   const int dof = P.dof;
   const SolveShared sh = carve_shared(smem_raw, dof);
+  int* const work_list = X.work_list;
+  int* const work_count = X.counters;
   const int lane = threadIdx.x, jt = threadIdx.y;
   const int64_t p = (int64_t)blockIdx.x * kTile + lane;
   const bool valid = p < n;
@@ -220,9 +252,9 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
   // a joint that needs the quartic tail has no t_opt yet: the whole problem is deferred
   const bool defer1 = (any & 2) != 0;
   const bool reached = !(any & 1) && slowest != -1;
-  if (jt == 0) sh.slowest[lane] = slowest;
   // stage 3 (cc:42-55), closed-form attempts only. Attempt 1 runs here; the joints it does
-  // not settle (about a third) are compacted over the CTA and attempt 2 runs on full warps.
+  // not settle (about a third) are queued for ltp_solve_attempt2_kernel, which runs attempt 2
+  // on full warps of such joints ("grouped by case").
   double t_sc[7];
   zero7(t_sc);
   double v_drive = L.v_max;
@@ -251,7 +283,8 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
       }
     }
   }
-  // compaction: slot = (items of the warps before mine) + (items of the lanes before mine)
+  // queue slot = base of this CTA (one atomic per CTA) + joints queued by the warps before
+  // mine + those of the lanes before mine
   const unsigned need_mask = __ballot_sync(0xffffffffu, need2);
   if (lane == 0) sh.warp_items[jt] = __popc(need_mask);
   __syncthreads();
@@ -261,49 +294,77 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
     before += (w < jt) ? c : 0;
     total += c;
   }
-  if (need2) {
-    Attempt2Item& it = sh.item[before + __popc(need_mask & ((1u << lane) - 1u))];
-    it.q_goal = qg; it.q_0 = q0; it.v_0 = v0; it.a_0 = a0; it.t_req = t_req;
-    it.lane = lane; it.jt = jt;
-  }
-  __syncthreads();
-  if (valid) {
-    store_joint_opt(S, dof, jt, n, p, t_opt, pro.dir, opt_case);
-    if (!need2) {
-      const int my_len = (reached && !defer1 && !my_defer) ? joint_samples(t_sc, Ts) : 0;
-      if (finish_problem(sh, S, dof, lane, jt, p, my_len, my_defer, reached, slowest)) {
-        const int slot = atomicAdd(work_count, 1);
-        work_list[slot] = (int)p;
-      }
-      store_joint_scaled(S, dof, jt, n, p, t_sc, v_drive, mod, ts_case, final_case);
+  if (total > 0) {  // uniform over the CTA
+    if (jt == 0 && lane == 0) sh.warp_items[dof + 1] = atomicAdd(X.counters + 1, total);
+    __syncthreads();
+    if (need2) {
+      const int e = sh.warp_items[dof + 1] + before + __popc(need_mask & ((1u << lane) - 1u));
+      X.queue.t_req[e] = t_req;
+      X.queue.q_goal[e] = qg;
+      X.queue.q_0[e] = q0;
+      X.queue.v_0[e] = v0;
+      X.queue.a_0[e] = a0;
+      X.queue.where[e] = make_int2((int)p, jt);
     }
   }
-  // attempt 2 on the compacted items (thread t takes item t; total <= blockDim)
-  const int tid = jt * kTile + lane;
-  if (tid >= total) return;
-  const Attempt2Item it = sh.item[tid];
-  const JointLimits L2 = P.lim[it.jt];
-  const Prologue pro2 = ost_prologue(L2, Ts, it.q_goal, it.q_0, it.v_0, it.a_0);
-  const TsInput I2 = make_ts_input(it.q_goal, it.q_0, it.v_0, it.a_0, pro2.dir, it.t_req);
-  double t2[7];
-  zero7(t2);
-  double v2 = L2.v_max;
-  unsigned char mod2 = 0, fc2 = 255;
-  const int c2 = time_scaling_attempt2(L2, Ts, pro2, I2, t2, v2, mod2, fc2);
-  double m2 = t2[0];
-#pragma unroll
-  for (int k = 1; k < 7; ++k)
-    if (m2 < t2[k]) m2 = t2[k];
-  // an accepted solve with no positive time falls back to the time-optimal times (cc:50-55),
-  // which this thread does not hold: leave that (degenerate) problem to the generic kernel
-  const bool defer2 = (c2 == 0) || (m2 <= 0.0);
-  const int64_t p2 = (int64_t)blockIdx.x * kTile + it.lane;
-  const int len2 = defer2 ? 0 : joint_samples(t2, Ts);
-  if (finish_problem(sh, S, dof, it.lane, it.jt, p2, len2, defer2, true, sh.slowest[it.lane])) {
+  if (!valid) return;
+  store_joint_opt(S, dof, jt, n, p, t_opt, pro.dir, opt_case);
+  // a queued joint contributes length 0 here; its length arrives by atomicMax later
+  const int my_len = (reached && !defer1 && !my_defer && !need2) ? joint_samples(t_sc, Ts) : 0;
+  if (finish_problem(sh, S, dof, lane, jt, p, my_len, my_defer, reached, slowest)) {
     const int slot = atomicAdd(work_count, 1);
-    work_list[slot] = (int)p2;
+    work_list[slot] = (int)p;
   }
-  store_joint_scaled(S, dof, it.jt, n, p2, t2, v2, mod2, (unsigned char)c2, fc2);
+  if (!need2) store_joint_scaled(S, dof, jt, n, p, t_sc, v_drive, mod, ts_case, final_case);
+}
+
+// Attempt 2 of the cruise-speed search (reference cc:408-446) for the queued joints: one
+// thread per entry, consecutive entries in consecutive lanes, so every lane of every warp
+// has the same work whatever the mix of joints that needed it. The start state comes with the
+// entry and the prologue is recomputed; results go straight to the solution arrays, the
+// sample count joins the problem's by atomicMax. A joint that attempt 2 does not settle
+// either sends its problem to the work list of the generic kernel (once per problem: the
+// exchange on traj_len elects the sender).
+#ifndef LTP_A2_MINB
+#define LTP_A2_MINB 2
+#endif
+__global__ void __launch_bounds__(256, LTP_A2_MINB)
+ltp_solve_attempt2_kernel(const __grid_constant__ PlannerParams P, int64_t n, DeviceSolution S, SolveScratch X) {
+  const int dof = P.dof;
+  const double Ts = P.ts;
+  const int count = X.counters[1];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+    const int2 where = X.queue.where[e];
+    const double t_req = X.queue.t_req[e];
+    const double qg = X.queue.q_goal[e], q0 = X.queue.q_0[e], v0 = X.queue.v_0[e], a0 = X.queue.a_0[e];
+    const int64_t p = where.x;
+    const int jt = where.y;
+    if (S.traj_len[p] == kDeferredMark) continue;  // already on its way to the generic kernel
+    const JointLimits L = P.lim[jt];
+    const Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0);
+    const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
+    double t[7];
+    zero7(t);
+    double v_drive = L.v_max;
+    unsigned char mod = 0, final_case = 255;
+    const int c = time_scaling_attempt2(L, Ts, pro, I, t, v_drive, mod, final_case);
+    double m = t[0];
+#pragma unroll
+    for (int k = 1; k < 7; ++k)
+      if (m < t[k]) m = t[k];
+    // an accepted solve with no positive time falls back to the time-optimal times (cc:50-55),
+    // which are not at hand here: that (degenerate) problem goes to the generic kernel too
+    const int len = (c == 0 || m <= 0.0) ? -1 : joint_samples(t, Ts);
+    if (len < 0) {
+      if (atomicExch(S.traj_len + p, kDeferredMark) != kDeferredMark) {
+        const int slot = atomicAdd(X.counters, 1);
+        X.work_list[slot] = (int)p;
+      }
+      continue;
+    }
+    store_joint_scaled(S, dof, jt, n, p, t, v_drive, mod, (unsigned char)c, final_case);
+    atomicMax(S.traj_len + p, len);
+  }
 }
 
 // every branch evaluated in-thread. work_list == nullptr: problem = tile index (generic-only
@@ -756,8 +817,9 @@ struct ltp_planner {
   size_t d_scratch_bytes;
   cudaStream_t stream;  // internal stream of the host entry points
   // work list of the two-kernel solve: [0] = count, [1..] = problem indices
-  int* d_work;
+  void* d_work;  // SolveScratch of ltp_solve_batch
   int64_t d_work_capacity;
+  int d_work_dof;
   int solve_mode;  // LTP_SOLVE_AUTO / LTP_SOLVE_GENERIC
   int sm_count;
   // optional per-kernel timing (ltp_set_profiling): CUDA events recorded on the launching
@@ -940,6 +1002,7 @@ int ltp_create(ltp_planner** out, int device, int dof, double t_sample, const do
   p->stream = nullptr;
   p->d_work = nullptr;
   p->d_work_capacity = 0;
+  p->d_work_dof = 0;
   p->solve_mode = LTP_SOLVE_AUTO;
   p->sm_count = 148;
   p->profiling = false;
@@ -1085,12 +1148,13 @@ int ltp_time_scaling_batch(ltp_planner* p, int64_t n, const double* q_goal, cons
 // launches of stages 1-3 on `st`. work: device buffer of n + 1 ints ([0] = count), only
 // touched in LTP_SOLVE_AUTO mode.
 static int solve_launch(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0, const double* v_0,
-                        const double* a_0, const ltp_solution* sol, int* work, cudaStream_t st) {
+                        const double* a_0, const ltp_solution* sol, void* scratch, cudaStream_t st) {
   const int dof = p->params.dof;
   const dim3 block(kTile, dof);
   const unsigned tiles = (unsigned)((n + kTile - 1) / kTile);
   const size_t smem = solve_smem_bytes(dof);
   const DeviceSolution ds = to_dev(sol);
+  const SolveScratch X = carve_scratch(scratch, dof, n);
 #define LTP_DISPATCH_W(KERNEL, GRID, ...)                                                   \
   do {                                                                                      \
     if (dof <= 1) KERNEL<1><<<GRID, block, smem, st>>>(__VA_ARGS__);                        \
@@ -1116,17 +1180,24 @@ static int solve_launch(ltp_planner* p, int64_t n, const double* q_goal, const d
     LTP_DISPATCH_W(ltp_solve_generic_kernel, tiles, p->params, n, q_goal, q_0, v_0, a_0, ds,
                    (const int*)nullptr, (const int*)nullptr);
   } else {
-    LTP_CUDA(cudaMemsetAsync(work, 0, sizeof(int), st));
+    LTP_CUDA(cudaMemsetAsync(X.counters, 0, 2 * sizeof(int), st));
     {
       ProfScope ps(p, LTP_PROFILE_SOLVE_FAST, st);
-      LTP_DISPATCH_FAST(tiles, p->params, n, q_goal, q_0, v_0, a_0, ds, work + 1, work);
+      LTP_DISPATCH_FAST(tiles, p->params, n, q_goal, q_0, v_0, a_0, ds, X);
     }
-    // the work list is drained by a fixed-size grid-stride launch: its length never leaves
-    // the device
+    // the queue and the work list are drained by fixed-size grid-stride launches: their
+    // lengths never leave the device
+    if (dof > 1) {
+      ProfScope ps(p, LTP_PROFILE_SOLVE_ATTEMPT2, st);
+      const int64_t want = ((int64_t)(dof - 1) * n + 255) / 256;
+      const int64_t cap = (int64_t)p->sm_count * 16;
+      ltp_solve_attempt2_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(p->params, n, ds, X);
+      p->launches++;
+    }
     const unsigned g2 = tiles < (unsigned)(p->sm_count * 4) ? tiles : (unsigned)(p->sm_count * 4);
     ProfScope ps(p, LTP_PROFILE_SOLVE_GENERIC, st);
     LTP_DISPATCH_W(ltp_solve_generic_kernel, g2, p->params, n, q_goal, q_0, v_0, a_0, ds,
-                   (const int*)(work + 1), (const int*)work);
+                   (const int*)X.work_list, (const int*)X.counters);
   }
 #undef LTP_DISPATCH_FAST
 #undef LTP_DISPATCH_W
@@ -1144,12 +1215,13 @@ int ltp_solve_batch(ltp_planner* p, int64_t n, const double* q_goal, const doubl
     return LTP_ERR_ARG;
   if (n > 0x7fffffff) return LTP_ERR_ARG;  // problem indices travel as int32 in the work list
   DeviceGuard g(p->device);
-  if (p->solve_mode != LTP_SOLVE_GENERIC && p->d_work_capacity < n) {
+  if (p->solve_mode != LTP_SOLVE_GENERIC && (p->d_work_capacity < n || p->d_work_dof < p->params.dof)) {
     if (p->d_work) LTP_CUDA(cudaFree(p->d_work));
     p->d_work = nullptr;
     p->d_work_capacity = 0;
-    LTP_CUDA(cudaMalloc(&p->d_work, sizeof(int) * (size_t)(n + 1)));
+    LTP_CUDA(cudaMalloc(&p->d_work, solve_scratch_bytes(p->params.dof, n)));
     p->d_work_capacity = n;
+    p->d_work_dof = p->params.dof;
   }
   return solve_launch(p, n, q_goal, q_0, v_0, a_0, sol, p->d_work, (cudaStream_t)stream);
 }
@@ -1227,10 +1299,10 @@ int ltp_solve_host(ltp_planner* p, int64_t n, const double* q_goal, const double
   const int slots = n > c_max ? 2 : 1;
   ltp_solution ds[2];
   double* d_in[2][4];
-  int* d_work[2];
+  void* d_work[2];
   const size_t in_bytes = up((size_t)dof * (size_t)c_max * 8, 256);
   const size_t sol_bytes = carve_solution(nullptr, dof, c_max, &ds[0]);
-  const size_t work_bytes = up(sizeof(int) * (size_t)(c_max + 1), 256);
+  const size_t work_bytes = up(solve_scratch_bytes(dof, c_max), 256);
   const size_t need = 4 * in_bytes + sol_bytes + work_bytes;
   for (int s = 0; s < slots; ++s) {
     if (!p->pipe_stream[s]) LTP_CUDA(cudaStreamCreateWithFlags(&p->pipe_stream[s], cudaStreamNonBlocking));
@@ -1244,7 +1316,7 @@ int ltp_solve_host(ltp_planner* p, int64_t n, const double* q_goal, const double
     unsigned char* base = (unsigned char*)p->pipe_buf[s];
     for (int i = 0; i < 4; ++i) d_in[s][i] = (double*)(base + i * in_bytes);
     carve_solution(base + 4 * in_bytes, dof, c_max, &ds[s]);
-    d_work[s] = (int*)(base + 4 * in_bytes + sol_bytes);
+    d_work[s] = base + 4 * in_bytes + sol_bytes;
     if (!hs->t_opt) ds[s].t_opt = nullptr;
     if (!hs->opt_case) ds[s].opt_case = nullptr;
     if (!hs->ts_case) ds[s].ts_case = nullptr;
@@ -1309,12 +1381,12 @@ int ltp_plan_stream(ltp_planner* p, int64_t n, const double* q_goal, const doubl
   // fields + success flags (ring_buf), all reused by every second chunk
   ltp_solution ds[2];
   double* d_in[2][4];
-  int* d_work[2];
+  void* d_work[2];
   double* d_traj[2][4];
   uint8_t* d_succ[2];
   const size_t in_bytes = up((size_t)dof * (size_t)c_max * 8, 256);
   const size_t sol_bytes = carve_solution(nullptr, dof, c_max, &ds[0]);
-  const size_t work_bytes = up(sizeof(int) * (size_t)(c_max + 1), 256);
+  const size_t work_bytes = up(solve_scratch_bytes(dof, c_max), 256);
   const size_t field_bytes = up((size_t)capacity * (size_t)c_max * (size_t)dof * 8, 256);
   const size_t succ_bytes = up((size_t)c_max, 256);
   for (int s = 0; s < slots; ++s) {
@@ -1327,7 +1399,7 @@ int ltp_plan_stream(ltp_planner* p, int64_t n, const double* q_goal, const doubl
     for (int i = 0; i < 4; ++i) d_in[s][i] = (double*)(base + i * in_bytes);
     carve_solution(base + 4 * in_bytes, dof, c_max, &ds[s]);
     ds[s].t_opt = nullptr; ds[s].opt_case = nullptr; ds[s].ts_case = nullptr; ds[s].final_case = nullptr;
-    d_work[s] = (int*)(base + 4 * in_bytes + sol_bytes);
+    d_work[s] = base + 4 * in_bytes + sol_bytes;
     unsigned char* ring = (unsigned char*)p->ring_buf[s];
     for (int i = 0; i < 4; ++i) d_traj[s][i] = (double*)(ring + i * field_bytes);
     d_succ[s] = ring + 4 * field_bytes;

@@ -22,7 +22,8 @@ for _ in range(20):
 ms, cnt = ltp.kernelTime("solve_fast")
 ms2, cnt2 = ltp.kernelTime("solve_generic")
 chk = int(sol.traj_len.sum().item())
-print(f"{os.environ.get('LTP_B200_LIB', 'default')}: dof {lim.dof} solve_fast {ms / cnt:.4f} ms -> {n / (ms / cnt) / 1e3:.1f} M plans/s; "
+ms3, cnt3 = ltp.kernelTime("solve_attempt2")
+print(f"{os.environ.get('LTP_B200_LIB', 'default')}: dof {lim.dof} solve_fast {ms / cnt:.4f} ms + attempt2 {ms3 / max(cnt3, 1):.4f} ms -> {n / (ms / cnt + ms3 / max(cnt3, 1)) / 1e3:.1f} M plans/s; "
       f"generic {ms2 / cnt2:.4f} ms; traj_len checksum {chk}", flush=True)
 if lim.dof == 7:
     n2, H = 4096, 2001
