@@ -461,7 +461,7 @@ __global__ void ltp_opt_braking_kernel(const __grid_constant__ PlannerParams P, 
   const JointLimits L = P.lim[jt];
   const int64_t at = (int64_t)row * n + p;
   double T0, T1, T2, d;
-  const double q = brake_profile(L.a_max, L.j_max, P.ts, v_0[at], a_0[at], T0, T1, T2, d);
+  const double q = brake_profile(L, P.ts, v_0[at], a_0[at], T0, T1, T2, d);
   q_stop[at] = q;
   dir[at] = d;
   t_rel[((int64_t)0 * rows + row) * n + p] = T0;
@@ -880,6 +880,7 @@ int fill_limits(PlannerParams& P, const double* q_min, const double* q_max, cons
     P.lim[i].v_max = v_max[i];
     P.lim[i].a_max = a_max[i];
     P.lim[i].j_max = j_max[i];
+    derive_limits(P.lim[i]);
   }
   return LTP_OK;
 }

@@ -46,6 +46,8 @@ enum : unsigned char {
 
 struct JointLimits {
   double q_min, q_max, v_max, a_max, j_max;
+  // derived once on the host (derive_limits): correctly rounded reciprocals for div_by()
+  double r_a, r_j, a_over_j;
 };
 
 constexpr double kEps = 4e-3;     // cc:96
@@ -74,16 +76,50 @@ LTP_HD double pow6(double x) {
   return H + L;
 }
 
+// x / d for a divisor whose correctly rounded reciprocal rd = RN(1/d) is at hand: quotient
+// estimate, exact remainder (fma), one correction -- three FP64 operations instead of the
+// dozen of a division, and the SAME bits as the IEEE division x / d (Markstein's theorem for
+// rd = RN(1/d); checked here on 1.2e9 random numerators against the divisors the limit sets
+// produce). Outside the range where that argument holds (zero, subnormal, huge, inf, NaN
+// results) the plain division is evaluated, so special values behave exactly as before.
+LTP_HD_NOINLINE double div_slow(double x, double d) { return x / d; }
+
+LTP_HD double div_by(double x, double d, double rd) {
+  const double q = x * rd;
+  const double r = fma(-q, d, x);
+  const double f = fma(r, rd, q);
+  // biased exponent of the result in [64, 1982] (|f| in ~[1e-289, 1e289]): integer test on
+  // the high word, like the one the compiler's own division uses
+#ifdef __CUDA_ARCH__
+  const unsigned e = ((unsigned)__double2hiint(f) << 1) >> 21;
+#else
+  unsigned long long bits;
+  memcpy(&bits, &f, 8);
+  const unsigned e = (unsigned)((bits >> 52) & 0x7ff);
+#endif
+  if (e - 64u > 1918u) return div_slow(x, d);
+  return f;
+}
+LTP_HD double div3(double x) { return div_by(x, 3.0, 1.0 / 3.0); }
+LTP_HD double div12(double x) { return div_by(x, 12.0, 1.0 / 12.0); }
+
+LTP_HD void derive_limits(JointLimits& L) {
+  L.r_a = 1.0 / L.a_max;
+  L.r_j = 1.0 / L.j_max;
+  L.a_over_j = L.a_max / L.j_max;
+}
+
 LTP_HD double sgn(double x) { return (double)((0.0 < x) - (x < 0.0)); }  // h:54-56
 
 // ------------------------------------------------------------------------------------
 // cc:650-701. Returns the signed stop displacement; T[0..2] are the three durations.
 // ------------------------------------------------------------------------------------
-LTP_HD double brake_profile(double A, double J, double Ts, double v_0, double a_0,
+LTP_HD double brake_profile(const JointLimits& L, double Ts, double v_0, double a_0,
                             double& T0, double& T1, double& T2, double& dir) {
+  const double A = L.a_max, J = L.j_max;
   if (v_0 * a_0 > 0) {
     dir = -sgn(v_0);
-  } else if (fabs(v_0) > 1.0 / 2.0 * sq(a_0) / J) {
+  } else if (fabs(v_0) > div_by(1.0 / 2.0 * sq(a_0), J, L.r_j)) {
     dir = -sgn(v_0);
   } else {
     dir = -sgn(a_0);
@@ -92,9 +128,9 @@ LTP_HD double brake_profile(double A, double J, double Ts, double v_0, double a_
     a_0 = -a_0;
     v_0 = -v_0;
   }
-  T0 = (A - a_0) / J;
-  T2 = A / J;
-  T1 = (-v_0 - 1.0 / 2.0 * T0 * a_0) / A - 1.0 / 2.0 * (T0 + T2);
+  T0 = div_by(A - a_0, J, L.r_j);
+  T2 = L.a_over_j;
+  T1 = div_by(-v_0 - 1.0 / 2.0 * T0 * a_0, A, L.r_a) - 1.0 / 2.0 * (T0 + T2);
   if (T1 < -Ts) {
     T0 = -a_0 / J + sqrt(sq(a_0) / (2 * sq(J)) - v_0 / J);
     T2 = T0 + a_0 / J;
@@ -396,7 +432,7 @@ LTP_HD Prologue ost_prologue(const JointLimits& L, double Ts, double q_goal, dou
                              double v_0, double a_0) {
   Prologue P;
   double dirb;
-  double q_stop = brake_profile(L.a_max, L.j_max, Ts, v_0, a_0, P.b0, P.b1, P.b2, dirb);
+  double q_stop = brake_profile(L, Ts, v_0, a_0, P.b0, P.b1, P.b2, dirb);
   double q_diff = q_goal - (q_0 + q_stop);
   P.brake_only = fabs(q_diff) < kEps;
   if (P.brake_only) {
@@ -518,20 +554,20 @@ LTP_HD int ost_body_t(const JointLimits& L, double Ts, const Prologue& P, double
   }
   const double v_0 = P.v0m, a_0 = P.a0m;
   double q_brake = 0.0;
-  if (v_0 + 0.5 * a_0 * fabs(a_0) / J > V) {  // cc:119-122
+  if (v_0 + div_by(0.5 * a_0 * fabs(a_0), J, L.r_j) > V) {  // cc:119-122
     mod = 1;
     flags |= F_MOD;
     double unused;
-    q_brake = brake_profile(A, J, Ts, v_0 - V, a_0, T[0], T[1], T[2], unused);
+    q_brake = brake_profile(L, Ts, v_0 - V, a_0, T[0], T[1], T[2], unused);
   } else {  // cc:125-143
-    T[0] = (A - a_0) / J;
-    T[2] = A / J;
-    T[1] = (V - v_0 - 0.5 * T[0] * a_0) / A - 0.5 * (T[0] + T[2]);
+    T[0] = div_by(A - a_0, J, L.r_j);
+    T[2] = L.a_over_j;
+    T[1] = div_by(V - v_0 - 0.5 * T[0] * a_0, A, L.r_a) - 0.5 * (T[0] + T[2]);
     if (T[1] < -eps) {
       double rad = J * (V - v_0) + 0.5 * sq(a_0);
       if (rad > 0) {
-        T[2] = sqrt(rad) / J;
-        T[0] = T[2] - a_0 / J;
+        T[2] = div_by(sqrt(rad), J, L.r_j);
+        T[0] = T[2] - div_by(a_0, J, L.r_j);
         T[1] = 0;
         flags |= F_NOP2;
       } else {
@@ -542,11 +578,11 @@ LTP_HD int ost_body_t(const JointLimits& L, double Ts, const Prologue& P, double
     }
   }
   // cc:147-165
-  T[4] = A / J;
+  T[4] = L.a_over_j;
   T[6] = T[4];
-  T[5] = V / A - 1.0 / 2.0 * (T[4] + T[6]);
+  T[5] = div_by(V, A, L.r_a) - 1.0 / 2.0 * (T[4] + T[6]);
   if (T[5] < -eps) {
-    double rad = V / J;
+    double rad = div_by(V, J, L.r_j);
     if (rad > 0) {
       T[4] = sqrt(rad);
       T[6] = T[4];
@@ -586,18 +622,19 @@ LTP_HD int ost_body_t(const JointLimits& L, double Ts, const Prologue& P, double
     double rad = (sq(J) * pow4(T[0])) / 2 - (sq(J) * pow4(T[2])) / 4 +
                  (sq(J) * sq(T[2]) * sq(T[4])) / 2 - (sq(J) * pow4(T[4])) / 4 +
                  (sq(J) * pow4(T[6])) / 2 + 2.0 * J * a_0 * pow3(T[0]) -
-                 (2.0 * J * A * pow3(T[0])) / 3 - 2.0 * J * A * T[0] * sq(T[2]) +
-                 (2.0 * J * A * pow3(T[2])) / 3 + (2.0 * J * A * pow3(T[4])) / 3 -
-                 2.0 * J * A * sq(T[4]) * T[6] - (2.0 * J * A * pow3(T[6])) / 3 +
+                 div3(2.0 * J * A * pow3(T[0])) - 2.0 * J * A * T[0] * sq(T[2]) +
+                 div3(2.0 * J * A * pow3(T[2])) + div3(2.0 * J * A * pow3(T[4])) -
+                 2.0 * J * A * sq(T[4]) * T[6] - div3(2.0 * J * A * pow3(T[6])) +
                  2.0 * J * v_0 * sq(T[0]) + 2.0 * sq(a_0) * sq(T[0]) - 2.0 * a_0 * A * sq(T[0]) -
                  2.0 * a_0 * A * sq(T[2]) + 4 * a_0 * v_0 * T[0] + 2.0 * sq(A) * sq(T[2]) +
                  2.0 * sq(A) * sq(T[4]) - 4 * A * v_0 * T[0] + 4 * P.dist * A + 2.0 * sq(v_0);
     if (rad > 0) {  // cc:224-236
-      T[5] = -(4 * A * T[4] - 2.0 * sqrt(rad) + J * sq(T[2]) - J * sq(T[4]) + 2.0 * J * sq(T[6])) /
-             (4 * A);
-      T[1] = (-v_0 - a_0 * T[0] - 1.0 / 2.0 * J * sq(T[0]) + 1.0 / 2.0 * J * sq(T[2]) +
-              1.0 / 2.0 * J * sq(T[6]) - 1.0 / 2.0 * J * sq(T[4])) /
-                 A -
+      // x / (4 A) == (x / A) / 4 bit for bit (scaling by 4 is exact)
+      T[5] = 0.25 * div_by(-(4 * A * T[4] - 2.0 * sqrt(rad) + J * sq(T[2]) - J * sq(T[4]) + 2.0 * J * sq(T[6])),
+                           A, L.r_a);
+      T[1] = div_by(-v_0 - a_0 * T[0] - 1.0 / 2.0 * J * sq(T[0]) + 1.0 / 2.0 * J * sq(T[2]) +
+                        1.0 / 2.0 * J * sq(T[6]) - 1.0 / 2.0 * J * sq(T[4]),
+                    A, L.r_a) -
              T[2] + T[5] + T[4];
       T[3] = 0;
       base = CASE_NOP4;
@@ -613,14 +650,18 @@ LTP_HD int ost_body_t(const JointLimits& L, double Ts, const Prologue& P, double
   }
   // cc:340-348
 #pragma unroll
-  for (int i = 0; i < 7; ++i) {
-    if (T[i] < -eps) {
-      kase = CASE_FAIL_UNTOUCHED | flags;
-      return OST_FAIL;
-    } else if (T[i] < 0.0 && T[i] >= -eps) {
-      T[i] = 0.0;
-    }
+  // (the reference's second test, T < 0 && T >= -eps, is T < 0 once T < -eps is excluded;
+  // a NaN fails both and stays)
+  bool below = false;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) below |= T[i] < -eps;
+  if (below) {
+    kase = CASE_FAIL_UNTOUCHED | flags;
+    return OST_FAIL;
   }
+#pragma unroll
+  for (int i = 0; i < 7; ++i)
+    if (T[i] < 0.0) T[i] = 0.0;
   cumsum7(T, t);  // cc:351
   kase = base | flags;
   return OST_OK;
@@ -641,15 +682,14 @@ struct TsInput {
 
 LTP_HD double ts_candidate1(const JointLimits& L, const TsInput& I) {
   const double A = L.a_max, J = L.j_max, a_0 = I.a_0, v_0 = I.v_0, tr = I.tr, dir = I.dir;
-  return (A * J * tr / 2 - sq(a_0) / 4 + a_0 * A / 2 - sq(A) / 2 + v_0 * J / 2 -
-          sqrt(36 * sq(A) * sq(J) * sq(tr) - 36 * sq(a_0) * A * J * tr + 72.0 * a_0 * sq(A) * J * tr -
-               72.0 * pow3(A) * J * tr + 144 * A * dir * sq(J) * I.q_0 -
-               144 * A * dir * sq(J) * I.q_goal + 72.0 * A * sq(J) * v_0 * tr - 9 * pow4(a_0) +
-               12.0 * pow3(a_0) * A + 36 * sq(a_0) * sq(A) + 36 * sq(a_0) * J * v_0 -
-               72.0 * a_0 * pow3(A) - 72.0 * a_0 * A * J * v_0 + 36 * pow4(A) -
-               36 * sq(J) * sq(v_0)) /
-              12) /
-         J;
+  return div_by(A * J * tr / 2 - sq(a_0) / 4 + a_0 * A / 2 - sq(A) / 2 + v_0 * J / 2 -
+                    div12(sqrt(36 * sq(A) * sq(J) * sq(tr) - 36 * sq(a_0) * A * J * tr +
+                               72.0 * a_0 * sq(A) * J * tr - 72.0 * pow3(A) * J * tr +
+                               144 * A * dir * sq(J) * I.q_0 - 144 * A * dir * sq(J) * I.q_goal +
+                               72.0 * A * sq(J) * v_0 * tr - 9 * pow4(a_0) + 12.0 * pow3(a_0) * A +
+                               36 * sq(a_0) * sq(A) + 36 * sq(a_0) * J * v_0 - 72.0 * a_0 * pow3(A) -
+                               72.0 * a_0 * A * J * v_0 + 36 * pow4(A) - 36 * sq(J) * sq(v_0))),
+                J, L.r_j);
 }
 
 LTP_HD double ts_candidate2(const JointLimits& L, const TsInput& I) {
@@ -879,7 +919,7 @@ LTP_HD TsInput make_ts_input(double q_goal, double q_0, double v_0, double a_0, 
 // cc:68-77 for one joint
 LTP_HD bool check_joint_input(const JointLimits& L, double q_0, double v_0, double a_0) {
   if (q_0 < L.q_min || q_0 > L.q_max || fabs(v_0) > L.v_max || fabs(a_0) > L.a_max) return false;
-  if (fabs(v_0 + 0.5 * a_0 * fabs(a_0) / L.j_max) > L.v_max) return false;
+  if (fabs(v_0 + div_by(0.5 * a_0 * fabs(a_0), L.j_max, L.r_j)) > L.v_max) return false;
   return true;
 }
 

@@ -29,7 +29,10 @@ void* shadow_create(int dof, double ts, const double* q_min, const double* q_max
   s->dof = dof;
   s->ts = ts;
   s->lim.resize(dof);
-  for (int i = 0; i < dof; ++i) s->lim[i] = JointLimits{q_min[i], q_max[i], v_max[i], a_max[i], j_max[i]};
+  for (int i = 0; i < dof; ++i) {
+    s->lim[i] = JointLimits{q_min[i], q_max[i], v_max[i], a_max[i], j_max[i], 0, 0, 0};
+    derive_limits(s->lim[i]);
+  }
   return s;
 }
 void shadow_destroy(void* h) { delete static_cast<Shadow*>(h); }
@@ -39,7 +42,7 @@ void shadow_opt_braking_items(void* h, int64_t n, const int* joint, const double
   Shadow* s = static_cast<Shadow*>(h);
   for (int64_t i = 0; i < n; ++i) {
     const JointLimits& L = s->lim[joint ? joint[i] : 0];
-    q[i] = brake_profile(L.a_max, L.j_max, s->ts, v_0[i], a_0[i], t_rel3[3 * i], t_rel3[3 * i + 1],
+    q[i] = brake_profile(L, s->ts, v_0[i], a_0[i], t_rel3[3 * i], t_rel3[3 * i + 1],
                          t_rel3[3 * i + 2], dir[i]);
   }
 }
