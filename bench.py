@@ -137,8 +137,15 @@ def bind_to_gpu_numa_node(index):
     Returns the node, or None where the topology is not exposed."""
     try:
         import torch
-        pr = torch.cuda.get_device_properties(index)
-        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        try:
+            pr = torch.cuda.get_device_properties(index)
+            bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        except AttributeError:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = vis.split(",")[index] if vis else str(index)
+            out = subprocess.run(["nvidia-smi", f"--id={phys}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=20).stdout.strip()
+            bdf = out.lower()[-12:]  # 00000000:1B:00.0 -> 0000:1b:00.0
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
         if node < 0:
             return None

@@ -138,6 +138,18 @@ class LongTermPlanner {
   int planTrajectories(int64_t n, const double* q_goal, const double* q_0, const double* v_0,
                        const double* a_0, const BatchPlan& plan, void* stream = nullptr);
 
+  /// NEW: planTrajectories for more trajectories than fit in memory (ltp_plan_stream): the run
+  /// is cut into chunks of `chunk` problems that are solved and sampled (time-major) into a
+  /// two-slot ring and handed to `consume` (see ltp_b200.h). Synchronises before returning.
+  int planStream(int64_t n, const double* q_goal, const double* q_0, const double* v_0, const double* a_0,
+                 int64_t chunk, int32_t horizon, int64_t capacity, ltp_chunk_consumer consume, void* user,
+                 ltp_stream_stats* stats = nullptr);
+
+  /// NEW: receding-horizon step (ltp_advance_batch): the state `tick` samples into time-major
+  /// trajectories becomes the next start state, clamped to what checkInputs accepts.
+  int advance(int64_t n, int32_t tick, const int32_t* traj_len, const uint8_t* valid, const double* q,
+              const double* v, const double* a, double* q_0, double* v_0, double* a_0, void* stream = nullptr);
+
  protected:
   /// reference long_term_planner.h:223-231, long_term_planner.cc:82-353
   bool optSwitchTimes(int joint, double q_goal, double q_0, double v_0, double a_0, double v_drive,

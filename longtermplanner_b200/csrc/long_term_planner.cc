@@ -94,6 +94,18 @@ int LongTermPlanner::planTrajectories(int64_t n, const double* q_goal, const dou
                           plan.v, plan.a, plan.j, plan.success, stream);
 }
 
+int LongTermPlanner::planStream(int64_t n, const double* q_goal, const double* q_0, const double* v_0,
+                                const double* a_0, int64_t chunk, int32_t horizon, int64_t capacity,
+                                ltp_chunk_consumer consume, void* user, ltp_stream_stats* stats) {
+  return ltp_plan_stream(handle(), n, q_goal, q_0, v_0, a_0, chunk, horizon, capacity, consume, user, stats);
+}
+
+int LongTermPlanner::advance(int64_t n, int32_t tick, const int32_t* traj_len, const uint8_t* valid,
+                             const double* q, const double* v, const double* a, double* q_0, double* v_0,
+                             double* a_0, void* stream) {
+  return ltp_advance_batch(handle(), n, tick, 1, traj_len, valid, q, v, a, q_0, v_0, a_0, stream);
+}
+
 bool LongTermPlanner::optSwitchTimes(int joint, double q_goal, double q_0, double v_0, double a_0,
                                      double v_drive, std::array<double, 7>& t, double& dir,
                                      char& mod_jerk_profile) {

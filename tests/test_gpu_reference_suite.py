@@ -34,3 +34,14 @@ def test_reference_gtest_case(name):
 def test_reference_grid_time_scaling():
     out = _run("GridTimeScalingTest")
     assert "[       OK ] LongTermPlannerTest1DoF.GridTimeScalingTest" in out
+
+
+CPP_BIN = os.path.join(HERE, "_build", "batched_dropin_test")
+
+
+@pytest.mark.skipif(not os.path.exists(CPP_BIN), reason="tests/build_cpp_tests.sh has not run")
+def test_cpp_batched_entry_points_of_the_dropin_class():
+    """tests/cpp/batched_dropin_test.cc: planTrajectories == planTrajectory bit for bit,
+    planStream chunking and totals, advance"""
+    r = subprocess.run([CPP_BIN], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "0 checks failed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
