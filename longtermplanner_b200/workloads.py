@@ -99,6 +99,43 @@ def random_states(lim: Limits, n: int, seed: int, start: int = 0, margin: float 
     return q_goal, q_0, v_0, a_0
 
 
+def edge_states(lim: Limits, n: int, seed: int):
+    """Random states with the situations a replanning controller produces mixed in per joint
+    (the reference's own tests only visit them on a single joint, tests.cc:111-196): joints that
+    hold position (goal = start, at rest), goals inside the 4e-3 brake-only window (cc:102),
+    tiny moves with tiny start velocities/accelerations (1e-9 .. 1e-3), joints at a velocity or
+    position limit, and whole problems at rest at their goal. Same return convention as
+    random_states."""
+    q_goal, q_0, v_0, a_0 = (x.copy() for x in random_states(lim, n, seed))
+    q_min, q_max, v_max, a_max, j_max = lim.arrays()
+    rng = np.random.default_rng(seed)
+    kind = rng.random((n, lim.dof))
+    hold = kind < 0.30
+    window = (kind >= 0.30) & (kind < 0.40)
+    tiny = (kind >= 0.40) & (kind < 0.50)
+    at_v = (kind >= 0.50) & (kind < 0.55)
+    at_q = (kind >= 0.55) & (kind < 0.58)
+    v_0[hold | window] = 0.0
+    a_0[hold | window] = 0.0
+    q_goal[hold] = q_0[hold]
+    q_goal[window] = (q_0 + rng.uniform(-3.9e-3, 3.9e-3, q_0.shape))[window]
+    mag = 10.0 ** rng.uniform(-9, -3, q_0.shape)
+    v_0[tiny] = (mag * rng.choice([-1.0, 1.0], q_0.shape))[tiny]
+    a_0[tiny] = (mag[:, ::-1] * rng.choice([-1.0, 1.0], q_0.shape))[tiny]
+    q_goal[tiny] = (q_0 + rng.uniform(-0.05, 0.05, q_0.shape))[tiny]
+    v_0[at_v] = (np.broadcast_to(v_max, q_0.shape) * rng.choice([-1.0, 1.0], q_0.shape))[at_v]
+    a_0[at_v] = 0.0
+    q_0[at_q] = np.broadcast_to(q_min, q_0.shape)[at_q]
+    v_0[at_q] = np.abs(v_0[at_q]) * 0.1
+    a_0[at_q] = 0.0
+    rest = rng.random(n) < 0.02
+    v_0[rest] = 0.0
+    a_0[rest] = 0.0
+    q_goal[rest] = q_0[rest]
+    q_goal = np.clip(q_goal, q_min, q_max)
+    return q_goal, q_0, v_0, a_0
+
+
 def to_joint_major(x: np.ndarray) -> np.ndarray:
     """[n, dof] -> contiguous [dof, n]."""
     return np.ascontiguousarray(x.T)

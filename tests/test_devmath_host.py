@@ -74,6 +74,20 @@ def test_device_math_solve_matches_oracle(lim, n, seed):
         assert bitdiff(got[k], ref[k]) < 1e-3 * ref[k].size, k
 
 
+@pytest.mark.parametrize("lim,n,seed", [(W.FRANKA7, 30_000, 301), (W.REF_RANDOM6, 30_000, 302)])
+def test_device_math_on_controller_like_states(lim, n, seed):
+    """joints holding position, goals inside the brake-only window, tiny moves, states on a
+    limit (workloads.edge_states): closed-form pass + deferral vs the oracle, all fields"""
+    qg, q0, v0, a0 = W.edge_states(lim, n, seed)
+    ref = OraclePort.from_limits(lim).solve(qg, q0, v0, a0, threads=4)
+    got = ShadowAuto.from_limits(lim).solve(qg, q0, v0, a0)
+    for k in ("dir", "mod", "opt_case", "ts_case", "final_case", "slowest", "traj_len", "reached"):
+        assert np.array_equal(got[k], ref[k]), k
+    for k in ("t_opt", "t_scaled", "v_drive"):
+        assert count_bad(got[k], ref[k]) == 0, k
+    assert (ref["ts_case"] == 9).mean() > 0.2  # the brake-only shortcut is what this exercises
+
+
 def test_device_math_sampler_is_bit_exact():
     for lim, n, seed in ((W.FRANKA7, 40, 211), (W.REF_RANDOM6, 300, 212)):
         qg, q0, v0, a0 = W.random_states(lim, n, seed)

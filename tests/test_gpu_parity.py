@@ -46,6 +46,38 @@ def test_solve_matches_oracle(lim, n, seed):
         assert count_bad(got, ref[k]) == 0, (k, bitdiff(got, ref[k]))
 
 
+@pytest.mark.parametrize("lim,n,seed", [(W.FRANKA7, 50_000, 301), (W.REF_RANDOM6, 30_000, 302), (W.FRANKA12, 10_000, 303)])
+def test_controller_like_states_match_oracle(lim, n, seed):
+    """what a replanning controller feeds the planner (workloads.edge_states): joints holding
+    position, goals inside the brake-only window, tiny moves, states on a limit, whole arms at
+    rest -- solve (all three kernels) and sampled trajectories against the oracle"""
+    qg, q0, v0, a0 = W.edge_states(lim, n, seed)
+    ltp = _planner(lim)
+    ins = [_dev(jm(x)) for x in (qg, q0, v0, a0)]
+    sol = ltp.solve(*ins, with_opt=True, with_cases=True)
+    torch.cuda.synchronize()
+    P = OraclePort.from_limits(lim)
+    ref = P.solve(qg, q0, v0, a0, threads=8)
+    for k in ("reached", "slowest", "traj_len"):
+        assert np.array_equal(getattr(sol, k).cpu().numpy(), ref[k]), k
+    for k in ("mod", "opt_case", "ts_case", "final_case", "dir"):
+        assert np.array_equal(pm(getattr(sol, k).cpu().numpy()), ref[k]), k
+    for k in ("t_opt", "t_scaled", "v_drive"):
+        assert count_bad(pm(getattr(sol, k).cpu().numpy()), ref[k]) == 0, k
+    m = 64
+    sub = [t[:, :m].contiguous() for t in ins]
+    sol_m = ltp.solve(*sub)
+    traj = ltp.sample(sub[1], sub[2], sub[3], sol_m)
+    torch.cuda.synchronize()
+    rows = _rows(traj)
+    succ = traj.success.cpu().numpy()
+    for i in range(m):
+        full = P.plan(qg[i], q0[i], v0[i], a0[i])
+        assert full["length"] == ref["traj_len"][i] and bool(succ[i]) == full["success"], i
+        for k in "qvaj":
+            assert count_bad(rows[k][i][:, :full["length"]], full[k]) == 0, (i, k)
+
+
 def test_solve_matches_reference_build():
     """same, against the reference's own .cc (oracle/_ref), observable fields only"""
     if not Reference.available():

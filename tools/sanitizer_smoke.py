@@ -1,0 +1,28 @@
+"""Small end-to-end pass for compute-sanitizer (memcheck / racecheck / initcheck): every kernel
+of the library on a few hundred problems, both limit sets (the toy limits exercise the root
+solver and the work list). Usage: compute-sanitizer --tool memcheck python tools/sanitizer_smoke.py"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from longtermplanner_b200 import LongTermPlanner, devtools, workloads as W  # noqa: E402
+
+for lim, n in ((W.FRANKA7, 333), (W.REF_RANDOM6, 257), (W.FRANKA12, 100), (W.REF_GRID, 500)):
+    ltp = LongTermPlanner(lim.dof, lim.t_sample, *lim.arrays(), device=0)
+    ins = devtools.random_states_device(lim, n, 11)
+    sol = ltp.solve(*ins, with_opt=True, with_cases=True)
+    for layout in ("time_major", "rows"):
+        traj = ltp.sample(ins[1], ins[2], ins[3], sol, layout=layout)
+        fixed = ltp.sample(ins[1], ins[2], ins[3], sol, horizon=300, layout=layout)
+    ltp.advance(fixed if fixed.layout == "time_major" else ltp.sample(ins[1], ins[2], ins[3], sol, horizon=300),
+                9, *[t.clone() for t in ins[1:]])
+    ltp.planStream(*ins, chunk=128, capacity=max(int(sol.traj_len.max()), 1))
+    ltp.setSolveMode(True)
+    ltp.solve(*ins)
+    ltp.optBrakingBatch(ins[2], ins[3])
+    o = ltp.optSwitchTimesBatch(*ins, torch.full_like(ins[0], float(lim.v_max[0])))
+    ltp.timeScalingBatch(*ins, o["dir"], (o["t"][6] + 0.2).contiguous())
+    torch.cuda.synchronize()
+    print(lim.name, "ok", int(sol.reached.sum()), "reached")
