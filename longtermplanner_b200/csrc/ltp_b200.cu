@@ -333,13 +333,29 @@ ltp_solve_attempt2_kernel(const __grid_constant__ PlannerParams P, int64_t n, De
   const int dof = P.dof;
   const double Ts = P.ts;
   const int count = X.counters[1];
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
-    const int2 where = X.queue.where[e];
-    const double t_req = X.queue.t_req[e];
-    const double qg = X.queue.q_goal[e], q0 = X.queue.q_0[e], v0 = X.queue.v_0[e], a0 = X.queue.a_0[e];
+  const int step = gridDim.x * blockDim.x;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= count) return;
+  // software pipeline: the next entry's six loads are in flight while this one is evaluated
+  // (the kernel was waiting on memory for half of its cycles, four warps per scheduler)
+  int2 where = X.queue.where[e];
+  double t_req = X.queue.t_req[e], qg = X.queue.q_goal[e], q0 = X.queue.q_0[e], v0 = X.queue.v_0[e],
+         a0 = X.queue.a_0[e];
+  while (true) {
+    const int en = e + step;
+    const bool more = en < count;
+    int2 where_n = where;
+    double t_req_n = 0, qg_n = 0, q0_n = 0, v0_n = 0, a0_n = 0;
+    if (more) {
+      where_n = X.queue.where[en];
+      t_req_n = X.queue.t_req[en]; qg_n = X.queue.q_goal[en]; q0_n = X.queue.q_0[en];
+      v0_n = X.queue.v_0[en]; a0_n = X.queue.a_0[en];
+    }
     const int64_t p = where.x;
     const int jt = where.y;
-    if (S.traj_len[p] == kDeferredMark) continue;  // already on its way to the generic kernel
+    // (a problem that is already on its way to the generic kernel is not skipped: what is
+    // stored here is overwritten there, and a look at traj_len first costs a second trip to
+    // memory per entry)
     const JointLimits L = P.lim[jt];
     const Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0);
     const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
@@ -360,10 +376,14 @@ ltp_solve_attempt2_kernel(const __grid_constant__ PlannerParams P, int64_t n, De
         const int slot = atomicAdd(X.counters, 1);
         X.work_list[slot] = (int)p;
       }
-      continue;
+    } else {
+      store_joint_scaled(S, dof, jt, n, p, t, v_drive, mod, (unsigned char)c, final_case);
+      atomicMax(S.traj_len + p, len);
     }
-    store_joint_scaled(S, dof, jt, n, p, t, v_drive, mod, (unsigned char)c, final_case);
-    atomicMax(S.traj_len + p, len);
+    if (!more) break;
+    e = en;
+    where = where_n;
+    t_req = t_req_n; qg = qg_n; q0 = q0_n; v0 = v0_n; a0 = a0_n;
   }
 }
 
