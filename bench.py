@@ -227,6 +227,44 @@ def replan_loop(ltp, lim, dev, hbm_peak, n_env=4096, horizon=2001, tick=9, ticks
             "timing": "CUDA events around 50 graph replays (solve fast + work-list kernel + sampler + state gather)"}
 
 
+def single_plan_latency(ltp, lim, calls=300, cpu_plans=2000):
+    """configs[0]: one 7-DoF planTrajectory at a time through the host-buffer C ABI (ltp_plan_host,
+    n = 1: inputs in, solve, dense sampling, the q/v/a/j rows back out), wall clock per call, next
+    to the reference's own planTrajectory on one host core."""
+    from longtermplanner_b200 import _capi as capi
+    qg, q0, v0, a0 = W.random_states(lim, max(calls, cpu_plans), W.SEEDS[1])
+    cap = 4096
+    rows = [np.empty((lim.dof, cap)) for _ in range(4)]
+    ln, ok, needed = np.zeros(1, np.int32), np.zeros(1, np.uint8), capi.i64(0)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    us = []
+    for k in range(calls + 20):
+        ins = [np.ascontiguousarray(x[k]) for x in (qg, q0, v0, a0)]
+        t0 = time.perf_counter()
+        rc = capi.plan_host(ltp._h, 1, *[vp(x) for x in ins], 0, cap, *[vp(r) for r in rows], vp(ln), vp(ok),
+                            C.byref(needed))
+        dt = time.perf_counter() - t0
+        assert rc == 0, rc
+        if k >= 20:
+            us.append(dt * 1e6)
+    out = {"workload": "configs[0]: single 7-DoF planTrajectory (FRANKA7, t_sample 1 ms, random states), "
+                       "solve + dense sampling, pageable host buffers in and out, one call at a time",
+           "gpu_us_per_plan_median": float(np.median(us)), "gpu_us_per_plan_p90": float(np.percentile(us, 90)),
+           "calls": calls, "mean_samples_per_plan": None}
+    try:
+        chk, kind = cpu_checker(lim)
+        chk.plan_batch(qg[:64], q0[:64], v0[:64], a0[:64], threads=1)
+        t0 = time.perf_counter()
+        r = chk.plan_batch(qg[:cpu_plans], q0[:cpu_plans], v0[:cpu_plans], a0[:cpu_plans], threads=1)
+        out["cpu_us_per_plan"] = (time.perf_counter() - t0) * 1e6 / cpu_plans
+        out["cpu_kind"] = kind
+        out["mean_samples_per_plan"] = float(np.mean(r["length"]))
+    except Exception as e:
+        out["cpu_us_per_plan"] = None
+        out["cpu_kind"] = f"unavailable: {e}"
+    return out
+
+
 def load_probe():
     from longtermplanner_b200 import _build
     path = _build.PROBELIB
@@ -246,6 +284,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stream", action="store_true")
     ap.add_argument("--no-replan", action="store_true")
+    ap.add_argument("--no-single", action="store_true")
     ap.add_argument("--stream-log2n", type=int, default=26, help="configs[4]: total problems = 2^k over all GPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -477,6 +516,10 @@ def main():
         # ---- configs[2] as a loop: replan every 10 ms from the state the previous plan reached ----
         if not args.no_replan and not args.no_sampler:
             extra["replan"] = replan_loop(ltp, lim, dev, hbm_peak)
+
+        # ---- configs[0]: one planTrajectory at a time -----------------------------------------
+        if not args.no_single and world == 1:
+            extra["single_plan"] = single_plan_latency(ltp, lim)
 
         # ---- CPU baseline: the reference's code on this box's host cores ---------------------
         if not args.no_cpu and world == 1:

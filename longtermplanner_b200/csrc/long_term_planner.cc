@@ -52,11 +52,13 @@ bool LongTermPlanner::planTrajectory(const std::vector<double>& q_goal, const st
   if (dof_ < 1) return false;
   ltp_planner* h = handle();
   int64_t cap = 4096, needed = 0;
-  std::vector<double> rows;
+  // receive buffer, kept between calls (every sample that is read back below was written by
+  // the call; nothing relies on a fill)
+  thread_local std::vector<double> rows;
   int32_t len = 0;
   uint8_t ok = 0;
   for (;;) {
-    rows.assign((size_t)4 * dof_ * cap, 0.0);
+    if (rows.size() < (size_t)4 * dof_ * cap) rows.resize((size_t)4 * dof_ * cap);
     double* q = rows.data();
     double* v = q + (size_t)dof_ * cap;
     double* a = v + (size_t)dof_ * cap;

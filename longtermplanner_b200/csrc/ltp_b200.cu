@@ -634,6 +634,98 @@ ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, int ppb, c
   }
 }
 
+// Latency variant of the row sampler for a handful of rows (the single-plan host calls): one
+// row per CTA, one thread. The batch kernels above hide the latency of the per-sample chain
+// (table look-up, then a -> v -> q) behind thousands of other rows; with seven rows in flight
+// that chain, ~115 cycles per sample, IS the run time. Here the row is walked piece by piece:
+// inside a piece the jerk and the update rule are constants, so the three recurrences
+// a += Ts*j, v += Ts*a, q += Ts*v are three independent chains of one dependent add per sample
+// and run overlapped, four samples per iteration. Same operations on the same operands as
+// SegCursorT::step, hence the same bits. Writes row_ok[row] (1 = the row ends inside its joint
+// limits, cc:59-61); the caller combines the rows of a problem.
+template <bool LIVE, bool CRUISE>
+__device__ __forceinline__ void run_piece(int& i, const int stop, const int n_out, const int len, const double Ts,
+                                          const double jv, const double vcruise, double& a, double& v, double& q,
+                                          double& q_last, double* qo, double* vo, double* ao, double* jo) {
+  const double c = Ts * jv;
+  while (i < stop) {
+    if ((i & 3) == 0 && i + 4 <= stop && i + 4 <= n_out) {
+      double aa[4], vv[4], qq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a = LIVE ? a + c : 0.0;
+        v = CRUISE ? vcruise : (LIVE ? v + Ts * a : 0.0);
+        q = q + Ts * v;
+        aa[u] = a; vv[u] = v; qq[u] = q;
+      }
+      const unsigned k = (unsigned)(len - 1 - i);
+      if (k < 4u) q_last = k == 0 ? qq[0] : k == 1 ? qq[1] : k == 2 ? qq[2] : qq[3];
+      store4(qo + i, qq[0], qq[1], qq[2], qq[3]);
+      store4(vo + i, vv[0], vv[1], vv[2], vv[3]);
+      store4(ao + i, aa[0], aa[1], aa[2], aa[3]);
+      store4(jo + i, jv, jv, jv, jv);
+      i += 4;
+    } else {
+      a = LIVE ? a + c : 0.0;
+      v = CRUISE ? vcruise : (LIVE ? v + Ts * a : 0.0);
+      q = q + Ts * v;
+      if (i == len - 1) q_last = q;
+      if (i < n_out) {
+        qo[i] = q; vo[i] = v; ao[i] = a; jo[i] = jv;
+      }
+      ++i;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32)
+ltp_sample_row_latency_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_0,
+                              const double* __restrict__ v_0, const double* __restrict__ a_0, DeviceSolution S,
+                              int horizon, int64_t stride, double* __restrict__ q, double* __restrict__ v,
+                              double* __restrict__ a, double* __restrict__ j, uint8_t* row_ok) {
+  __shared__ __align__(16) double s_tab[kMaxSeg][2];
+  if (threadIdx.x != 0) return;
+  const int dof = P.dof;
+  const int64_t row = blockIdx.x;
+  const int64_t p = row / dof;
+  const int jt = (int)(row - p * dof);
+  bool ok = false;
+  if (S.reached[p]) {
+    const int len = S.traj_len[p];
+    if (len > 0) {
+      const JointLimits L = P.lim[jt];
+      const int64_t at = (int64_t)jt * n + p;
+      double t[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) t[k] = S.t_scaled[((int64_t)k * dof + jt) * n + p];
+      const int n_out = horizon > 0 ? horizon : (len < stride ? len : (int)stride);
+      const int n_run = n_out > len ? n_out : len;
+      const SegTableT<2> T{&s_tab[0][0]};
+      RowSampler R;
+      R.init(P.ts, L.j_max, t, S.dir[at], S.mod[at], q_0[at], v_0[at], a_0[at], S.v_drive[at], n_run);
+      T.build(R, n_run, true);
+      double av = R.a, vv = R.v, qv = R.q, q_last = 0.0;
+      const double Ts = R.Ts, vcruise = R.vcruise;
+      const int64_t base = (p * dof + jt) * stride;
+      double* qo = q + base; double* vo = v + base; double* ao = a + base; double* jo = j + base;
+      int i = 0;
+      for (int m = 0; m < kMaxSeg && i < n_run; ++m) {
+        const double jv = s_tab[m][0];
+        int next;
+        bool vc, live;
+        seg_unpack(s_tab[m][1], next, vc, live);
+        const int stop = next < n_run ? next : n_run;
+        if (!live && vc) run_piece<false, true>(i, stop, n_out, len, Ts, jv, vcruise, av, vv, qv, q_last, qo, vo, ao, jo);
+        else if (!live) run_piece<false, false>(i, stop, n_out, len, Ts, jv, vcruise, av, vv, qv, q_last, qo, vo, ao, jo);
+        else if (vc) run_piece<true, true>(i, stop, n_out, len, Ts, jv, vcruise, av, vv, qv, q_last, qo, vo, ao, jo);
+        else run_piece<true, false>(i, stop, n_out, len, Ts, jv, vcruise, av, vv, qv, q_last, qo, vo, ao, jo);
+      }
+      ok = !(q_last < L.q_min || q_last > L.q_max);  // cc:60
+    }
+  }
+  row_ok[row] = (uint8_t)ok;
+}
+
 // Time-major variant: q[(sample * n + problem) * dof + joint] (a torch tensor of shape
 // (samples, n, dof)). Lane l of CTA b owns row r = 32 b + l of the flattened (problem, joint)
 // index, so the 32 lanes of a warp write 32 consecutive doubles -- one aligned 256-byte
@@ -835,6 +927,9 @@ struct ltp_planner {
   // scratch for the host-buffer entry points (grown on demand)
   void* d_scratch;
   size_t d_scratch_bytes;
+  // pinned, device-mapped host staging of the small-batch host calls (ltp_plan_host with a
+  // handful of problems): the kernels read the inputs from it and write the rows into it
+  void* h_stage;
   cudaStream_t stream;  // internal stream of the host entry points
   // work list of the two-kernel solve: [0] = count, [1..] = problem indices
   void* d_work;  // SolveScratch of ltp_solve_batch
@@ -1020,6 +1115,7 @@ int ltp_create(ltp_planner** out, int device, int dof, double t_sample, const do
   p->launches = 0;
   p->d_scratch = nullptr;
   p->d_scratch_bytes = 0;
+  p->h_stage = nullptr;
   p->stream = nullptr;
   p->d_work = nullptr;
   p->d_work_capacity = 0;
@@ -1105,6 +1201,7 @@ void ltp_destroy(ltp_planner* p) {
   {
     DeviceGuard g(p->device);
     if (p->d_scratch) cudaFree(p->d_scratch);
+    if (p->h_stage) cudaFreeHost(p->h_stage);
     if (p->d_work) cudaFree(p->d_work);
     if (p->d_totals) cudaFree(p->d_totals);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -1196,7 +1293,9 @@ static int solve_launch(ltp_planner* p, int64_t n, const double* q_goal, const d
     else { LTP_DISPATCH_W(ltp_solve_fast_kernel, GRID, __VA_ARGS__); break; }               \
     p->launches++;                                                                          \
   } while (0)
-  if (p->solve_mode == LTP_SOLVE_GENERIC) {
+  // a single tile is one CTA whichever way it is run: the every-branch kernel alone (one launch
+  // instead of a memset and three) gives the same results sooner
+  if (p->solve_mode == LTP_SOLVE_GENERIC || n <= kTile) {
     ProfScope ps(p, LTP_PROFILE_SOLVE_GENERIC, st);
     LTP_DISPATCH_W(ltp_solve_generic_kernel, tiles, p->params, n, q_goal, q_0, v_0, a_0, ds,
                    (const int*)nullptr, (const int*)nullptr);
@@ -1236,7 +1335,8 @@ int ltp_solve_batch(ltp_planner* p, int64_t n, const double* q_goal, const doubl
     return LTP_ERR_ARG;
   if (n > 0x7fffffff) return LTP_ERR_ARG;  // problem indices travel as int32 in the work list
   DeviceGuard g(p->device);
-  if (p->solve_mode != LTP_SOLVE_GENERIC && (p->d_work_capacity < n || p->d_work_dof < p->params.dof)) {
+  if (p->solve_mode != LTP_SOLVE_GENERIC && n > kTile &&
+      (p->d_work_capacity < n || p->d_work_dof < p->params.dof)) {
     if (p->d_work) LTP_CUDA(cudaFree(p->d_work));
     p->d_work = nullptr;
     p->d_work_capacity = 0;
@@ -1492,6 +1592,87 @@ int ltp_advance_batch(ltp_planner* p, int64_t n, int32_t tick, int32_t clamp, co
   return LTP_OK;
 }
 
+// Small batches (the drop-in planTrajectory is n = 1) and the single-item calls: latency, not
+// bandwidth. Everything the host exchanges with the kernels sits in one block of pinned,
+// device-mapped host memory: the kernels read their inputs from it and write their results
+// (for a plan: the sampled rows, as posted 32-byte PCIe writes) straight into it, so a call is
+// two launches and ONE stream synchronisation -- no copies, no host round trip between solve
+// and sampling.
+constexpr size_t kStageHeadBytes = 65536;
+constexpr size_t kStageRowBytes = 4u << 20;
+
+static int ensure_stage(ltp_planner* p) {
+  if (!p->h_stage) LTP_CUDA(cudaHostAlloc(&p->h_stage, kStageHeadBytes + kStageRowBytes, cudaHostAllocMapped));
+  return LTP_OK;
+}
+
+static void launch_row_latency_sampler(ltp_planner* p, int64_t n, const double* q_0, const double* v_0,
+                                       const double* a_0, const ltp_solution* ds, int32_t horizon, int64_t stride,
+                                       double* rows, size_t field, uint8_t* row_ok, cudaStream_t st) {
+  ProfScope ps(p, LTP_PROFILE_SAMPLE_ROWS, st);
+  ltp_sample_row_latency_kernel<<<(unsigned)(n * p->params.dof), 32, 0, st>>>(
+      p->params, n, q_0, v_0, a_0, to_dev(ds), horizon, stride, rows, rows + field, rows + 2 * field, rows + 3 * field,
+      row_ok);
+  p->launches++;
+}
+
+static int plan_host_small(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0, const double* v_0,
+                           const double* a_0, int32_t horizon, int64_t capacity, double* q, double* v, double* a,
+                           double* j, int32_t* traj_len, uint8_t* success, int64_t* needed) {
+  const int dof = p->params.dof;
+  const size_t dn = (size_t)dof * (size_t)n;
+  const int64_t dstride = (capacity + 3) / 4 * 4;
+  int rc = ensure_stage(p);
+  if (rc != LTP_OK) return rc;
+  unsigned char* hs = (unsigned char*)p->h_stage;
+  double* h_in = (double*)hs;                         // [4][dof][n]
+  int32_t* h_len = (int32_t*)(hs + 4 * dn * 8);       // [n]     written by the solve kernel
+  uint8_t* h_reached = (uint8_t*)(h_len + n);         // [n]     written by the solve kernel
+  uint8_t* h_row_ok = h_reached + n;                  // [n*dof] written by the sampler
+  double* h_rows = (double*)(hs + kStageHeadBytes);   // [4][n*dof][dstride]
+  const double* user_in[4] = {q_goal, q_0, v_0, a_0};
+  for (int i = 0; i < 4; ++i) std::memcpy(h_in + i * dn, user_in[i], dn * 8);
+  ltp_solution ds;
+  const size_t sol_bytes = carve_solution(nullptr, dof, n, &ds);
+  rc = ensure_scratch(p, sol_bytes);
+  if (rc != LTP_OK) return rc;
+  carve_solution((unsigned char*)p->d_scratch, dof, n, &ds);
+  ds.t_opt = nullptr; ds.opt_case = nullptr; ds.ts_case = nullptr; ds.final_case = nullptr;
+  ds.traj_len = h_len;
+  ds.reached = h_reached;
+  cudaStream_t st = p->stream;
+  rc = ltp_solve_batch(p, n, h_in, h_in + dn, h_in + 2 * dn, h_in + 3 * dn, &ds, st);
+  if (rc != LTP_OK) return rc;
+  const size_t field = dn * (size_t)dstride;
+  const bool rows_ok = q && v && a && j;
+  if (rows_ok) {
+    launch_row_latency_sampler(p, n, h_in + dn, h_in + 2 * dn, h_in + 3 * dn, &ds, horizon, dstride, h_rows, field,
+                               h_row_ok, st);
+    LTP_CUDA(cudaGetLastError());
+  }
+  LTP_CUDA(cudaStreamSynchronize(st));
+  int64_t need = horizon;
+  for (int64_t i = 0; i < n; ++i) {
+    traj_len[i] = h_len[i];
+    if (horizon == 0) need = h_len[i] > need ? h_len[i] : need;
+  }
+  if (needed) *needed = need;
+  if (need > capacity || !rows_ok) {
+    for (int64_t i = 0; i < n; ++i) success[i] = 0;
+    return need > capacity ? LTP_ERR_CAPACITY : LTP_ERR_ARG;
+  }
+  double* user_rows[4] = {q, v, a, j};
+  for (int f = 0; f < 4; ++f)
+    for (size_t r = 0; r < dn; ++r)
+      std::memcpy(user_rows[f] + r * (size_t)capacity, h_rows + f * field + r * (size_t)dstride, (size_t)need * 8);
+  for (int64_t i = 0; i < n; ++i) {
+    uint8_t ok = 1;
+    for (int k = 0; k < dof; ++k) ok &= h_row_ok[i * dof + k];
+    success[i] = ok;
+  }
+  return LTP_OK;
+}
+
 int ltp_plan_host(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0, const double* v_0,
                   const double* a_0, int32_t horizon, int64_t capacity, double* q, double* v, double* a,
                   double* j, int32_t* traj_len, uint8_t* success, int64_t* needed) {
@@ -1503,6 +1684,9 @@ int ltp_plan_host(ltp_planner* p, int64_t n, const double* q_goal, const double*
   DeviceGuard g(p->device);
   const int dof = p->params.dof;
   const size_t dn = (size_t)dof * (size_t)n;
+  if (n <= kTile && capacity >= 4 && horizon <= capacity && 4 * dn * 8 + 6 * dn <= kStageHeadBytes &&
+      4 * dn * (size_t)((capacity + 3) / 4 * 4) * 8 <= kStageRowBytes)
+    return plan_host_small(p, n, q_goal, q_0, v_0, a_0, horizon, capacity, q, v, a, j, traj_len, success, needed);
   ltp_solution ds;
   const size_t sol_bytes = carve_solution(nullptr, dof, n, &ds);
   const size_t in_bytes = up(dn * 8, 256);
@@ -1553,16 +1737,14 @@ int ltp_opt_braking_host(ltp_planner* p, int joint, double v_0, double a_0, doub
                          double* t_rel3, double* dir) {
   if (!p || joint < 0 || joint >= p->params.dof || !q_stop || !t_rel3 || !dir) return LTP_ERR_ARG;
   DeviceGuard g(p->device);
-  int rc = ensure_scratch(p, 4096);
+  int rc = ensure_stage(p);
   if (rc != LTP_OK) return rc;
-  double* d = (double*)p->d_scratch;  // [0]=v0 [1]=a0 [2]=q [3]=dir [4..6]=t_rel
-  double h[7] = {v_0, a_0, 0, 0, 0, 0, 0};
+  double* h = (double*)p->h_stage;  // [0]=v0 [1]=a0 [2]=q [3]=dir [4..6]=t_rel
+  h[0] = v_0; h[1] = a_0;
   cudaStream_t st = p->stream;
-  LTP_CUDA(cudaMemcpyAsync(d, h, sizeof h, cudaMemcpyHostToDevice, st));
-  ltp_opt_braking_kernel<<<1, 32, 0, st>>>(p->params, joint, 1, d, d + 1, d + 2, d + 4, d + 3);
+  ltp_opt_braking_kernel<<<1, 32, 0, st>>>(p->params, joint, 1, h, h + 1, h + 2, h + 4, h + 3);
   p->launches++;
   LTP_CUDA(cudaGetLastError());
-  LTP_CUDA(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, st));
   LTP_CUDA(cudaStreamSynchronize(st));
   *q_stop = h[2];
   *dir = h[3];
@@ -1575,20 +1757,17 @@ int ltp_opt_switch_times_host(ltp_planner* p, int joint, double q_goal, double q
                               uint8_t* kase, uint8_t* ok) {
   if (!p || joint < 0 || joint >= p->params.dof || !t7 || !dir || !mod || !ok) return LTP_ERR_ARG;
   DeviceGuard g(p->device);
-  int rc = ensure_scratch(p, 4096);
+  int rc = ensure_stage(p);
   if (rc != LTP_OK) return rc;
-  double* d = (double*)p->d_scratch;  // in: 0..4; out: t 5..11, dir 12; bytes at 16*8
-  uint8_t* db = (uint8_t*)(d + 16);
-  double h[13] = {q_goal, q_0, v_0, a_0, v_drive};
+  double* h = (double*)p->h_stage;  // in: 0..4; out: t 5..11, dir 12; bytes at 16*8
+  uint8_t* hb = (uint8_t*)(h + 16);
+  h[0] = q_goal; h[1] = q_0; h[2] = v_0; h[3] = a_0; h[4] = v_drive;
+  for (int k = 5; k < 13; ++k) h[k] = 0.0;  // the kernel leaves t untouched on the cc:340-344 failure
   cudaStream_t st = p->stream;
-  LTP_CUDA(cudaMemcpyAsync(d, h, sizeof h, cudaMemcpyHostToDevice, st));
-  ltp_opt_switch_times_kernel<<<1, 32, 0, st>>>(p->params, joint, 1, d, d + 1, d + 2, d + 3, d + 4, d + 5,
-                                                d + 12, db, db + 1, db + 2);
+  ltp_opt_switch_times_kernel<<<1, 32, 0, st>>>(p->params, joint, 1, h, h + 1, h + 2, h + 3, h + 4, h + 5,
+                                                h + 12, hb, hb + 1, hb + 2);
   p->launches++;
   LTP_CUDA(cudaGetLastError());
-  uint8_t hb[3];
-  LTP_CUDA(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, st));
-  LTP_CUDA(cudaMemcpyAsync(hb, db, 3, cudaMemcpyDeviceToHost, st));
   LTP_CUDA(cudaStreamSynchronize(st));
   for (int k = 0; k < 7; ++k) t7[k] = h[5 + k];
   *dir = h[12];
@@ -1603,20 +1782,17 @@ int ltp_time_scaling_host(ltp_planner* p, int joint, double q_goal, double q_0, 
                           uint8_t* ts_case, uint8_t* ok) {
   if (!p || joint < 0 || joint >= p->params.dof || !t7 || !v_drive || !mod || !ok) return LTP_ERR_ARG;
   DeviceGuard g(p->device);
-  int rc = ensure_scratch(p, 4096);
+  int rc = ensure_stage(p);
   if (rc != LTP_OK) return rc;
-  double* d = (double*)p->d_scratch;  // in 0..5; out t 6..12, v_drive 13
-  uint8_t* db = (uint8_t*)(d + 16);
-  double h[14] = {q_goal, q_0, v_0, a_0, dir, t_required};
+  double* h = (double*)p->h_stage;  // in 0..5; out t 6..12, v_drive 13
+  uint8_t* hb = (uint8_t*)(h + 16);
+  h[0] = q_goal; h[1] = q_0; h[2] = v_0; h[3] = a_0; h[4] = dir; h[5] = t_required;
+  for (int k = 6; k < 14; ++k) h[k] = 0.0;
   cudaStream_t st = p->stream;
-  LTP_CUDA(cudaMemcpyAsync(d, h, sizeof h, cudaMemcpyHostToDevice, st));
-  ltp_time_scaling_kernel<<<1, 32, 0, st>>>(p->params, joint, 1, d, d + 1, d + 2, d + 3, d + 4, d + 5, d + 6,
-                                            d + 13, db, db + 1, db + 2, db + 3);
+  ltp_time_scaling_kernel<<<1, 32, 0, st>>>(p->params, joint, 1, h, h + 1, h + 2, h + 3, h + 4, h + 5, h + 6,
+                                            h + 13, hb, hb + 1, hb + 2, hb + 3);
   p->launches++;
   LTP_CUDA(cudaGetLastError());
-  uint8_t hb[4];
-  LTP_CUDA(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, st));
-  LTP_CUDA(cudaMemcpyAsync(hb, db, 4, cudaMemcpyDeviceToHost, st));
   LTP_CUDA(cudaStreamSynchronize(st));
   for (int k = 0; k < 7; ++k) t7[k] = h[6 + k];
   *v_drive = h[13];
@@ -1648,6 +1824,42 @@ int ltp_get_trajectory_host(ltp_planner* p, const double* t7, const double* dir,
   DeviceGuard g(p->device);
   const int64_t dstride = ((int64_t)len + 3) / 4 * 4;
   ltp_solution ds;
+  if (4 * (size_t)dof * (size_t)dstride * 8 <= kStageRowBytes) {
+    // everything through the mapped staging block: no copies, one launch, one synchronisation
+    int rc = ensure_stage(p);
+    if (rc != LTP_OK) return rc;
+    double* h = (double*)p->h_stage;
+    std::memset(&ds, 0, sizeof ds);
+    ds.t_scaled = h;                       // [7][dof][1]
+    ds.dir = h + 7 * dof;
+    ds.v_drive = h + 8 * dof;
+    double* h_in = h + 9 * dof;            // q_0, v_0, a_0
+    ds.traj_len = (int32_t*)(h + 12 * dof);
+    ds.mod = (uint8_t*)(ds.traj_len + 2);
+    ds.reached = ds.mod + dof;
+    uint8_t* row_ok = ds.reached + 1;
+    double* h_rows = (double*)((unsigned char*)p->h_stage + kStageHeadBytes);
+    for (int i = 0; i < dof; ++i) {
+      for (int k = 0; k < 7; ++k) ds.t_scaled[k * dof + i] = t7[7 * i + k];
+      ds.dir[i] = dir[i];
+      ds.v_drive[i] = v_drive[i];
+      h_in[i] = q_0[i]; h_in[dof + i] = v_0[i]; h_in[2 * dof + i] = a_0[i];
+      ds.mod[i] = mod[i];
+    }
+    ds.traj_len[0] = len;
+    ds.reached[0] = 1;
+    cudaStream_t st = p->stream;
+    const size_t field = (size_t)dof * (size_t)dstride;
+    launch_row_latency_sampler(p, 1, h_in, h_in + dof, h_in + 2 * dof, &ds, 0, dstride, h_rows, field, row_ok, st);
+    LTP_CUDA(cudaGetLastError());
+    LTP_CUDA(cudaStreamSynchronize(st));
+    double* user_rows[4] = {q, v, a, j};
+    for (int f = 0; f < 4; ++f)
+      for (int r = 0; r < dof; ++r)
+        std::memcpy(user_rows[f] + (size_t)r * (size_t)capacity, h_rows + f * field + (size_t)r * (size_t)dstride,
+                    (size_t)len * 8);
+    return LTP_OK;
+  }
   const size_t sol_bytes = carve_solution(nullptr, dof, 1, &ds);
   const size_t in_bytes = up((size_t)dof * 8, 256);
   const size_t row_bytes = up((size_t)dof * (size_t)dstride * 8, 256);

@@ -1123,7 +1123,9 @@ template <int ENTRY_STRIDE>
 struct SegTableT {
   double* base;  // entry 0 of this row
 
-  LTP_HD void build(const RowSampler& R, int limit) const {
+  // stop_at_end: leave the entries behind the last piece unwritten (they are never entered);
+  // for a caller that builds one table per thread and pays for every iteration
+  LTP_HD void build(const RowSampler& R, int limit, bool stop_at_end = false) const {
     int cur = 0;
 #pragma unroll 1
     for (int m = 0; m < kMaxSeg; ++m) {
@@ -1138,6 +1140,7 @@ struct SegTableT {
       double* e = base + m * ENTRY_STRIDE;
       e[0] = j;
       e[1] = seg_pack(cur, vc, live);
+      if (stop_at_end && cur == 0x7fffffff) break;
     }
   }
 };

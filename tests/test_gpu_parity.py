@@ -320,3 +320,72 @@ def test_two_kernel_solve_equals_generic_kernel(lim, n, seed):
     auto2 = ltp.solve(*ins)
     torch.cuda.synchronize()
     assert torch.equal(again.traj_len, auto2.traj_len) and torch.equal(auto.traj_len, auto2.traj_len)
+
+
+@pytest.mark.parametrize("lim,seed", [(W.FRANKA7, 31), (W.REF_RANDOM6, 32), (W.FRANKA12, 33)])
+def test_small_batch_host_path_equals_batch_kernels(lim, seed):
+    """ltp_plan_host with a handful of problems (the drop-in planTrajectory is n = 1) takes the
+    latency path: mapped host staging, every-branch solve kernel, piece-wise row sampler. Its
+    rows must be the batch kernels' rows bit for bit -- exact length, fixed horizon longer and
+    shorter than the plan, capacity not a multiple of four, the too-small-capacity answer."""
+    import ctypes as C
+    from longtermplanner_b200 import _capi as capi
+    n_all = 48
+    qg, q0, v0, a0 = W.random_states(lim, n_all, seed)
+    ltp = _planner(lim)
+    ins = [_dev(jm(x)) for x in (qg, q0, v0, a0)]
+    sol = ltp.solve(*ins)
+    tl = sol.traj_len.cpu().numpy()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+
+    def call(sel, horizon, cap):
+        n = len(sel)
+        rows = [np.full((n, lim.dof, cap), np.nan) for _ in range(4)]
+        ln, ok, needed = np.zeros(n, np.int32), np.zeros(n, np.uint8), capi.i64(0)
+        hin = [np.ascontiguousarray(jm(x[sel])) for x in (qg, q0, v0, a0)]
+        rc = capi.plan_host(ltp._h, n, *[vp(x) for x in hin], horizon, cap, *[vp(r) for r in rows], vp(ln), vp(ok),
+                            C.byref(needed))
+        return rc, rows, ln, ok, int(needed.value)
+
+    for horizon in (0, int(tl.max()) + 13, max(int(tl.min()) // 2, 4)):
+        want = ltp.sample(ins[1], ins[2], ins[3], sol, horizon=horizon, layout="rows")
+        torch.cuda.synchronize()
+        wrows = [getattr(want, k).cpu().numpy() for k in "qvaj"]
+        wok = want.success.cpu().numpy()
+        for sel in ([0], [7], [1, 2, 3], list(range(10, 15)), list(range(16, 48))):
+            sel = np.asarray(sel)
+            cap = (horizon if horizon else int(tl[sel].max())) + 3  # not a multiple of four in general
+            if 4 * len(sel) * lim.dof * (cap + 3) * 8 > (4 << 20):
+                continue  # beyond the staging block: the general path, covered elsewhere
+            rc, rows, ln, ok, needed = call(sel, horizon, cap)
+            assert rc == 0
+            assert np.array_equal(ln, tl[sel]) and np.array_equal(ok, wok[sel])
+            for f in range(4):
+                for i, pidx in enumerate(sel):
+                    m = horizon if horizon else tl[pidx]
+                    assert np.array_equal(rows[f][i, :, :m], wrows[f][pidx, :, :m]), (horizon, f, pidx)
+    # capacity too small: the needed capacity comes back, nothing is reported as success
+    rc, rows, ln, ok, needed = call(np.asarray([5]), 0, 8)
+    assert rc == capi.LTP_ERR_CAPACITY and needed == tl[5] and not ok.any()
+
+
+def test_single_item_calls_through_mapped_staging():
+    """optBraking / optSwitchTimes / timeScaling / getTrajectory one item at a time: inputs
+    and results travel through pinned, device-mapped host memory (no copies); same answers as
+    the batched primitives and the oracle."""
+    lim = W.REF_RANDOM6
+    ltp = _planner(lim)
+    P = OraclePort.from_limits(lim)
+    qg, q0, v0, a0 = W.random_states(lim, 40, 99)
+    for i in range(40):
+        jt = i % lim.dof
+        ok, qs, trel, d = ltp.optBraking(jt, v0[i, jt], a0[i, jt])
+        rb = P.opt_braking(np.array([v0[i, jt]]), np.array([a0[i, jt]]), joint=np.array([jt]))
+        assert count_bad([qs, *trel], [rb["q"][0], *rb["t_rel"][0]]) == 0 and d == rb["dir"][0]
+        full = P.plan(qg[i], q0[i], v0[i], a0[i])
+        from longtermplanner_b200 import Trajectory
+        tr = Trajectory()
+        assert ltp.planTrajectory(qg[i], q0[i], v0[i], a0[i], tr) == full["success"]
+        assert tr.length == full["length"]
+        for k in "qvaj":
+            assert count_bad(np.asarray(getattr(tr, k)), full[k]) == 0
