@@ -75,6 +75,13 @@ def main():
     table = line_table(kern)
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
+    # one section per captured launch: "Kernel Name",<demangled> / header / instructions
+    m = re.match(r"(\w+?)ILi(\d+)$", kern)
+    want = f"{m.group(1)}<(int){m.group(2)}>" if m else kern
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    sect = next(i for i in starts if want in rows[i][1])
+    end = next((i for i in starts if i > sect), len(rows))
+    rows = rows[sect:end]
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     h = rows[hi]
     ia, ii, it, isamp = h.index("Address"), h.index("Instructions Executed"), h.index(

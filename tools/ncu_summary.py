@@ -47,7 +47,7 @@ def main(path, json_out=None):
     hdr, units = rows[0], rows[1]
     seen = {}
     for r in rows[2:]:
-        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void <unnamed>::", "")
+        name = r[hdr.index("Kernel Name")].replace("void ", "").replace("<unnamed>::", "").split("(")[0]
         seen.setdefault(name, []).append(r)
     facts = {}
     for name, rs in seen.items():
