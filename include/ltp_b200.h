@@ -116,7 +116,11 @@ typedef struct {
   uint8_t* mod;        /* [dof][n]  modified jerk profile flag */
   int32_t* slowest;    /* [n]  index of the slowest joint, -1 if none */
   int32_t* traj_len;   /* [n]  samples of the trajectory (cc:716-719); 0 if not reached */
-  uint8_t* reached;    /* [n]  1 if the reference would go on to getTrajectory (cc:58) */
+  uint8_t* reached;    /* [n]  1 if the reference would go on to getTrajectory (cc:58). With
+                        *      reached = 0 the reference has returned false before producing
+                        *      anything (cc:15,29,39): traj_len is 0 and the other fields of that
+                        *      problem are unspecified (all joints are evaluated in parallel here,
+                        *      the reference stops at the first joint that fails) */
   double* t_opt;       /* optional [7][dof][n]  time-optimal switching times (cc:27-30) */
   uint8_t* opt_case;   /* optional [dof][n] */
   uint8_t* ts_case;    /* optional [dof][n] */

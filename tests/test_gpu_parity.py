@@ -389,3 +389,79 @@ def test_single_item_calls_through_mapped_staging():
         assert tr.length == full["length"]
         for k in "qvaj":
             assert count_bad(np.asarray(getattr(tr, k)), full[k]) == 0
+
+
+def _random_limits(dof, seed):
+    r = np.random.default_rng(seed)
+    half = r.uniform(1.0, 3.1, dof)
+    centre = r.uniform(-0.5, 0.5, dof)
+    v = r.uniform(0.5, 3.0, dof)
+    a = r.uniform(1.0, 20.0, dof)
+    j = a * np.exp(r.uniform(np.log(4.0), np.log(600.0), dof))  # a_max / j_max between 1.7 and 250 ms
+    ts = float(r.choice([0.001, 0.004, 0.01]))
+    return W.Limits(f"rand{dof}", ts, tuple(centre - half), tuple(centre + half), tuple(v), tuple(a), tuple(j))
+
+
+@pytest.mark.parametrize("dof", [1, 2, 3, 5, 8, 9, 16, 17, 31, 32])
+def test_every_joint_count_bucket(dof):
+    """The kernels are instantiated per CTA-size bucket (1, 2, 4, 8, 16, 32 warps; 6, 7, 12 exact)
+    and the row sampler packs floor(32 / dof) problems per warp: every bucket, with random limit
+    sets (mixed ratios a_max/j_max, three sample times), against the oracle -- solve in both
+    modes, both sampler layouts, the small-batch host path."""
+    import ctypes as C
+    from longtermplanner_b200 import _capi as capi
+    lim = _random_limits(dof, 1000 + dof)
+    n = 700 if dof <= 9 else 200
+    ltp, ins, sol, ref, (qg, q0, v0, a0) = _solve_both(lim, n, 4000 + dof)
+    assert np.array_equal(sol.reached.cpu().numpy(), ref["reached"])
+    assert np.array_equal(sol.traj_len.cpu().numpy(), ref["traj_len"])
+    # a problem the reference gives up on (start state rejected, a joint without a solution) has
+    # reached = 0 and traj_len = 0; its other fields are unspecified (include/ltp_b200.h)
+    r = ref["reached"].astype(bool)
+    assert r.sum() > n // 2
+    assert np.array_equal(sol.slowest.cpu().numpy()[r], ref["slowest"][r])
+    assert np.array_equal(pm(sol.final_case.cpu().numpy())[r], ref["final_case"][r])
+    assert np.array_equal(pm(sol.ts_case.cpu().numpy())[r], ref["ts_case"][r])
+    assert np.array_equal(pm(sol.mod.cpu().numpy())[r], ref["mod"][r])
+    assert np.array_equal(pm(sol.dir.cpu().numpy())[r], ref["dir"][r])
+    assert count_bad(pm(sol.t_scaled.cpu().numpy())[r], ref["t_scaled"][r]) == 0
+    assert count_bad(pm(sol.v_drive.cpu().numpy())[r], ref["v_drive"][r]) == 0
+    ltp.setSolveMode(True)
+    gen = ltp.solve(*ins, with_opt=True, with_cases=True)
+    ltp.setSolveMode(False)
+    for k in ("t_scaled", "v_drive", "dir", "mod", "traj_len", "reached", "slowest", "final_case", "ts_case"):
+        assert bitdiff(getattr(gen, k).cpu().numpy(), getattr(sol, k).cpu().numpy()) == 0, k
+    P = OraclePort.from_limits(lim)
+    tl = sol.traj_len.cpu().numpy()
+    rows = {}
+    for layout in ("time_major", "rows"):
+        traj = ltp.sample(ins[1], ins[2], ins[3], sol, layout=layout)
+        torch.cuda.synchronize()
+        rows[layout] = _rows(traj)
+        succ = traj.success.cpu().numpy()
+        for i in range(0, n, max(n // 12, 1)):
+            full = P.plan(qg[i], q0[i], v0[i], a0[i])
+            assert bool(succ[i]) == full["success"]
+            if not r[i]:  # early false of the reference: no trajectory at all
+                assert full["length"] <= 0 and tl[i] == 0 and not succ[i]
+                continue
+            assert full["length"] == tl[i]
+            for k in "qvaj":
+                assert count_bad(rows[layout][k][i, :, :tl[i]], full[k]) == 0, (layout, k, i)
+    for k in "qvaj":
+        for i in range(n):
+            assert np.array_equal(rows["rows"][k][i, :, :tl[i]], rows["time_major"][k][i, :, :tl[i]])
+    # small-batch host path: three problems at once
+    sel = np.array([0, n // 2, n - 1])
+    cap = int(tl[sel].max()) + 1
+    if 4 * 3 * dof * (cap + 3) * 8 <= (4 << 20):
+        out = [np.full((3, dof, cap), np.nan) for _ in range(4)]
+        ln, ok, needed = np.zeros(3, np.int32), np.zeros(3, np.uint8), capi.i64(0)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        hin = [np.ascontiguousarray(jm(x[sel])) for x in (qg, q0, v0, a0)]
+        assert capi.plan_host(ltp._h, 3, *[vp(x) for x in hin], 0, cap, *[vp(r) for r in out], vp(ln), vp(ok),
+                              C.byref(needed)) == 0
+        assert np.array_equal(ln, tl[sel])
+        for f, k in enumerate("qvaj"):
+            for i, pidx in enumerate(sel):
+                assert np.array_equal(out[f][i, :, :tl[pidx]], rows["rows"][k][pidx, :, :tl[pidx]]), (k, pidx)

@@ -25,4 +25,15 @@ for lim, n in ((W.FRANKA7, 333), (W.REF_RANDOM6, 257), (W.FRANKA12, 100), (W.REF
     o = ltp.optSwitchTimesBatch(*ins, torch.full_like(ins[0], float(lim.v_max[0])))
     ltp.timeScalingBatch(*ins, o["dir"], (o["t"][6] + 0.2).contiguous())
     torch.cuda.synchronize()
+    # the latency path: single plans and single items through the mapped staging block
+    from longtermplanner_b200 import Trajectory
+    host = [t.cpu().numpy().T.copy() for t in ins]
+    ltp.setSolveMode(False)
+    for i in range(3):
+        ltp.planTrajectory(host[0][i], host[1][i], host[2][i], host[3][i], Trajectory())
+        ltp.optBraking(0, float(host[2][i][0]), float(host[3][i][0]))
+        ok, t7, d, m = ltp.optSwitchTimes(0, float(host[0][i][0]), float(host[1][i][0]), float(host[2][i][0]),
+                                          float(host[3][i][0]), float(lim.v_max[0]))
+        ltp.timeScaling(0, float(host[0][i][0]), float(host[1][i][0]), float(host[2][i][0]), float(host[3][i][0]),
+                        d, float(t7[6]) + 0.2)
     print(lim.name, "ok", int(sol.reached.sum()), "reached")
