@@ -409,27 +409,37 @@ def main():
         ltp12 = LongTermPlanner(lim12.dof, lim12.t_sample, *lim12.arrays(), device=local)
         ins12 = devtools.random_states_device(lim12, n_rank, W.SEEDS[5], start=rank * n_rank, device=local)
         ltp12.planStream(*[t[:, :2 * chunk + 7].contiguous() for t in ins12], chunk=chunk, capacity=cap)  # warm-up
-        launches12 = ltp12.launches
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        s0.record()
-        st12 = ltp12.planStream(*ins12, chunk=chunk, capacity=cap)  # synchronises before returning
-        s1.record()
-        barrier()
-        stream_ms = max_over_ranks(s0.elapsed_time(s1))
-        tot = torch.tensor([st12["problems"], st12["bytes"], st12["success"], st12["clipped"], st12["reached"]],
-                           dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tot)
-        tot = tot.tolist()
+        runs = {}
+        for mode in ("sorted_slots", "problem_order"):
+            launches12 = ltp12.launches
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            s0.record()
+            st12 = ltp12.planStream(*ins12, chunk=chunk, capacity=cap, sorted_slots=(mode == "sorted_slots"))
+            s1.record()
+            barrier()
+            stream_ms = max_over_ranks(s0.elapsed_time(s1))
+            tot = torch.tensor([st12["problems"], st12["bytes"], st12["success"], st12["clipped"], st12["reached"]],
+                               dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tot)
+            runs[mode] = (stream_ms, tot.tolist(), int(ltp12.launches - launches12))
+        stream_ms, tot, launches_stream = runs["sorted_slots"]
+        assert tot == runs["problem_order"][1], "both slot orders must produce the same totals"
+        po_ms = runs["problem_order"][0]
         extra_stream = {
             "workload": f"configs[4]: 2^{args.stream_log2n} random 12-DoF dual-arm problems (FRANKA12), solve + "
                         "exact-length dense q/v/a/j sampling, contiguous problem-index shards, each rank streams its "
-                        f"shard through a two-slot ring of {chunk}-problem chunks (time-major, capacity {cap} samples)",
+                        f"shard through a two-slot ring of {chunk}-problem chunks (time-major, capacity {cap} samples); "
+                        "headline = sorted-slot mode (each chunk's problems ordered by trajectory length on the "
+                        "device, slot k holds problem order[k]), problem-order mode beside it",
             "scaling": "strong", "seconds": stream_ms * 1e-3, "plans_per_s": tot[0] / (stream_ms * 1e-3),
             "write_gbs": tot[1] / (stream_ms * 1e-3) / 1e9, "write_gbs_per_gpu": tot[1] / (stream_ms * 1e-3) / 1e9 / world,
+            "problem_order": {"seconds": po_ms * 1e-3, "plans_per_s": tot[0] / (po_ms * 1e-3),
+                              "write_gbs": tot[1] / (po_ms * 1e-3) / 1e9,
+                              "write_gbs_per_gpu": tot[1] / (po_ms * 1e-3) / 1e9 / world},
             "bytes_written": tot[1], "problems": tot[0], "reached": tot[4], "success": tot[2], "clipped": tot[3],
-            "gpu_launches": int(ltp12.launches - launches12),
+            "gpu_launches": launches_stream,
             "timing": "CUDA events around the call (it synchronises its two streams), max over ranks"}
         del ins12, ltp12
         torch.cuda.empty_cache()

@@ -141,9 +141,11 @@ class LongTermPlanner {
   /// NEW: planTrajectories for more trajectories than fit in memory (ltp_plan_stream): the run
   /// is cut into chunks of `chunk` problems that are solved and sampled (time-major) into a
   /// two-slot ring and handed to `consume` (see ltp_b200.h). Synchronises before returning.
+  /// sorted_slots (exact-length mode): every chunk's problems are ordered by trajectory length
+  /// on the device and trajectory slot k holds problem ltp_chunk.order[k] (ltp_set_stream_sorted).
   int planStream(int64_t n, const double* q_goal, const double* q_0, const double* v_0, const double* a_0,
                  int64_t chunk, int32_t horizon, int64_t capacity, ltp_chunk_consumer consume, void* user,
-                 ltp_stream_stats* stats = nullptr);
+                 ltp_stream_stats* stats = nullptr, bool sorted_slots = false);
 
   /// NEW: receding-horizon step (ltp_advance_batch): the state `tick` samples into time-major
   /// trajectories becomes the next start state, clamped to what checkInputs accepts.

@@ -171,6 +171,11 @@ typedef struct {
   const double *q_goal, *q_0, *v_0, *a_0;
   const double *q, *v, *a, *j;
   const uint8_t* success;
+  /* NULL: trajectory slot k of the chunk holds problem k of the chunk. Otherwise (sorted-slot
+   * mode, ltp_set_stream_sorted): slot k holds problem order[k], i.e.
+   * q[(sample * count + k) * dof + joint] belongs to problem first + order[k]. The solution,
+   * the inputs and `success` stay indexed by problem. */
+  const int32_t* order;
 } ltp_chunk;
 
 /* called on the host right after a chunk's kernels were enqueued; enqueue the consuming work
@@ -196,6 +201,12 @@ int ltp_plan_stream(ltp_planner* p, int64_t n, const double* q_goal, const doubl
                     const double* v_0, const double* a_0, int64_t chunk, int32_t horizon,
                     int64_t capacity, ltp_chunk_consumer consume, void* user,
                     ltp_stream_stats* stats);
+/* Sorted-slot mode of ltp_plan_stream for exact-length sampling (horizon = 0); off by default.
+ * The lanes of a sampler warp run until the longest of their 32 rows ends, so with problems of
+ * mixed length a sixth of the store slots of random problems is idle. When on, every chunk's
+ * problems are ordered by trajectory length on the device (longest first) and trajectory slot k
+ * holds problem ltp_chunk.order[k]: same samples, permuted slots, full warps. */
+int ltp_set_stream_sorted(ltp_planner* p, int on);
 
 /* Receding-horizon replanning (the reference's stated use, README.md:10-13: a new target
  * arrives before the previous one is reached): the state `tick` samples into the current

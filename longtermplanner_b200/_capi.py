@@ -37,7 +37,7 @@ def _sig(name, restype, *argtypes):
 
 
 EXPORTS = [
-    "ltp_create", "ltp_set_limits", "ltp_set_sample_time", "ltp_set_dof", "ltp_set_solve_mode", "ltp_set_profiling", "ltp_profile_read", "ltp_get_dof", "ltp_get_device",
+    "ltp_create", "ltp_set_limits", "ltp_set_sample_time", "ltp_set_dof", "ltp_set_solve_mode", "ltp_set_stream_sorted", "ltp_set_profiling", "ltp_profile_read", "ltp_get_dof", "ltp_get_device",
     "ltp_destroy", "ltp_status_string", "ltp_last_cuda_error", "ltp_launch_count",
     "ltp_opt_braking_batch", "ltp_opt_switch_times_batch", "ltp_time_scaling_batch", "ltp_solve_batch",
     "ltp_sample_batch", "ltp_plan_stream", "ltp_advance_batch", "ltp_solve_host", "ltp_plan_host", "ltp_opt_braking_host",
@@ -48,7 +48,7 @@ class Chunk(C.Structure):
     """ltp_chunk"""
     _fields_ = [("first", i64), ("count", i64), ("capacity", i64), ("horizon", i32), ("solution", Solution),
                 ("q_goal", vp), ("q_0", vp), ("v_0", vp), ("a_0", vp), ("q", vp), ("v", vp), ("a", vp), ("j", vp),
-                ("success", vp)]
+                ("success", vp), ("order", vp)]
 
 
 class StreamStats(C.Structure):
@@ -65,6 +65,7 @@ set_sample_time = _sig("ltp_set_sample_time", C.c_int, vp, f64)
 set_dof = _sig("ltp_set_dof", C.c_int, vp, C.c_int)
 set_solve_mode = _sig("ltp_set_solve_mode", C.c_int, vp, C.c_int)
 set_profiling = _sig("ltp_set_profiling", C.c_int, vp, C.c_int)
+set_stream_sorted = _sig("ltp_set_stream_sorted", C.c_int, vp, C.c_int)
 profile_read = _sig("ltp_profile_read", C.c_int, vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64), C.c_int)
 get_dof = _sig("ltp_get_dof", C.c_int, vp)
 get_device = _sig("ltp_get_device", C.c_int, vp)

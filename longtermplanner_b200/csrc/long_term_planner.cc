@@ -98,8 +98,11 @@ int LongTermPlanner::planTrajectories(int64_t n, const double* q_goal, const dou
 
 int LongTermPlanner::planStream(int64_t n, const double* q_goal, const double* q_0, const double* v_0,
                                 const double* a_0, int64_t chunk, int32_t horizon, int64_t capacity,
-                                ltp_chunk_consumer consume, void* user, ltp_stream_stats* stats) {
-  return ltp_plan_stream(handle(), n, q_goal, q_0, v_0, a_0, chunk, horizon, capacity, consume, user, stats);
+                                ltp_chunk_consumer consume, void* user, ltp_stream_stats* stats,
+                                bool sorted_slots) {
+  ltp_planner* h = handle();
+  ltp_set_stream_sorted(h, sorted_slots ? 1 : 0);
+  return ltp_plan_stream(h, n, q_goal, q_0, v_0, a_0, chunk, horizon, capacity, consume, user, stats);
 }
 
 int LongTermPlanner::advance(int64_t n, int32_t tick, const int32_t* traj_len, const uint8_t* valid,

@@ -307,12 +307,16 @@ class LongTermPlanner:
         return sol, self.sample(q_0, v_0, a_0, sol, horizon, layout=layout)
 
     def planStream(self, q_goal, q_0, v_0, a_0, chunk: int, horizon: int = 0, capacity: int = 4096,
-                   consumer=None) -> dict:
+                   consumer=None, sorted_slots: bool = False) -> dict:
         """planTrajectories for more problems than fit in memory at once (ltp_plan_stream): chunks
         of `chunk` problems are solved and sampled (time-major) into a two-slot ring; `consumer`,
         if given, is called per chunk as consumer(view, stream) with view a dict of CUDA tensors
         that alias the ring slot (valid for work enqueued on `stream` = a torch ExternalStream).
-        Returns the totals accumulated on the device."""
+        sorted_slots (exact-length mode only): trajectory slot k of a chunk holds problem
+        view["order"][k] (problems ordered by length on the device, ltp_set_stream_sorted); the
+        solution, inputs and success flags stay indexed by problem. Returns the totals accumulated
+        on the device."""
+        capi.check(capi.set_stream_sorted(self._h, 1 if sorted_slots else 0), "ltp_set_stream_sorted")
         n = q_goal.shape[1]
         ins = [self._chk(t, n, nm) for t, nm in zip((q_goal, q_0, v_0, a_0), ("q_goal", "q_0", "v_0", "a_0"))]
         dof, dev = self.dof_, torch.device("cuda", self.device)
@@ -339,6 +343,7 @@ class LongTermPlanner:
                     traj_len=_alias(sol.traj_len, (cnt,), torch.int32),
                     reached=_alias(sol.reached, (cnt,), torch.uint8),
                     success=_alias(c.success, (cnt,), torch.uint8),
+                    order=_alias(c.order, (cnt,), torch.int32) if c.order else None,
                     q=_alias(c.q, (cap, cnt, dof), torch.float64), v=_alias(c.v, (cap, cnt, dof), torch.float64),
                     a=_alias(c.a, (cap, cnt, dof), torch.float64), j=_alias(c.j, (cap, cnt, dof), torch.float64))
                 ext = torch.cuda.ExternalStream(int(stream), device=dev)

@@ -55,6 +55,46 @@ def test_streamed_run_equals_one_shot(lim, n, chunk):
     assert stats["clipped"] == 0 and stats["max_traj_len"] == int(sol.traj_len.max())
 
 
+@pytest.mark.parametrize("lim,n,chunk", [(W.FRANKA12, 5000, 1536), (W.FRANKA7, 4097, 2048), (W.REF_RANDOM6, 1500, 700)])
+def test_streamed_run_sorted_slots(lim, n, chunk):
+    """sorted-slot mode: every chunk's problems ordered by trajectory length on the device, slot k
+    of the chunk's trajectories holds problem order[k]. Same samples bit for bit once the slots
+    are mapped back; order is a permutation, longest first; flags and totals unchanged."""
+    from longtermplanner_b200 import devtools
+    ltp = _planner(lim)
+    ins = devtools.random_states_device(lim, n, W.SEEDS[5], start=123)
+    sol, traj = ltp.planTrajectories(*ins)
+    want = devtools.row_stats(traj, sol.traj_len)
+    got = torch.zeros_like(want)
+    succ = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    orders = []
+
+    def consumer(view, stream):
+        a, c = view["first"], view["count"]
+        order = view["order"].long()
+        orders.append(order.clone())
+        # row statistics of slot k are those of problem order[k]; the slot's own length applies
+        slot_len = view["traj_len"][order].contiguous()
+        got[a + order] = devtools.row_stats(_view_as_traj(view), slot_len)
+        succ[a:a + c] = view["success"]
+
+    stats = ltp.planStream(*ins, chunk=chunk, capacity=4096, consumer=consumer, sorted_slots=True)
+    torch.cuda.synchronize()
+    assert torch.equal(got.view(torch.int64), want.view(torch.int64))
+    assert torch.equal(succ, traj.success)
+    tl = sol.traj_len.long() * sol.reached.long()
+    for k, order in enumerate(orders):
+        c = order.numel()
+        assert torch.equal(torch.sort(order).values, torch.arange(c, device="cuda"))
+        lens = tl[k * chunk + order]
+        assert bool((lens[:-1] + 8 > lens[1:]).all())  # longest first, buckets of 8 samples at this capacity
+    assert stats["samples"] == int(sol.traj_len.long().sum()) * lim.dof and stats["success"] == int(traj.success.sum())
+    # the switch is per call: the default run afterwards is in problem order again
+    seen = []
+    ltp.planStream(*ins, chunk=chunk, capacity=4096, consumer=lambda v, s: seen.append(v["order"]))
+    assert all(o is None for o in seen)
+
+
 def test_streamed_run_fixed_horizon_and_clipping():
     from longtermplanner_b200 import devtools
     lim, n, H = W.FRANKA7, 2500, 600
