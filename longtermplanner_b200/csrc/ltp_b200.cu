@@ -325,6 +325,9 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
 // sample count joins the problem's by atomicMax. A joint that attempt 2 does not settle
 // either sends its problem to the work list of the generic kernel (once per problem: the
 // exchange on traj_len elects the sender).
+#ifndef LTP_TM_BUILD_EARLY_EXIT
+#define LTP_TM_BUILD_EARLY_EXIT 1
+#endif
 #ifndef LTP_A2_MINB
 #define LTP_A2_MINB 2
 #endif
@@ -739,6 +742,12 @@ ltp_sample_row_latency_kernel(const __grid_constant__ PlannerParams P, int64_t n
 // run-up per chunk) do not help: the pure-store kernel of this pattern tops out at
 // 5.9-6.05 TB/s with 1, 2, 4 or 8 warps per tile, and this kernel reaches 96 % of that with
 // one (tools/experiments/sampler_variants.cu).
+// Alignment matters (measured, tools/sampler_scaling_probe.py): a sample plane is n*dof*8 bytes,
+// so the warp's 256-byte piece stays line-aligned from sample to sample only if n*dof is a
+// multiple of 32 -- 5.8 TB/s at n = 4096 (7 joints), 4.8 TB/s at n = 4104 (sector-aligned,
+// pieces straddle lines), 3.1 TB/s at n = 4097 (partial sectors: the neighbouring warp completes
+// them later and the memory system reads them back to merge), whatever the cache hint of the
+// store. Callers pad the batch to a multiple of 32 problems (ltp_b200.h).
 // success[] must have been initialised with reached[]; a row that ends outside its joint
 // limits clears its problem's flag.
 __device__ __forceinline__ void clear_flag(uint8_t* flags, int64_t p) {
@@ -796,7 +805,7 @@ ltp_sample_tm_kernel(const __grid_constant__ PlannerParams P, int64_t n, const d
   {
     RowSampler R;
     R.init(P.ts, L.j_max, t, S.dir[at], S.mod[at], q_0[at], v_0[at], a_0[at], S.v_drive[at], n_run);
-    T.build(R, n_run);
+    T.build(R, n_run, LTP_TM_BUILD_EARLY_EXIT != 0);
     C.begin(R);
   }
   char* qb = reinterpret_cast<char*>(q);

@@ -268,6 +268,8 @@ class LongTermPlanner:
         return sol
 
     def alloc_trajectories(self, n: int, samples: int, layout: str = "time_major") -> BatchTrajectories:
+        """time_major: (samples, n, dof) tensors. Full store bandwidth needs n * dof to be a
+        multiple of 32 (include/ltp_b200.h): pad the batch to a multiple of 32 problems."""
         dev = torch.device("cuda", self.device)
         if layout == "time_major":
             stride = samples
