@@ -1453,10 +1453,10 @@ static int sample_tm_launch(ltp_planner* p, int64_t n, const double* q_0, const 
   ProfScope ps(p, LTP_PROFILE_SAMPLE_TIME_MAJOR, st);
   if ((double)rows * 8.0 * (double)(samples + 1) < 4294967296.0)
     ltp_sample_tm_kernel<uint32_t><<<grid, 32, 0, st>>>(p->params, n, q_0, v_0, a_0, to_dev(sol), horizon, stride,
-                                                         q, v, a, j, success, order);
+                                                           q, v, a, j, success, order);
   else
     ltp_sample_tm_kernel<uint64_t><<<grid, 32, 0, st>>>(p->params, n, q_0, v_0, a_0, to_dev(sol), horizon, stride,
-                                                         q, v, a, j, success, order);
+                                                           q, v, a, j, success, order);
   p->launches++;
   LTP_CUDA(cudaGetLastError());
   return LTP_OK;
