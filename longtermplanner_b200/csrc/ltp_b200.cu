@@ -651,6 +651,70 @@ __device__ __forceinline__ void run_piece(int& i, const int stop, const int n_ou
                                           const double jv, const double vcruise, double& a, double& v, double& q,
                                           double& q_last, double* qo, double* vo, double* ao, double* jo) {
   const double c = Ts * jv;
+  if (LIVE && !CRUISE) {
+    // The common piece (accelerating or braking): blocks of four samples, software-pipelined
+    // one block deep per recurrence -- while q of block b-1 is summed up, v of block b and a of
+    // block b+1 are already on their way, so an iteration costs one chain of four dependent
+    // adds (~28 cycles each on this part) instead of the eight of a -> v -> q in sequence.
+    while ((i & 3) != 0 && i < stop) {
+      a = a + c;
+      v = v + Ts * a;
+      q = q + Ts * v;
+      if (i == len - 1) q_last = q;
+      if (i < n_out) {
+        qo[i] = q; vo[i] = v; ao[i] = a; jo[i] = jv;
+      }
+      ++i;
+    }
+    const int lim = stop < n_out ? stop : n_out;
+    const int nblk = (lim - i) >> 2;
+    if (nblk >= 2) {
+#define LTP_CHAIN_A(dst, from)            \
+  dst[0] = (from) + c; dst[1] = dst[0] + c; dst[2] = dst[1] + c; dst[3] = dst[2] + c
+#define LTP_CHAIN_S(dst, from, src)       \
+  {                                       \
+    const double t0_ = Ts * src[0], t1_ = Ts * src[1], t2_ = Ts * src[2], t3_ = Ts * src[3]; \
+    dst[0] = (from) + t0_; dst[1] = dst[0] + t1_; dst[2] = dst[1] + t2_; dst[3] = dst[2] + t3_; \
+  }
+#define LTP_EMIT(at, ab, vb, qb)                                                     \
+  {                                                                                  \
+    const unsigned k_ = (unsigned)(len - 1 - (at));                                  \
+    if (k_ < 4u) q_last = k_ == 0 ? qb[0] : k_ == 1 ? qb[1] : k_ == 2 ? qb[2] : qb[3]; \
+    store4(qo + (at), qb[0], qb[1], qb[2], qb[3]);                                   \
+    store4(vo + (at), vb[0], vb[1], vb[2], vb[3]);                                   \
+    store4(ao + (at), ab[0], ab[1], ab[2], ab[3]);                                   \
+    store4(jo + (at), jv, jv, jv, jv);                                               \
+  }
+      double a_cur[4], a_nxt[4], v_cur[4], qb[4];
+      LTP_CHAIN_A(a_cur, a);                 // block 0
+      LTP_CHAIN_A(a_nxt, a_cur[3]);          // block 1
+      LTP_CHAIN_S(v_cur, v, a_cur);          // block 0
+      for (int b = 1; b < nblk - 1; ++b) {
+        double a_nn[4], v_nxt[4];
+        LTP_CHAIN_A(a_nn, a_nxt[3]);         // a of block b + 1
+        LTP_CHAIN_S(v_nxt, v_cur[3], a_nxt); // v of block b
+        LTP_CHAIN_S(qb, q, v_cur);           // q of block b - 1
+        q = qb[3];
+        LTP_EMIT(i + 4 * (b - 1), a_cur, v_cur, qb);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          a_cur[u] = a_nxt[u]; a_nxt[u] = a_nn[u]; v_cur[u] = v_nxt[u];
+        }
+      }
+      double v_nxt[4];
+      LTP_CHAIN_S(v_nxt, v_cur[3], a_nxt);   // v of the last block
+      LTP_CHAIN_S(qb, q, v_cur);             // q of the last block but one
+      q = qb[3];
+      LTP_EMIT(i + 4 * (nblk - 2), a_cur, v_cur, qb);
+      LTP_CHAIN_S(qb, q, v_nxt);             // q of the last block
+      LTP_EMIT(i + 4 * (nblk - 1), a_nxt, v_nxt, qb);
+      a = a_nxt[3]; v = v_nxt[3]; q = qb[3];
+      i += 4 * nblk;
+#undef LTP_CHAIN_A
+#undef LTP_CHAIN_S
+#undef LTP_EMIT
+    }
+  }
   while (i < stop) {
     if ((i & 3) == 0 && i + 4 <= stop && i + 4 <= n_out) {
       double aa[4], vv[4], qq[4];
