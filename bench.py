@@ -251,6 +251,14 @@ def single_plan_latency(ltp, lim, calls=300, cpu_plans=2000):
                        "solve + dense sampling, pageable host buffers in and out, one call at a time",
            "gpu_us_per_plan_median": float(np.median(us)), "gpu_us_per_plan_p90": float(np.percentile(us, 90)),
            "calls": calls, "mean_samples_per_plan": None}
+    # the same through the drop-in C++ class (Trajectory's vectors filled), tests/cpp/single_plan_bench.cc
+    exe = os.path.join(ROOT, "tests", "_build", "single_plan_bench")
+    if os.path.exists(exe):
+        try:
+            r = subprocess.run([exe, str(calls)], capture_output=True, text=True, timeout=120)
+            out["cpp_class"] = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:
+            out["cpp_class"] = {"unavailable": str(e)}
     try:
         chk, kind = cpu_checker(lim)
         chk.plan_batch(qg[:64], q0[:64], v0[:64], a0[:64], threads=1)

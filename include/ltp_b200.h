@@ -244,6 +244,17 @@ int ltp_plan_host(ltp_planner* p, int64_t n, const double* q_goal, const double*
                   double* q, double* v, double* a, double* j, int32_t* traj_len,
                   uint8_t* success, int64_t* needed);
 
+/* planTrajectory (reference long_term_planner.cc:7-63) for ONE problem, result left in the
+ * planner's pinned staging block instead of being copied out: rows4[f] (f = 0..3: q, v, a, j)
+ * points at dof rows of *row_stride doubles each, of which the first *length are samples.
+ * The pointers stay valid until the next call on this planner. This is what the drop-in
+ * class's planTrajectory uses (it copies straight into Trajectory's vectors). *length <= 0:
+ * the reference's early `return false`. LTP_ERR_CAPACITY when the trajectory is longer than a
+ * staging row (*length tells how long): use ltp_plan_host. */
+int ltp_plan_one_view(ltp_planner* p, const double* q_goal, const double* q_0, const double* v_0,
+                      const double* a_0, const double** rows4, int64_t* row_stride,
+                      int32_t* length, uint8_t* success);
+
 /* single-item host forms of the protected per-joint methods (used by the C++ drop-in) */
 int ltp_opt_braking_host(ltp_planner* p, int joint, double v_0, double a_0, double* q_stop,
                          double* t_rel3, double* dir);

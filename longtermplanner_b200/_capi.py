@@ -40,7 +40,7 @@ EXPORTS = [
     "ltp_create", "ltp_set_limits", "ltp_set_sample_time", "ltp_set_dof", "ltp_set_solve_mode", "ltp_set_stream_sorted", "ltp_set_profiling", "ltp_profile_read", "ltp_get_dof", "ltp_get_device",
     "ltp_destroy", "ltp_status_string", "ltp_last_cuda_error", "ltp_launch_count",
     "ltp_opt_braking_batch", "ltp_opt_switch_times_batch", "ltp_time_scaling_batch", "ltp_solve_batch",
-    "ltp_sample_batch", "ltp_plan_stream", "ltp_advance_batch", "ltp_solve_host", "ltp_plan_host", "ltp_opt_braking_host",
+    "ltp_sample_batch", "ltp_plan_stream", "ltp_advance_batch", "ltp_solve_host", "ltp_plan_host", "ltp_plan_one_view", "ltp_opt_braking_host",
     "ltp_opt_switch_times_host", "ltp_time_scaling_host", "ltp_get_trajectory_host",
 ]
 
@@ -88,6 +88,8 @@ advance_batch = _sig("ltp_advance_batch", C.c_int, vp, i64, i32, i32, vp, vp, vp
 solve_host = _sig("ltp_solve_host", C.c_int, vp, i64, vp, vp, vp, vp, C.POINTER(Solution))
 plan_host = _sig("ltp_plan_host", C.c_int, vp, i64, vp, vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, vp,
                  C.POINTER(i64))
+plan_one_view = _sig("ltp_plan_one_view", C.c_int, vp, vp, vp, vp, vp, C.POINTER(vp * 4), C.POINTER(i64),
+                     C.POINTER(i32), C.POINTER(C.c_uint8))
 opt_braking_host = _sig("ltp_opt_braking_host", C.c_int, vp, C.c_int, f64, f64, vp, vp, vp)
 opt_switch_times_host = _sig("ltp_opt_switch_times_host", C.c_int, vp, C.c_int, f64, f64, f64, f64, f64, vp,
                              vp, vp, vp, vp)

@@ -51,6 +51,27 @@ bool LongTermPlanner::planTrajectory(const std::vector<double>& q_goal, const st
                                      Trajectory& traj) {
   if (dof_ < 1) return false;
   ltp_planner* h = handle();
+  {
+    // latency path: the sampled rows are read straight out of the planner's staging block
+    const double* view[4];
+    int64_t pitch = 0;
+    int32_t vlen = 0;
+    uint8_t vok = 0;
+    const int rc = ltp_plan_one_view(h, q_goal.data(), q_0.data(), v_0.data(), a_0.data(), view, &pitch, &vlen, &vok);
+    if (rc == LTP_OK) {
+      if (vlen <= 0) return false;  // early `return false` of the reference: traj untouched
+      traj.dof = dof_;
+      traj.length = vlen;
+      traj.t_sample = t_sample_;
+      std::vector<std::vector<double>>* out[4] = {&traj.q, &traj.v, &traj.a, &traj.j};
+      for (int f = 0; f < 4; ++f) {
+        out[f]->resize(dof_);
+        for (int i = 0; i < dof_; ++i) (*out[f])[i].assign(view[f] + (size_t)i * pitch, view[f] + (size_t)i * pitch + vlen);
+      }
+      return vok != 0;
+    }
+    if (rc != LTP_ERR_CAPACITY) return false;
+  }
   int64_t cap = 4096, needed = 0;
   // receive buffer, kept between calls (every sample that is read back below was written by
   // the call; nothing relies on a fill)

@@ -1787,12 +1787,13 @@ static void launch_row_latency_sampler(ltp_planner* p, int64_t n, const double* 
   p->launches++;
 }
 
-static int plan_host_small(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0, const double* v_0,
-                           const double* a_0, int32_t horizon, int64_t capacity, double* q, double* v, double* a,
-                           double* j, int32_t* traj_len, uint8_t* success, int64_t* needed) {
+// solve + sample n <= 32 problems through the staging block; rows are left there:
+// field f of row r (= problem * dof + joint) starts at (*rows) + (f * n * dof + r) * dstride
+static int plan_small_run(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0, const double* v_0,
+                          const double* a_0, int32_t horizon, int64_t dstride, bool want_rows, const double** rows,
+                          const int32_t** lens, const uint8_t** row_ok) {
   const int dof = p->params.dof;
   const size_t dn = (size_t)dof * (size_t)n;
-  const int64_t dstride = (capacity + 3) / 4 * 4;
   int rc = ensure_stage(p);
   if (rc != LTP_OK) return rc;
   unsigned char* hs = (unsigned char*)p->h_stage;
@@ -1814,14 +1815,30 @@ static int plan_host_small(ltp_planner* p, int64_t n, const double* q_goal, cons
   cudaStream_t st = p->stream;
   rc = ltp_solve_batch(p, n, h_in, h_in + dn, h_in + 2 * dn, h_in + 3 * dn, &ds, st);
   if (rc != LTP_OK) return rc;
-  const size_t field = dn * (size_t)dstride;
-  const bool rows_ok = q && v && a && j;
-  if (rows_ok) {
-    launch_row_latency_sampler(p, n, h_in + dn, h_in + 2 * dn, h_in + 3 * dn, &ds, horizon, dstride, h_rows, field,
-                               h_row_ok, st);
+  if (want_rows) {
+    launch_row_latency_sampler(p, n, h_in + dn, h_in + 2 * dn, h_in + 3 * dn, &ds, horizon, dstride, h_rows,
+                               dn * (size_t)dstride, h_row_ok, st);
     LTP_CUDA(cudaGetLastError());
   }
   LTP_CUDA(cudaStreamSynchronize(st));
+  *rows = h_rows;
+  *lens = h_len;
+  *row_ok = h_row_ok;
+  return LTP_OK;
+}
+
+static int plan_host_small(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0, const double* v_0,
+                           const double* a_0, int32_t horizon, int64_t capacity, double* q, double* v, double* a,
+                           double* j, int32_t* traj_len, uint8_t* success, int64_t* needed) {
+  const int dof = p->params.dof;
+  const size_t dn = (size_t)dof * (size_t)n;
+  const int64_t dstride = (capacity + 3) / 4 * 4;
+  const bool rows_ok = q && v && a && j;
+  const double* h_rows;
+  const int32_t* h_len;
+  const uint8_t* h_row_ok;
+  int rc = plan_small_run(p, n, q_goal, q_0, v_0, a_0, horizon, dstride, rows_ok, &h_rows, &h_len, &h_row_ok);
+  if (rc != LTP_OK) return rc;
   int64_t need = horizon;
   for (int64_t i = 0; i < n; ++i) {
     traj_len[i] = h_len[i];
@@ -1832,6 +1849,7 @@ static int plan_host_small(ltp_planner* p, int64_t n, const double* q_goal, cons
     for (int64_t i = 0; i < n; ++i) success[i] = 0;
     return need > capacity ? LTP_ERR_CAPACITY : LTP_ERR_ARG;
   }
+  const size_t field = dn * (size_t)dstride;
   double* user_rows[4] = {q, v, a, j};
   for (int f = 0; f < 4; ++f)
     for (size_t r = 0; r < dn; ++r)
@@ -1841,6 +1859,30 @@ static int plan_host_small(ltp_planner* p, int64_t n, const double* q_goal, cons
     for (int k = 0; k < dof; ++k) ok &= h_row_ok[i * dof + k];
     success[i] = ok;
   }
+  return LTP_OK;
+}
+
+int ltp_plan_one_view(ltp_planner* p, const double* q_goal, const double* q_0, const double* v_0, const double* a_0,
+                      const double** rows4, int64_t* row_stride, int32_t* length, uint8_t* success) {
+  if (!p || !q_goal || !q_0 || !v_0 || !a_0 || !rows4 || !row_stride || !length || !success || p->params.dof < 1)
+    return LTP_ERR_ARG;
+  DeviceGuard g(p->device);
+  const int dof = p->params.dof;
+  int64_t dstride = (int64_t)(kStageRowBytes / (4 * (size_t)dof * 8)) & ~(int64_t)3;
+  if (dstride > 16384) dstride = 16384;
+  const double* h_rows;
+  const int32_t* h_len;
+  const uint8_t* h_row_ok;
+  int rc = plan_small_run(p, 1, q_goal, q_0, v_0, a_0, 0, dstride, true, &h_rows, &h_len, &h_row_ok);
+  if (rc != LTP_OK) return rc;
+  *length = h_len[0];
+  *row_stride = dstride;
+  *success = 0;
+  for (int f = 0; f < 4; ++f) rows4[f] = h_rows + (size_t)f * (size_t)dof * (size_t)dstride;
+  if (h_len[0] > dstride) return LTP_ERR_CAPACITY;
+  uint8_t ok = 1;
+  for (int k = 0; k < dof; ++k) ok &= h_row_ok[k];
+  *success = ok;
   return LTP_OK;
 }
 

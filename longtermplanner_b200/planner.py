@@ -164,6 +164,23 @@ class LongTermPlanner:
     def planTrajectory(self, q_goal, q_0, v_0, a_0, traj: Trajectory) -> bool:
         dof = self.dof_
         ins = [_vec(x, dof) for x in (q_goal, q_0, v_0, a_0)]
+        # latency path: read the rows straight out of the planner's pinned staging block
+        view, pitch, vlen, vok = (capi.vp * 4)(), capi.i64(0), capi.i32(0), C.c_uint8(0)
+        rc = capi.plan_one_view(self._h, *[_np_ptr(x) for x in ins], C.byref(view), C.byref(pitch), C.byref(vlen),
+                                C.byref(vok))
+        if rc == capi.LTP_OK:
+            n = int(vlen.value)
+            if n <= 0:
+                return False  # early `return false` of the reference: traj untouched
+            traj.dof, traj.t_sample, traj.length = dof, self.t_sample_, n
+            fields = []
+            for f in range(4):
+                buf = (C.c_double * (dof * pitch.value)).from_address(view[f])
+                fields.append(np.frombuffer(buf, dtype=np.float64).reshape(dof, pitch.value)[:, :n].tolist())
+            traj.q, traj.v, traj.a, traj.j = fields
+            return bool(vok.value)
+        if rc != capi.LTP_ERR_CAPACITY:
+            capi.check(rc, "ltp_plan_one_view")
         cap = 4096
         while True:
             rows = [np.empty((dof, cap)) for _ in range(4)]
