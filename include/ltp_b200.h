@@ -161,6 +161,17 @@ int ltp_sample_batch(ltp_planner* p, int64_t n, const double* q_0, const double*
                      int64_t stride, double* q, double* v, double* a, double* j, uint8_t* success,
                      void* stream);
 
+/* ltp_sample_batch in time-major layout and exact-length mode with the SLOTS ordered by
+ * trajectory length (longest first): q[(sample * n + k) * dof + joint] belongs to problem
+ * order[k]; `order` (device, n int32) is written by the call, `success` stays indexed by
+ * problem. The lanes of a sampler warp run until the longest of their 32 rows ends; with
+ * problems of mixed length in index order a sixth of the store slots of random problems is
+ * idle, with equal neighbours none (5.4 -> 6.2 TB/s on B200). Same samples, permuted slots. */
+int ltp_sample_batch_sorted(ltp_planner* p, int64_t n, const double* q_0, const double* v_0,
+                            const double* a_0, const ltp_solution* sol, int64_t capacity, double* q,
+                            double* v, double* a, double* j, uint8_t* success, int32_t* order,
+                            void* stream);
+
 /* ---- streaming: more trajectories than fit in memory -------------------------------- */
 
 /* One chunk of a streamed run, as seen by the consumer. Everything is a DEVICE pointer into

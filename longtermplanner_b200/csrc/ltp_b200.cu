@@ -1064,6 +1064,7 @@ struct ltp_planner {
   // handful of problems): the kernels read the inputs from it and write the rows into it
   void* h_stage;
   int stream_sorted;  // ltp_set_stream_sorted
+  int* d_bins;        // ltp_sample_batch_sorted: kOrderBins counters
   cudaStream_t stream;  // internal stream of the host entry points
   // work list of the two-kernel solve: [0] = count, [1..] = problem indices
   void* d_work;  // SolveScratch of ltp_solve_batch
@@ -1251,6 +1252,7 @@ int ltp_create(ltp_planner** out, int device, int dof, double t_sample, const do
   p->d_scratch_bytes = 0;
   p->h_stage = nullptr;
   p->stream_sorted = 0;
+  p->d_bins = nullptr;
   p->stream = nullptr;
   p->d_work = nullptr;
   p->d_work_capacity = 0;
@@ -1343,6 +1345,7 @@ void ltp_destroy(ltp_planner* p) {
     DeviceGuard g(p->device);
     if (p->d_scratch) cudaFree(p->d_scratch);
     if (p->h_stage) cudaFreeHost(p->h_stage);
+    if (p->d_bins) cudaFree(p->d_bins);
     if (p->d_work) cudaFree(p->d_work);
     if (p->d_totals) cudaFree(p->d_totals);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -1492,15 +1495,25 @@ static size_t order_scratch_bytes(int64_t n) { return (size_t)(kOrderBins + n) *
 
 // order_scratch: kOrderBins + n ints on the device -> sorted-slot output, the order is left in
 // order_scratch + kOrderBins; nullptr: slot = problem index
+static int sample_tm_launch2(ltp_planner* p, int64_t n, const double* q_0, const double* v_0, const double* a_0,
+                             const ltp_solution* sol, int32_t horizon, int64_t stride, double* q, double* v,
+                             double* a, double* j, uint8_t* success, int* bins, int* ord, cudaStream_t st);
+
 static int sample_tm_launch(ltp_planner* p, int64_t n, const double* q_0, const double* v_0, const double* a_0,
                             const ltp_solution* sol, int32_t horizon, int64_t stride, double* q, double* v,
                             double* a, double* j, uint8_t* success, int* order_scratch, cudaStream_t st) {
+  return sample_tm_launch2(p, n, q_0, v_0, a_0, sol, horizon, stride, q, v, a, j, success, order_scratch,
+                           order_scratch ? order_scratch + kOrderBins : nullptr, st);
+}
+
+// bins (kOrderBins ints) + ord (n ints), both on the device -> sorted-slot output; nullptr: slot = problem
+static int sample_tm_launch2(ltp_planner* p, int64_t n, const double* q_0, const double* v_0, const double* a_0,
+                             const ltp_solution* sol, int32_t horizon, int64_t stride, double* q, double* v,
+                             double* a, double* j, uint8_t* success, int* bins, int* ord, cudaStream_t st) {
   const int dof = p->params.dof;
   LTP_CUDA(cudaMemcpyAsync(success, sol->reached, (size_t)n, cudaMemcpyDeviceToDevice, st));
   const int* order = nullptr;
-  if (order_scratch) {
-    int* bins = order_scratch;
-    int* ord = order_scratch + kOrderBins;
+  if (bins && ord) {
     int shift = 0;
     while ((stride >> shift) >= kOrderBins) ++shift;
     const unsigned g = (unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
@@ -1524,6 +1537,21 @@ static int sample_tm_launch(ltp_planner* p, int64_t n, const double* q_0, const 
   p->launches++;
   LTP_CUDA(cudaGetLastError());
   return LTP_OK;
+}
+
+int ltp_sample_batch_sorted(ltp_planner* p, int64_t n, const double* q_0, const double* v_0, const double* a_0,
+                            const ltp_solution* sol, int64_t capacity, double* q, double* v, double* a, double* j,
+                            uint8_t* success, int32_t* order, void* stream) {
+  if (!p || n < 0 || p->params.dof < 1 || capacity < 1) return LTP_ERR_ARG;
+  if (n == 0) return LTP_OK;
+  if (!q_0 || !v_0 || !a_0 || !sol || !q || !v || !a || !j || !success || !order) return LTP_ERR_ARG;
+  if (!sol->t_scaled || !sol->dir || !sol->v_drive || !sol->mod || !sol->traj_len || !sol->reached)
+    return LTP_ERR_ARG;
+  if (n > 0x7fffffff) return LTP_ERR_ARG;
+  DeviceGuard g(p->device);
+  if (!p->d_bins) LTP_CUDA(cudaMalloc(&p->d_bins, kOrderBins * sizeof(int)));
+  return sample_tm_launch2(p, n, q_0, v_0, a_0, sol, 0, capacity, q, v, a, j, success, p->d_bins, order,
+                           (cudaStream_t)stream);
 }
 
 int ltp_sample_batch(ltp_planner* p, int64_t n, const double* q_0, const double* v_0, const double* a_0,

@@ -72,6 +72,7 @@ class BatchTrajectories:
     j: torch.Tensor
     success: torch.Tensor   # [n] u8
     traj_len: torch.Tensor  # [n] i32
+    order: Optional[torch.Tensor] = None  # [n] i32: slot k holds problem order[k] (sorted-slot sampling)
 
 
 class _DevMem:
@@ -302,9 +303,12 @@ class LongTermPlanner:
         return BatchTrajectories(layout, 0, stride, *rows, succ, None)
 
     def sample(self, q_0, v_0, a_0, sol: BatchSolution, horizon: int = 0,
-               out: Optional[BatchTrajectories] = None, layout: str = "time_major") -> BatchTrajectories:
+               out: Optional[BatchTrajectories] = None, layout: str = "time_major",
+               sorted_slots: bool = False) -> BatchTrajectories:
         """stage 4. horizon = 0: exact length per problem (synchronises once to size the output
-        unless `out` is given); horizon > 0: fixed number of samples per problem."""
+        unless `out` is given); horizon > 0: fixed number of samples per problem.
+        sorted_slots (time-major, exact length): slot k of the tensors holds problem out.order[k],
+        problems ordered by trajectory length on the device (ltp_sample_batch_sorted)."""
         n = sol.n
         ins = [self._chk(t, n, nm) for t, nm in zip((q_0, v_0, a_0), ("q_0", "v_0", "a_0"))]
         if out is None:
@@ -313,6 +317,16 @@ class LongTermPlanner:
         out.horizon = horizon
         out.traj_len = sol.traj_len
         cs = sol.c_struct()
+        if sorted_slots:
+            if out.layout != "time_major" or horizon != 0:
+                raise ValueError("sorted_slots needs the time-major layout and exact-length mode")
+            out.order = torch.empty(n, dtype=torch.int32, device=out.q.device)
+            capi.check(capi.sample_batch_sorted(self._h, n, *[t.data_ptr() for t in ins], C.byref(cs), out.stride,
+                                                out.q.data_ptr(), out.v.data_ptr(), out.a.data_ptr(),
+                                                out.j.data_ptr(), out.success.data_ptr(), out.order.data_ptr(),
+                                                self._stream()), "ltp_sample_batch_sorted")
+            return out
+        out.order = None
         lay = capi.LAYOUT_TIME_MAJOR if out.layout == "time_major" else capi.LAYOUT_ROWS
         capi.check(capi.sample_batch(self._h, n, *[t.data_ptr() for t in ins], C.byref(cs), horizon, lay,
                                      out.stride, out.q.data_ptr(), out.v.data_ptr(), out.a.data_ptr(),

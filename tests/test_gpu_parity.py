@@ -465,3 +465,27 @@ def test_every_joint_count_bucket(dof):
         for f, k in enumerate("qvaj"):
             for i, pidx in enumerate(sel):
                 assert np.array_equal(out[f][i, :, :tl[pidx]], rows["rows"][k][pidx, :, :tl[pidx]]), (k, pidx)
+
+
+@pytest.mark.parametrize("lim,n", [(W.FRANKA7, 1111), (W.FRANKA12, 640), (W.REF_RANDOM6, 500)])
+def test_sorted_slot_sampling_equals_problem_order_sampling(lim, n):
+    """ltp_sample_batch_sorted: slot k of the time-major tensors holds problem order[k] (longest
+    trajectory first); gathered back, the samples are those of ltp_sample_batch bit for bit and
+    the success flags (indexed by problem in both) are equal"""
+    ltp, ins, sol, ref, _ = _solve_both(lim, n, 515)
+    plain = ltp.sample(ins[1], ins[2], ins[3], sol)
+    srt = ltp.sample(ins[1], ins[2], ins[3], sol, sorted_slots=True)
+    torch.cuda.synchronize()
+    order = srt.order.long()
+    assert torch.equal(torch.sort(order).values, torch.arange(n, device="cuda"))
+    tl = (sol.traj_len.long() * sol.reached.long())
+    lens = tl[order]
+    assert bool((lens[:-1] + 8 > lens[1:]).all())
+    assert torch.equal(plain.success, srt.success)
+    tlc = tl.cpu().numpy()
+    oc = order.cpu().numpy()
+    for k in "qvaj":
+        a, b = getattr(plain, k).cpu().numpy(), getattr(srt, k).cpu().numpy()
+        for slot in range(0, n, 7):
+            p = oc[slot]
+            assert np.array_equal(a[:tlc[p], p, :], b[:tlc[p], slot, :]), (k, slot, p)
