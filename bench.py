@@ -251,14 +251,8 @@ def single_plan_latency(ltp, lim, calls=300, cpu_plans=2000):
                        "solve + dense sampling, pageable host buffers in and out, one call at a time",
            "gpu_us_per_plan_median": float(np.median(us)), "gpu_us_per_plan_p90": float(np.percentile(us, 90)),
            "calls": calls, "mean_samples_per_plan": None}
-    # the same through the drop-in C++ class (Trajectory's vectors filled), tests/cpp/single_plan_bench.cc
-    exe = os.path.join(ROOT, "tests", "_build", "single_plan_bench")
-    if os.path.exists(exe):
-        try:
-            r = subprocess.run([exe, str(calls)], capture_output=True, text=True, timeout=120)
-            out["cpp_class"] = json.loads(r.stdout.strip().splitlines()[-1])
-        except Exception as e:
-            out["cpp_class"] = {"unavailable": str(e)}
+    if CPP_CLASS_LATENCY is not None:
+        out["cpp_class"] = CPP_CLASS_LATENCY
     try:
         chk, kind = cpu_checker(lim)
         chk.plan_batch(qg[:64], q0[:64], v0[:64], a0[:64], threads=1)
@@ -271,6 +265,23 @@ def single_plan_latency(ltp, lim, calls=300, cpu_plans=2000):
         out["cpu_us_per_plan"] = None
         out["cpu_kind"] = f"unavailable: {e}"
     return out
+
+
+CPP_CLASS_LATENCY = None
+
+
+def cpp_class_latency(calls=300):
+    """One planTrajectory at a time through the drop-in C++ class (Trajectory's vectors filled),
+    tests/cpp/single_plan_bench.cc. Run BEFORE this process creates its own CUDA context: two
+    contexts on one GPU time-slice, which adds tens of microseconds to every launch."""
+    exe = os.path.join(ROOT, "tests", "_build", "single_plan_bench")
+    if not os.path.exists(exe):
+        return None
+    try:
+        r = subprocess.run([exe, str(calls)], capture_output=True, text=True, timeout=120)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        return {"unavailable": str(e)}
 
 
 def load_probe():
@@ -299,11 +310,15 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world == 1 and not args.no_single:
+        global CPP_CLASS_LATENCY
+        CPP_CLASS_LATENCY = cpp_class_latency()
+
     import torch
     import torch.distributed as dist
     from longtermplanner_b200 import LongTermPlanner
 
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
