@@ -751,13 +751,13 @@ ltp_sample_row_latency_kernel(const __grid_constant__ PlannerParams P, int64_t n
                               int horizon, int64_t stride, double* __restrict__ q, double* __restrict__ v,
                               double* __restrict__ a, double* __restrict__ j, uint8_t* row_ok) {
   __shared__ __align__(16) double s_tab[kMaxSeg][2];
-  if (threadIdx.x != 0) return;
   const int dof = P.dof;
+  const int lane = threadIdx.x;
   const int64_t row = blockIdx.x;
   const int64_t p = row / dof;
   const int jt = (int)(row - p * dof);
   bool ok = false;
-  if (S.reached[p]) {
+  if (S.reached[p]) {  // uniform over the warp
     const int len = S.traj_len[p];
     if (len > 0) {
       const JointLimits L = P.lim[jt];
@@ -767,10 +767,42 @@ ltp_sample_row_latency_kernel(const __grid_constant__ PlannerParams P, int64_t n
       for (int k = 0; k < 7; ++k) t[k] = S.t_scaled[((int64_t)k * dof + jt) * n + p];
       const int n_out = horizon > 0 ? horizon : (len < stride ? len : (int)stride);
       const int n_run = n_out > len ? n_out : len;
-      const SegTableT<2> T{&s_tab[0][0]};
       RowSampler R;
       R.init(P.ts, L.j_max, t, S.dir[at], S.mod[at], q_0[at], v_0[at], a_0[at], S.v_drive[at], n_run);
-      T.build(R, n_run, true);
+      {
+        // The piece table, built by the whole warp instead of piece after piece by one thread:
+        // every lane takes one of the 26 places where the jerk or the update rule can change
+        // (the candidates of RowSampler::next_break, plus sample 0), duplicates drop out, the
+        // rank of a lane's place among the distinct ones is its piece number, the next larger
+        // place ends its piece. Same table as SegTableT::build, ~1.5 us instead of ~9.
+        int key = 0x7fffffff;
+        if (lane < 7) key = R.s[lane];
+        else if (lane == 7) key = 1;
+        else if (lane == 8) key = R.s[6] + 1;
+        else if (lane == 9) key = R.s[2] + 1;
+        else if (lane == 10) key = R.s[3] - 1;
+        else if (lane < 18) key = R.imp_idx[lane - 11];
+        else if (lane < 25) key = R.imp_idx[lane - 18] + 1;
+        else if (lane == 25) key = 0;
+        const bool in_range = (lane == 25) || (lane < 25 && key > 0 && key < n_run);
+        if (!in_range) key = 0x7fffffff;
+        const unsigned same = __match_any_sync(0xffffffffu, key);
+        const bool mine = in_range && (lane == __ffs(same) - 1);  // first lane holding this place
+        int rank = 0, nxt = 0x7fffffff;
+#pragma unroll 8
+        for (int o = 0; o < 32; ++o) {
+          const int k2 = __shfl_sync(0xffffffffu, key, o);
+          const bool f2 = __shfl_sync(0xffffffffu, (int)mine, o) != 0;
+          rank += (f2 && k2 < key) ? 1 : 0;
+          nxt = (f2 && k2 > key && k2 < nxt) ? k2 : nxt;
+        }
+        if (mine && rank < kMaxSeg) {
+          s_tab[rank][0] = R.jerk_at(key);
+          s_tab[rank][1] = seg_pack(nxt, R.v_cruise(key) ? 1 : 0, R.a_zero(key) ? 0 : 1);
+        }
+        __syncwarp();
+      }
+      if (lane != 0) return;
       double av = R.a, vv = R.v, qv = R.q, q_last = 0.0;
       const double Ts = R.Ts, vcruise = R.vcruise;
       const int64_t base = (p * dof + jt) * stride;
@@ -790,7 +822,7 @@ ltp_sample_row_latency_kernel(const __grid_constant__ PlannerParams P, int64_t n
       ok = !(q_last < L.q_min || q_last > L.q_max);  // cc:60
     }
   }
-  row_ok[row] = (uint8_t)ok;
+  if (lane == 0) row_ok[row] = (uint8_t)ok;
 }
 
 // Time-major variant: q[(sample * n + problem) * dof + joint] (a torch tensor of shape
