@@ -54,6 +54,19 @@ REF_UNIT = Limits("ref_unit", 0.001, (-3.1,), (3.1,), (10.0,), (2.0,), (4.0,))
 REF_RANDOM6 = Limits("ref_random6", 0.004, (-3.14,) * 6, (3.14,) * 6, (1.0,) * 6, (2.0,) * 6,
                      (15.0,) * 6)
 
+def random_limits(dof: int, seed: int) -> Limits:
+    """A random limit set for tests: mixed ratios a_max / j_max (1.7 ... 250 ms), three sample
+    times, asymmetric joint ranges."""
+    r = np.random.default_rng(seed)
+    half = r.uniform(1.0, 3.1, dof)
+    centre = r.uniform(-0.5, 0.5, dof)
+    v = r.uniform(0.5, 3.0, dof)
+    a = r.uniform(1.0, 20.0, dof)
+    j = a * np.exp(r.uniform(np.log(4.0), np.log(600.0), dof))
+    ts = float(r.choice([0.001, 0.004, 0.01]))
+    return Limits(f"rand{dof}", ts, tuple(centre - half), tuple(centre + half), tuple(v), tuple(a), tuple(j))
+
+
 SEEDS = {1: 0xB2000001, 2: 0xB2000002, 3: 0xB2000003, 4: 0xB2000004, 5: 0xB2000005}
 
 _GOLD = np.uint64(0x9E3779B97F4A7C15)

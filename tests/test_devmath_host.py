@@ -143,3 +143,21 @@ def test_device_math_on_reference_time_scaling_grid():
         for k in ("mod", "ts_case", "final_case", "ok"):
             assert np.array_equal(x[k], y[k]), (inc, k)
         assert count_bad(y["t"], x["t"]) == 0 and count_bad(y["v_drive"], x["v_drive"]) == 0
+
+
+@pytest.mark.parametrize("dof", [1, 3, 8, 17, 32])
+def test_device_math_on_random_limit_sets(dof):
+    """the device arithmetic (compiled for the host) against the oracle on random limit sets:
+    exact fields equal and values within tolerance wherever the reference produces a plan"""
+    lim = W.random_limits(dof, 1000 + dof)
+    n = 3000 if dof <= 8 else 800
+    qg, q0, v0, a0 = W.random_states(lim, n, 4000 + dof)
+    ref = OraclePort.from_limits(lim).solve(qg, q0, v0, a0, threads=4)
+    got = Shadow.from_limits(lim).solve(qg, q0, v0, a0)
+    r = ref["reached"].astype(bool)
+    assert np.array_equal(got["reached"], ref["reached"]) and np.array_equal(got["traj_len"], ref["traj_len"])
+    assert r.sum() > n // 2
+    for k in ("dir", "mod", "ts_case", "final_case", "slowest"):
+        assert np.array_equal(got[k][r], ref[k][r]), k
+    for k in ("t_scaled", "v_drive"):
+        assert count_bad(got[k][r], ref[k][r]) == 0, k

@@ -392,14 +392,7 @@ def test_single_item_calls_through_mapped_staging():
 
 
 def _random_limits(dof, seed):
-    r = np.random.default_rng(seed)
-    half = r.uniform(1.0, 3.1, dof)
-    centre = r.uniform(-0.5, 0.5, dof)
-    v = r.uniform(0.5, 3.0, dof)
-    a = r.uniform(1.0, 20.0, dof)
-    j = a * np.exp(r.uniform(np.log(4.0), np.log(600.0), dof))  # a_max / j_max between 1.7 and 250 ms
-    ts = float(r.choice([0.001, 0.004, 0.01]))
-    return W.Limits(f"rand{dof}", ts, tuple(centre - half), tuple(centre + half), tuple(v), tuple(a), tuple(j))
+    return W.random_limits(dof, seed)
 
 
 @pytest.mark.parametrize("dof", [1, 2, 3, 5, 8, 9, 16, 17, 31, 32])
