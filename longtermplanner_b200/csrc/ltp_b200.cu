@@ -638,7 +638,8 @@ ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, int ppb, c
 }
 
 // Latency variant of the row sampler for a handful of rows (the single-plan host calls): one
-// row per CTA, one thread. The batch kernels above hide the latency of the per-sample chain
+// row per one-warp CTA; the warp builds the piece table together, lane 0 then runs the row.
+// The batch kernels above hide the latency of the per-sample chain
 // (table look-up, then a -> v -> q) behind thousands of other rows; with seven rows in flight
 // that chain, ~115 cycles per sample, IS the run time. Here the row is walked piece by piece:
 // inside a piece the jerk and the update rule are constants, so the three recurrences
