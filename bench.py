@@ -99,6 +99,39 @@ def cpu_solve_rate(n_sample, threads, seed):
     return n_sample / dt, kind
 
 
+RTOL, ATOL = 1e-9, 1e-12  # north_star: 1e-9 relative / 1e-12 absolute on FP64 values
+
+
+def _close(got, ref):
+    with np.errstate(invalid="ignore"):
+        ok = np.abs(got - ref) <= ATOL + RTOL * np.abs(ref)
+    return ok | (got == ref) | (np.isnan(got) & np.isnan(ref))
+
+
+def parity_counts(sol, ref, only=None):
+    """Counts of disagreement between a BatchSolution (joint-major CUDA tensors, with case bytes and
+    t_opt) and the CPU checker's solve of the same problems (problem-major numpy). exact_mismatch:
+    reached, slowest, traj_len, dir, mod and the three case bytes; numeric_mismatch: switching times
+    and v_drive outside 1e-9 rel / 1e-12 abs; bitdiff: values that are not bit-identical."""
+    idx = slice(None) if only is None else only
+    exact = {}
+    for k in ("reached", "slowest", "traj_len"):
+        exact[k] = int((getattr(sol, k).cpu().numpy()[idx] != ref[k]).sum())
+    for k in ("mod", "opt_case", "ts_case", "final_case"):
+        exact[k] = int((getattr(sol, k).cpu().numpy().T[idx] != ref[k]).sum())
+    exact["dir"] = int((sol.dir.cpu().numpy().T[idx] != ref["dir"]).sum())
+    numeric, bits, values = {}, 0, 0
+    for k in ("t_scaled", "t_opt", "v_drive"):
+        got = getattr(sol, k).cpu().numpy()
+        got = (got.transpose(2, 1, 0) if got.ndim == 3 else got.T)[idx]
+        numeric[k] = int((~_close(got, ref[k])).sum())
+        bits += int((~((got == ref[k]) | (np.isnan(got) & np.isnan(ref[k])))).sum())
+        values += got.size
+    return {"checked": int(ref["reached"].shape[0]), "exact_mismatch": int(sum(exact.values())),
+            "numeric_mismatch": int(sum(numeric.values())), "bitdiff": bits, "values_compared": values,
+            "exact_by_field": exact, "numeric_by_field": numeric, "tolerance": {"rel": RTOL, "abs": ATOL}}
+
+
 def run_reference_arm(args):
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     if rank != 0:
@@ -304,6 +337,7 @@ def main():
     ap.add_argument("--no-stream", action="store_true")
     ap.add_argument("--no-replan", action="store_true")
     ap.add_argument("--no-single", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--stream-log2n", type=int, default=26, help="configs[4]: total problems = 2^k over all GPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -412,10 +446,29 @@ def main():
     clock_info = clocks.stop() if rank == 0 else None
     os.sched_setaffinity(0, all_cpus)  # the CPU baseline below uses every host core
 
-    # a cheap integrity check on what was timed (not a parity test; those live in tests/)
+    # a cheap integrity check on what was timed
     reached_frac = float(sol.reached.double().mean().item())
     assert reached_frac > 0.99, reached_frac
     assert np.array_equal(host_out["traj_len"], sol.traj_len.cpu().numpy())
+
+    # ---- parity of the timed workload at its full size: every one of this rank's 2^20 problems
+    # against the reference's own CPU code (oracle/_ref; the checker, never the thing measured)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        try:
+            chk, kind = cpu_checker(lim)
+            t0 = time.perf_counter()
+            ref = chk.solve(qg, q0, v0, a0, threads=len(all_cpus))
+            cpu_s = time.perf_counter() - t0
+            full = ltp.solve(*dev_in, with_opt=True, with_cases=True)
+            torch.cuda.synchronize()
+            parity = parity_counts(full, ref)
+            parity.update({"against": kind, "cpu_seconds": cpu_s, "workload": "configs[1], all problems of rank 0",
+                           "matches_timed_output": bool(torch.equal(full.t_scaled, sol.t_scaled)
+                                                        and torch.equal(full.traj_len, sol.traj_len))})
+            del full, ref
+        except Exception as e:  # the checker is test infrastructure; never fail the bench on it
+            parity = {"checked": 0, "unavailable": str(e)}
 
     extra = {}
     # free the configs[1] buffers before the memory-hungry sections
@@ -584,6 +637,7 @@ def main():
                     "steps": e2e_steps, "api": "ltp_solve_host (pinned host buffers in and out)",
                     "host_numa_node": numa},
             "gpu_launches": int(gpu_launches), "clocks": clock_info, "reached_frac": reached_frac,
+            "parity": parity,
         }
         line.update(extra)
         print(json.dumps(line), flush=True)

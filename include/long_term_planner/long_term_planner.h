@@ -145,12 +145,14 @@ class LongTermPlanner {
   /// on the device and trajectory slot k holds problem ltp_chunk.order[k] (ltp_set_stream_sorted).
   int planStream(int64_t n, const double* q_goal, const double* q_0, const double* v_0, const double* a_0,
                  int64_t chunk, int32_t horizon, int64_t capacity, ltp_chunk_consumer consume, void* user,
-                 ltp_stream_stats* stats = nullptr, bool sorted_slots = false);
+                 ltp_stream_stats* stats = nullptr, bool sorted_slots = false, void* input_stream = nullptr);
 
   /// NEW: receding-horizon step (ltp_advance_batch): the state `tick` samples into time-major
   /// trajectories becomes the next start state, clamped to what checkInputs accepts.
-  int advance(int64_t n, int32_t tick, const int32_t* traj_len, const uint8_t* valid, const double* q,
-              const double* v, const double* a, double* q_0, double* v_0, double* a_0, void* stream = nullptr);
+  /// capacity: sample capacity (first extent) of q, v, a; valid: pass the solution's `reached`.
+  int advance(int64_t n, int32_t tick, int64_t capacity, const int32_t* traj_len, const uint8_t* valid,
+              const double* q, const double* v, const double* a, double* q_0, double* v_0, double* a_0,
+              void* stream = nullptr);
 
  protected:
   /// reference long_term_planner.h:223-231, long_term_planner.cc:82-353

@@ -68,12 +68,15 @@ int ltp_set_solve_mode(ltp_planner* p, int mode);
  * bracketed by a CUDA event pair on the launching stream. ltp_profile_read waits for the
  * recorded launches of one kernel, returns the sum of their durations in ms and their number
  * since the last reset. Off by default; results do not depend on it. */
-#define LTP_PROFILE_SOLVE_FAST 0
+#define LTP_PROFILE_SOLVE_STAGE1 0
+#define LTP_PROFILE_SOLVE_FAST LTP_PROFILE_SOLVE_STAGE1 /* former name of slot 0 */
 #define LTP_PROFILE_SOLVE_GENERIC 1
 #define LTP_PROFILE_SAMPLE_TIME_MAJOR 2
 #define LTP_PROFILE_SAMPLE_ROWS 3
-#define LTP_PROFILE_SOLVE_ATTEMPT2 4
-#define LTP_PROFILE_KERNELS 5
+#define LTP_PROFILE_SOLVE_SCALE 4
+#define LTP_PROFILE_SOLVE_ATTEMPT2 LTP_PROFILE_SOLVE_SCALE /* former name of slot 4 */
+#define LTP_PROFILE_SOLVE_QUEUES 5 /* modified-profile + second-candidate kernels together */
+#define LTP_PROFILE_KERNELS 6
 int ltp_set_profiling(ltp_planner* p, int on);
 int ltp_profile_read(ltp_planner* p, int kernel, double* ms_sum, int64_t* launches, int reset);
 int ltp_get_dof(const ltp_planner* p);
@@ -128,7 +131,17 @@ typedef struct {
 } ltp_solution;
 
 /* replaces the solve part of LongTermPlanner::planTrajectory
- * (reference long_term_planner.cc:14-55) for n independent problems. */
+ * (reference long_term_planner.cc:14-55) for n independent problems.
+ * ONE STREAM PER PLANNER AT A TIME: the work list of the solve, the sort bins of
+ * ltp_sample_batch_sorted and the staging block of the host calls belong to the planner, not to
+ * the stream. Calls on one planner must be stream-ordered with respect to each other (same
+ * stream, or separated by events); for concurrent streams or host threads create one planner
+ * per stream -- a planner is a few hundred bytes plus its scratch. (The reference's
+ * planTrajectory is re-entrant on one object; the drop-in class is not, for the same reason.)
+ * The solve scratch (about n * (4 + 97 * dof) bytes: work list, stage hand-over and the two
+ * item queues) is allocated on the first call and whenever n grows,
+ * which must not happen inside a CUDA-graph capture: call ltp_reserve first. */
+int ltp_reserve(ltp_planner* p, int64_t n); /* scratch for solves of up to n problems, now */
 int ltp_solve_batch(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
                     const double* v_0, const double* a_0, const ltp_solution* sol, void* stream);
 
@@ -138,7 +151,10 @@ int ltp_solve_batch(ltp_planner* p, int64_t n, const double* q_goal, const doubl
  *                 capacity `stride` (traj_len[p] > stride tells the caller a row was clipped;
  *                 the success flag still refers to the complete trajectory);
  *   horizon  > 0: every problem writes exactly `horizon` samples (clipped, or continued
- *                 with the recurrence's own steady state q_last, 0, 0, 0).
+ *                 with the recurrence's own steady state q_last, 0, 0, 0). A problem that was
+ *                 not planned (reached = 0 or traj_len <= 0) holds its start position:
+ *                 (q_0, 0, 0, 0) in every sample, success = 0. With horizon == 0 nothing is
+ *                 stored for such a problem.
  * layout:
  *   LTP_LAYOUT_ROWS        q[(problem * dof + joint) * stride + sample]  -- one row per
  *                          (problem, joint) like Trajectory::q[joint][sample]; stride =
@@ -213,11 +229,13 @@ typedef struct {
  * and `capacity` as in ltp_sample_batch) into one of two ring slots on its own stream, handed
  * to `consume` (may be NULL), and the slot is recycled (`chunk` a multiple of 32 keeps the
  * sample planes aligned, see LTP_LAYOUT_TIME_MAJOR). Synchronises before returning;
- * `stats` (may be NULL) receives the totals, accumulated on the device. */
+ * `stats` (may be NULL) receives the totals, accumulated on the device. The run uses the
+ * planner's own streams; input_stream (a cudaStream_t, NULL = the default stream) is the stream
+ * on which the caller produced the inputs: the run waits for the work enqueued on it so far. */
 int ltp_plan_stream(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
                     const double* v_0, const double* a_0, int64_t chunk, int32_t horizon,
                     int64_t capacity, ltp_chunk_consumer consume, void* user,
-                    ltp_stream_stats* stats);
+                    ltp_stream_stats* stats, void* input_stream);
 /* Sorted-slot mode of ltp_plan_stream for exact-length sampling (horizon = 0); off by default.
  * The lanes of a sampler warp run until the longest of their 32 rows ends, so with problems of
  * mixed length a sixth of the store slots of random problems is idle. When on, every chunk's
@@ -231,11 +249,15 @@ int ltp_set_stream_sorted(ltp_planner* p, int on);
  * cc:810-812) becomes the next start state, joint-major [dof][n]. traj_len (may be NULL for
  * fixed-horizon trajectories, which hold every sample up to the horizon): [n], the tick is
  * limited to traj_len - 1 per problem. valid (may be NULL): [n], problems with 0 keep their
- * q_0/v_0/a_0. clamp != 0 pulls a state that overshoots a limit by
- * the recurrence's rounding back inside what checkInputs accepts (reference cc:68-77). */
-int ltp_advance_batch(ltp_planner* p, int64_t n, int32_t tick, int32_t clamp, const int32_t* traj_len,
-                      const uint8_t* valid, const double* q, const double* v, const double* a,
-                      double* q_0, double* v_0, double* a_0, void* stream);
+ * q_0/v_0/a_0 (pass the solution's `reached`: the samplers store nothing for a problem that
+ * was not planned unless a fixed horizon is used). capacity: the sample capacity of q, v, a
+ * (their first extent); the sample read is limited to capacity - 1 (a trajectory clipped by the
+ * capacity), and with traj_len == NULL a tick >= capacity is LTP_ERR_ARG. clamp != 0 pulls a
+ * state that overshoots a limit by the recurrence's rounding back inside what checkInputs
+ * accepts (reference cc:68-77). */
+int ltp_advance_batch(ltp_planner* p, int64_t n, int32_t tick, int32_t clamp, int64_t capacity,
+                      const int32_t* traj_len, const uint8_t* valid, const double* q, const double* v,
+                      const double* a, double* q_0, double* v_0, double* a_0, void* stream);
 
 /* ---- host-buffer entry points (what a caller without device buffers uses) ------------ */
 

@@ -39,7 +39,7 @@ def _sig(name, restype, *argtypes):
 EXPORTS = [
     "ltp_create", "ltp_set_limits", "ltp_set_sample_time", "ltp_set_dof", "ltp_set_solve_mode", "ltp_set_stream_sorted", "ltp_set_profiling", "ltp_profile_read", "ltp_get_dof", "ltp_get_device",
     "ltp_destroy", "ltp_status_string", "ltp_last_cuda_error", "ltp_launch_count",
-    "ltp_opt_braking_batch", "ltp_opt_switch_times_batch", "ltp_time_scaling_batch", "ltp_solve_batch",
+    "ltp_opt_braking_batch", "ltp_opt_switch_times_batch", "ltp_time_scaling_batch", "ltp_reserve", "ltp_solve_batch",
     "ltp_sample_batch", "ltp_sample_batch_sorted", "ltp_plan_stream", "ltp_advance_batch", "ltp_solve_host", "ltp_plan_host", "ltp_plan_one_view", "ltp_opt_braking_host",
     "ltp_opt_switch_times_host", "ltp_time_scaling_host", "ltp_get_trajectory_host",
 ]
@@ -85,8 +85,9 @@ LAYOUT_ROWS, LAYOUT_TIME_MAJOR = 0, 1
 sample_batch_sorted = _sig("ltp_sample_batch_sorted", C.c_int, vp, i64, vp, vp, vp, C.POINTER(Solution), i64, vp, vp,
                            vp, vp, vp, vp, vp)
 plan_stream = _sig("ltp_plan_stream", C.c_int, vp, i64, vp, vp, vp, vp, i64, i32, i64, CHUNK_CONSUMER, vp,
-                   C.POINTER(StreamStats))
-advance_batch = _sig("ltp_advance_batch", C.c_int, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp)
+                   C.POINTER(StreamStats), vp)
+advance_batch = _sig("ltp_advance_batch", C.c_int, vp, i64, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp)
+reserve = _sig("ltp_reserve", C.c_int, vp, i64)
 solve_host = _sig("ltp_solve_host", C.c_int, vp, i64, vp, vp, vp, vp, C.POINTER(Solution))
 plan_host = _sig("ltp_plan_host", C.c_int, vp, i64, vp, vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, vp,
                  C.POINTER(i64))

@@ -3,6 +3,7 @@
 #include "long_term_planner/long_term_planner.h"
 
 #include <cstdio>
+#include <initializer_list>
 #include <stdexcept>
 
 namespace long_term_planner {
@@ -12,13 +13,20 @@ const unsigned char kCaseFailUntouched = 13;  // cc:340-344: returns false WITHO
 }
 
 ltp_planner* LongTermPlanner::handle() const {
+  // The reference has no joint-count limit and reports errors through bool only; here a planner
+  // with more than LTP_MAX_DOF joints or limit vectors shorter than dof cannot be put on the
+  // device, and silently keeping the previous configuration would index past the staging block.
+  if (dof_ < 0 || dof_ > LTP_MAX_DOF)
+    throw std::invalid_argument("long_term_planner: dof outside [0, LTP_MAX_DOF = 32]");
+  for (const std::vector<double>* v : {&q_min_, &q_max_, &v_max_, &a_max_, &j_max_})
+    if ((int)v->size() < dof_) throw std::invalid_argument("long_term_planner: a limit vector is shorter than dof");
   if (!handle_) {
     ltp_planner* h = nullptr;
     int rc = ltp_create(&h, device_, dof_, t_sample_, q_min_.data(), q_max_.data(), v_max_.data(),
                         a_max_.data(), j_max_.data());
+    if (rc == LTP_ERR_ARG) throw std::invalid_argument("long_term_planner: ltp_create rejected the configuration");
     if (rc != LTP_OK) {
-      // the reference reports errors through bool only; a missing GPU is not something a
-      // caller can recover from by looking at `false`, so it is loud
+      // a missing GPU is not something a caller can recover from by looking at `false`, so it is loud
       std::fprintf(stderr, "long_term_planner: ltp_create failed: %s %s\n", ltp_status_string(rc),
                    ltp_last_cuda_error());
       throw std::runtime_error("long_term_planner: no CUDA device / ltp_create failed (no CPU fallback)");
@@ -26,10 +34,11 @@ ltp_planner* LongTermPlanner::handle() const {
     handle_ = std::shared_ptr<ltp_planner>(h, [](ltp_planner* p) { ltp_destroy(p); });
     dirty_ = false;
   } else if (dirty_) {
-    ltp_set_dof(handle_.get(), dof_);
-    ltp_set_sample_time(handle_.get(), t_sample_);
-    if (dof_ > 0)
-      ltp_set_limits(handle_.get(), q_min_.data(), q_max_.data(), v_max_.data(), a_max_.data(), j_max_.data());
+    int rc = ltp_set_dof(handle_.get(), dof_);
+    if (rc == LTP_OK) rc = ltp_set_sample_time(handle_.get(), t_sample_);
+    if (rc == LTP_OK && dof_ > 0)
+      rc = ltp_set_limits(handle_.get(), q_min_.data(), q_max_.data(), v_max_.data(), a_max_.data(), j_max_.data());
+    if (rc != LTP_OK) throw std::invalid_argument("long_term_planner: the device planner rejected the new configuration");
     dirty_ = false;
   }
   return handle_.get();
@@ -120,16 +129,17 @@ int LongTermPlanner::planTrajectories(int64_t n, const double* q_goal, const dou
 int LongTermPlanner::planStream(int64_t n, const double* q_goal, const double* q_0, const double* v_0,
                                 const double* a_0, int64_t chunk, int32_t horizon, int64_t capacity,
                                 ltp_chunk_consumer consume, void* user, ltp_stream_stats* stats,
-                                bool sorted_slots) {
+                                bool sorted_slots, void* input_stream) {
   ltp_planner* h = handle();
   ltp_set_stream_sorted(h, sorted_slots ? 1 : 0);
-  return ltp_plan_stream(h, n, q_goal, q_0, v_0, a_0, chunk, horizon, capacity, consume, user, stats);
+  return ltp_plan_stream(h, n, q_goal, q_0, v_0, a_0, chunk, horizon, capacity, consume, user, stats,
+                         input_stream);
 }
 
-int LongTermPlanner::advance(int64_t n, int32_t tick, const int32_t* traj_len, const uint8_t* valid,
-                             const double* q, const double* v, const double* a, double* q_0, double* v_0,
-                             double* a_0, void* stream) {
-  return ltp_advance_batch(handle(), n, tick, 1, traj_len, valid, q, v, a, q_0, v_0, a_0, stream);
+int LongTermPlanner::advance(int64_t n, int32_t tick, int64_t capacity, const int32_t* traj_len,
+                             const uint8_t* valid, const double* q, const double* v, const double* a,
+                             double* q_0, double* v_0, double* a_0, void* stream) {
+  return ltp_advance_batch(handle(), n, tick, 1, capacity, traj_len, valid, q, v, a, q_0, v_0, a_0, stream);
 }
 
 bool LongTermPlanner::optSwitchTimes(int joint, double q_goal, double q_0, double v_0, double a_0,

@@ -538,7 +538,19 @@ LTP_HD_NOINLINE unsigned char ost_quartic_tail(const JointLimits& L, const Prolo
 // and the caller must hand the problem to the generic kernel.
 enum { OST_FAIL = 0, OST_OK = 1, OST_DEFER = 2 };
 
-template <bool ALLOW_TAIL>
+// The cc:119 test (does the joint have to slow down first, i.e. the modified jerk profile?)
+// as a function of its own, because the regrouping kernels evaluate it ahead of the solve to
+// decide which warp an item joins; same operations as inside ost_body_t, hence the same bits.
+LTP_HD bool ost_needs_mod_profile(const JointLimits& L, double v0m, double a0m, double V) {
+  return v0m + div_by(0.5 * a0m * fabs(a0m), L.j_max, L.r_j) > V;
+}
+
+// MODE: OST_ANY evaluates the cc:119 test; OST_NORMAL / OST_MODIFIED are for callers that have
+// evaluated it already (ost_needs_mod_profile on the same operands) and compile only the branch
+// that is taken -- the warps of the regrouped kernels run one branch each.
+enum { OST_ANY = 0, OST_NORMAL = 1, OST_MODIFIED = 2 };
+
+template <bool ALLOW_TAIL, int MODE = OST_ANY>
 LTP_HD int ost_body_t(const JointLimits& L, double Ts, const Prologue& P, double q_goal, double q_0,
                       double V, double* t, unsigned char& mod, unsigned char& kase) {
   const double A = L.a_max, J = L.j_max;
@@ -554,7 +566,8 @@ LTP_HD int ost_body_t(const JointLimits& L, double Ts, const Prologue& P, double
   }
   const double v_0 = P.v0m, a_0 = P.a0m;
   double q_brake = 0.0;
-  if (v_0 + div_by(0.5 * a_0 * fabs(a_0), J, L.r_j) > V) {  // cc:119-122
+  const bool slow_down_first = MODE == OST_ANY ? ost_needs_mod_profile(L, v_0, a_0, V) : MODE == OST_MODIFIED;
+  if (slow_down_first) {  // cc:119-122
     mod = 1;
     flags |= F_MOD;
     double unused;
@@ -692,15 +705,16 @@ LTP_HD double ts_candidate1(const JointLimits& L, const TsInput& I) {
                 J, L.r_j);
 }
 
-LTP_HD double ts_candidate2(const JointLimits& L, const TsInput& I) {
-  const double A = L.a_max, J = L.j_max, a_0 = I.a_0, v_0 = I.v_0, tr = I.tr, dir = I.dir;
+// dq = dir * (q_0 - q_goal), the only way the two positions enter (cc:413)
+LTP_HD double ts_candidate2_core(const JointLimits& L, double a_0, double v_0, double tr, double dq) {
+  const double A = L.a_max, J = L.j_max;
   // w, h, g: sub-expressions the reference writes out repeatedly (cc:413-431)
   const double w = (v_0 + (a_0 * (a_0 - A)) / (2.0 * J)) / A;
   const double h = A / (2.0 * J);
   const double g = (a_0 - A) / (2.0 * J);
   const double sA = a_0 + A;
   const double J3 = pow3(J);
-  return -(dir * (I.q_0 - I.q_goal) -
+  return -(dq -
            J * (pow3(sA) / (6 * J3) - pow3(A) / (6 * J3) + (sq(A) * sA) / (2.0 * J3) +
                 (sq(sA) * (w + h + g)) / (2.0 * sq(J))) +
            a_0 * (sq(sA) / (2.0 * sq(J)) + sq(A) / (2.0 * sq(J)) + (sA * (w + h + g)) / J) -
@@ -708,6 +722,10 @@ LTP_HD double ts_candidate2(const JointLimits& L, const TsInput& I) {
          (h - v_0 / A + A * ((w - h + g) / A + 1.0 / J) -
           (sq(a_0) + 2.0 * a_0 * A + 4 * sq(A) - 2.0 * J * tr * A + 2.0 * J * v_0) / (2.0 * A * J) +
           sq(sA) / (2.0 * A * J) - (a_0 * sA) / (A * J));
+}
+
+LTP_HD double ts_candidate2(const JointLimits& L, const TsInput& I) {
+  return ts_candidate2_core(L, I.a_0, I.v_0, I.tr, I.dir * (I.q_0 - I.q_goal));
 }
 
 // candidates 3..8 need a polynomial root (quartic, quartic, quintic, quartic, quartic, sextic)

@@ -133,7 +133,8 @@ class LongTermPlanner:
         """validation switch: run every problem through the generic kernel (same results)"""
         capi.check(capi.set_solve_mode(self._h, 1 if generic_only else 0), "ltp_set_solve_mode")
 
-    KERNELS = {"solve_fast": 0, "solve_generic": 1, "sample_time_major": 2, "sample_rows": 3, "solve_attempt2": 4}
+    KERNELS = {"solve_stage1": 0, "solve_fast": 0, "solve_generic": 1, "sample_time_major": 2, "sample_rows": 3,
+               "solve_scale": 4, "solve_attempt2": 4, "solve_queues": 5}
 
     def setProfiling(self, on: bool) -> None:
         """bracket every launch of the hot kernels with CUDA events on the launching stream"""
@@ -263,6 +264,11 @@ class LongTermPlanner:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def reserve(self, n: int) -> None:
+        """allocate the solve scratch for up to n problems now (ltp_reserve), so that no later
+        solve allocates -- needed before capturing solves of a growing batch into a CUDA graph"""
+        capi.check(capi.reserve(self._h, int(n)), "ltp_reserve")
+
     def alloc_solution(self, n: int, with_opt: bool = False, with_cases: bool = False) -> BatchSolution:
         dev = torch.device("cuda", self.device)
         dof = self.dof_
@@ -390,7 +396,7 @@ class LongTermPlanner:
         cb = capi.CHUNK_CONSUMER(_cb) if consumer is not None else capi.CHUNK_CONSUMER()
         stats = capi.StreamStats()
         rc = capi.plan_stream(self._h, n, *[t.data_ptr() for t in ins], int(chunk), int(horizon), int(capacity),
-                              cb, None, C.byref(stats))
+                              cb, None, C.byref(stats), self._stream())
         if err:
             raise err[0]
         capi.check(rc, "ltp_plan_stream")
@@ -408,7 +414,7 @@ class LongTermPlanner:
         if not (0 <= tick < traj.stride):
             raise ValueError("tick outside the sampled range")
         tl = None if traj.horizon > 0 else traj.traj_len.data_ptr()
-        capi.check(capi.advance_batch(self._h, n, int(tick), 1 if clamp else 0, tl,
+        capi.check(capi.advance_batch(self._h, n, int(tick), 1 if clamp else 0, int(traj.stride), tl,
                                       None if valid is None else valid.data_ptr(), traj.q.data_ptr(),
                                       traj.v.data_ptr(), traj.a.data_ptr(), q_0.data_ptr(), v_0.data_ptr(),
                                       a_0.data_ptr(), self._stream()), "ltp_advance_batch")

@@ -141,7 +141,7 @@ int main() {
 
   // receding horizon: the state at sample 9 of the batched plan
   double *n_q = dev_alloc<double>(dof * n), *n_v = dev_alloc<double>(dof * n), *n_a = dev_alloc<double>(dof * n);
-  rc = ltp.advance(n, 9, plan.solution.traj_len, nullptr, plan.q, plan.v, plan.a, n_q, n_v, n_a, nullptr);
+  rc = ltp.advance(n, 9, plan.stride, plan.solution.traj_len, plan.solution.reached, plan.q, plan.v, plan.a, n_q, n_v, n_a, nullptr);
   CHECK(rc == LTP_OK, "advance rc=%d", rc);
   cudaDeviceSynchronize();
   std::vector<double> hn(dof * n);

@@ -16,6 +16,14 @@ ins = [torch.from_numpy(W.to_joint_major(x)).cuda() for x in W.random_states(lim
 sol = ltp.alloc_solution(n)
 for _ in range(3):
     ltp.solve(*ins, out=sol)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(20):
+    ltp.solve(*ins, out=sol)
+e1.record()
+torch.cuda.synchronize()
+step_ms = e0.elapsed_time(e1) / 20
 ltp.setProfiling(True)
 for _ in range(20):
     ltp.solve(*ins, out=sol)
@@ -23,7 +31,11 @@ ms, cnt = ltp.kernelTime("solve_fast")
 ms2, cnt2 = ltp.kernelTime("solve_generic")
 chk = int(sol.traj_len.sum().item())
 ms3, cnt3 = ltp.kernelTime("solve_attempt2")
-print(f"{os.environ.get('LTP_B200_LIB', 'default')}: dof {lim.dof} solve_fast {ms / cnt:.4f} ms + attempt2 {ms3 / max(cnt3, 1):.4f} ms -> {n / (ms / cnt + ms3 / max(cnt3, 1)) / 1e3:.1f} M plans/s; "
+try:
+    ms4, cnt4 = ltp.kernelTime("solve_queues")
+except Exception:
+    ms4, cnt4 = 0.0, 0
+print(f"{os.environ.get('LTP_B200_LIB', 'default')}: dof {lim.dof} step {step_ms:.4f} ms = {n / step_ms / 1e3:.1f} M plans/s; kernel slot0 {ms / cnt:.4f} ms + slot4 {ms3 / max(cnt3, 1):.4f} ms + slot5 {ms4 / max(cnt4, 1):.4f} ms; "
       f"generic {ms2 / cnt2:.4f} ms; traj_len checksum {chk}", flush=True)
 if lim.dof == 7:
     n2, H = 4096, 2001
