@@ -68,14 +68,12 @@ int ltp_set_solve_mode(ltp_planner* p, int mode);
  * bracketed by a CUDA event pair on the launching stream. ltp_profile_read waits for the
  * recorded launches of one kernel, returns the sum of their durations in ms and their number
  * since the last reset. Off by default; results do not depend on it. */
-#define LTP_PROFILE_SOLVE_STAGE1 0
-#define LTP_PROFILE_SOLVE_FAST LTP_PROFILE_SOLVE_STAGE1 /* former name of slot 0 */
-#define LTP_PROFILE_SOLVE_GENERIC 1
+#define LTP_PROFILE_SOLVE_TILE 0     /* stage 1 + team meeting + first candidate (every problem) */
+#define LTP_PROFILE_SOLVE_GENERIC 1  /* every-branch kernel (work list, or all problems in GENERIC mode) */
 #define LTP_PROFILE_SAMPLE_TIME_MAJOR 2
 #define LTP_PROFILE_SAMPLE_ROWS 3
-#define LTP_PROFILE_SOLVE_SCALE 4
-#define LTP_PROFILE_SOLVE_ATTEMPT2 LTP_PROFILE_SOLVE_SCALE /* former name of slot 4 */
-#define LTP_PROFILE_SOLVE_QUEUES 5 /* modified-profile + second-candidate kernels together */
+#define LTP_PROFILE_SOLVE_MODIFIED 4 /* queue B: modified-profile nested solve */
+#define LTP_PROFILE_SOLVE_SECOND 5   /* queue C: second candidate */
 #define LTP_PROFILE_KERNELS 6
 int ltp_set_profiling(ltp_planner* p, int on);
 int ltp_profile_read(ltp_planner* p, int kernel, double* ms_sum, int64_t* launches, int reset);

@@ -49,28 +49,31 @@ struct DeviceSolution {  // ltp_solution, by value
 constexpr int kTile = 32;  // problems per CTA
 
 // ------------------------------------------------------------------------------------
-// Stages 1-3 (reference cc:14-55) run as three kernels on one stream:
+// Stages 1-3 (reference cc:14-55) run as four kernels on one stream:
 //
-//   ltp_solve_stage1_kernel  every (problem, joint): input check, braking solution and the
-//                            time-optimal phase solve (closed form, no quartic tail). The
-//                            joint's record is written as if it were the slowest joint of its
-//                            problem -- which settles one joint in dof for good.
-//   ltp_solve_scale_kernel   every (problem, joint) again: slowest-joint arg-max over the
-//                            stage-1 end times, first cruise-speed candidate, then the nested
-//                            phase solves REGROUPED inside the CTA so that a warp runs one
-//                            branch of the reference's control flow (see below).
+//   ltp_solve_tile_kernel    every (problem, joint). A CTA is ONE joint of 128 consecutive
+//                            problems; the dof CTAs that share a tile of problems form a team.
+//                            Stage 1 (input check, braking solution, time-optimal phase solve,
+//                            closed form, no quartic tail) -> the team exchanges its end times
+//                            through an L2-resident buffer and meets at a device-scope arrival
+//                            counter -> slowest-joint arg-max -> first cruise-speed candidate ->
+//                            the majority (normal jerk profile) runs its nested phase solve on
+//                            the spot; the joints that have to slow down first are appended to
+//                            queue B, those the first candidate does not settle to queue C.
+//   ltp_solve_modified_kernel  queue B: nested solve with only the modified-profile branch.
+//   ltp_solve_second_kernel    queue C: second candidate + nested solve.
 //   ltp_solve_generic_kernel the work list (or, in generic-only mode, every problem): every
 //                            branch of the reference evaluated in-thread, including the
-//                            Francis-QR root finder. It overwrites whatever the other two
-//                            stored for a deferred problem.
+//                            Francis-QR root finder. It overwrites whatever the others stored
+//                            for a deferred problem.
 //
-// A CTA of the first two kernels is ONE joint of 128 consecutive problems (joint = block index
-// modulo dof, so the dof CTAs of a tile of problems are scheduled next to each other and the
-// second kernel finds the tile's end times in L2). The joint being a function of the block
-// index, the limit set sits in uniform registers / constant-bank operands instead of sixteen
-// vector registers per thread, and both kernels fit a register budget that keeps 40+ warps
-// per SM in flight -- the solve is bound by FP64 dependency latency, not pipe throughput.
-// Splitting at the arg-max also keeps the time-optimal times out of the search's live range.
+// The joint being a function of the block index, the limit set sits in uniform registers /
+// constant-bank operands instead of sixteen vector registers per thread, and a warp runs one
+// branch of the reference's control flow wherever the branches are expensive.
+//
+// The tile kernel is persistent: the grid is a whole number of teams that are all resident at
+// once (occupancy query at planner creation), every team walks the tiles round robin. That is
+// what makes the meeting point safe -- a team only ever waits for CTAs that are running.
 //
 // The split changes no result: every step is the same per-item function the every-branch
 // kernel evaluates (csrc/ltp_pipeline.cuh; tests/host_shadow.cc replays the hand-overs on the
@@ -101,10 +104,10 @@ __device__ __forceinline__ SolveShared carve_shared(unsigned char* raw, int dof)
 }
 
 // Device scratch of one solve: counters (the lengths of the work sub-lists, then of the B and C
-// sub-queues), the work list (kStripes sub-lists of q_cap problem indices), what stage 1 hands to the scaling kernel per
-// joint -- the time-optimal end time ([dof][n] doubles; the copy in t_scaled is overwritten by
-// the scaling kernels while other CTAs still read it) and the flags ([dof][n] bytes) -- and the
-// two item queues (structure of arrays).
+// sub-queues, then the arrival counters of the teams), the work list (kStripes sub-lists of q_cap
+// problem indices), the teams' exchange buffers (per team, double-buffered by tile parity: dof x
+// 128 end times and flag bytes -- 1.5 MB in all, it never leaves L2) and the two item queues
+// (structure of arrays).
 //
 // A queue is cut into kStripes sub-queues per joint, each with its own counter: an append is one
 // atomicAdd per warp, and atomics on ONE address retire at ~200 M/s on this part (measured: with
@@ -120,15 +123,16 @@ struct ItemQueue {
 #define LTP_QUEUE_STRIPES 32
 #endif
 constexpr int kStripes = LTP_QUEUE_STRIPES;
+constexpr int kMaxTeams = 2048;  // >= resident CTAs of the tile kernel / dof on any part
 constexpr int kCountW = 0, kCountB = kStripes, kCountC = kCountB + LTP_MAX_DOF * kStripes,
-              kCounters = kCountC + LTP_MAX_DOF * kStripes;
+              kCountTeam = kCountC + LTP_MAX_DOF * kStripes, kCounters = kCountTeam + kMaxTeams;
 constexpr size_t kCounterBytes = ((kCounters * sizeof(int) + 255) / 256) * 256;
 
 struct SolveScratch {
   int* counters;
   int* work_list;
-  double* t_end;
-  unsigned char* jflag;
+  double* t_end;         // [team][parity][dof][128]
+  unsigned char* jflag;  // [team][parity][dof][128]
   ItemQueue queue_b, queue_c;
   int q_cap;         // items per sub-queue
   int64_t q_stride;  // items per joint = kStripes * q_cap
@@ -144,7 +148,7 @@ inline int queue_cap(int64_t n) {
 }
 
 inline size_t solve_scratch_bytes(int dof, int64_t n) {
-  const size_t dn = (size_t)dof * (size_t)n;
+  const size_t dn = (size_t)kMaxTeams * 2 * (size_t)dof * kJointCta;
   const size_t dq = (size_t)dof * (size_t)kStripes * (size_t)queue_cap(n);
   return kCounterBytes + scratch_round((size_t)kStripes * queue_cap(n) * sizeof(int)) + scratch_round(dn * 8) +
          scratch_round(dn) +
@@ -154,7 +158,7 @@ inline size_t solve_scratch_bytes(int dof, int64_t n) {
 inline SolveScratch carve_scratch(void* base, int dof, int64_t n) {
   SolveScratch s;
   unsigned char* b = static_cast<unsigned char*>(base);
-  const size_t dn = (size_t)dof * (size_t)n;
+  const size_t dn = (size_t)kMaxTeams * 2 * (size_t)dof * kJointCta;
   s.q_cap = queue_cap(n);
   s.q_stride = (int64_t)kStripes * s.q_cap;
   const size_t dq = (size_t)dof * (size_t)s.q_stride;
@@ -254,8 +258,8 @@ __device__ __forceinline__ bool finish_problem(const SolveShared& sh, const Devi
 
 // Register budgets (ptxas -v, sm_100a): stage 1 needs 64 registers unconstrained and spills
 // 56 bytes at 48; the scaling kernel is larger.
-#ifndef LTP_STAGE1_MINB
-#define LTP_STAGE1_MINB 10
+#ifndef LTP_TILE_MINB
+#define LTP_TILE_MINB 8
 #endif
 #ifndef LTP_SCALE_MINB
 #define LTP_SCALE_MINB 8
@@ -263,25 +267,6 @@ __device__ __forceinline__ bool finish_problem(const SolveShared& sh, const Devi
 #ifndef LTP_QUEUE_CTAS_PER_SM
 #define LTP_QUEUE_CTAS_PER_SM 8
 #endif
-
-__global__ void __launch_bounds__(kJointCta, LTP_STAGE1_MINB)
-ltp_solve_stage1_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_goal,
-                        const double* __restrict__ q_0, const double* __restrict__ v_0,
-                        const double* __restrict__ a_0, DeviceSolution S, SolveScratch X) {
-  const int dof = P.dof;
-  const unsigned tile = blockIdx.x / (unsigned)dof;
-  const int jt = (int)(blockIdx.x - tile * (unsigned)dof);
-  const int64_t p = (int64_t)tile * kJointCta + threadIdx.x;
-  if (p >= n) return;
-  const JointLimits& L = P.lim[jt];
-  const int64_t at = (int64_t)jt * n + p;
-  Stage1Out o;
-  stage1_joint(L, P.ts, q_goal[at], q_0[at], v_0[at], a_0[at], o);
-  store_joint(S, dof, jt, n, p, o.t_opt, o.t_opt, o.dir, L.v_max, o.mod, o.opt_case, 0, o.opt_case);
-  X.t_end[at] = o.t_opt[6];
-  X.jflag[at] = o.flags;
-  if (jt == 0) S.traj_len[p] = 0;
-}
 
 // The work list is striped like the queues (by problem tile): the exchange on traj_len elects one
 // sender per problem, so a sub-list receives at most the problems behind its stripe (q_cap).
@@ -336,79 +321,121 @@ __device__ __forceinline__ ScaleItem queue_load(const ItemQueue& Q, int64_t e, i
   return it;
 }
 
-// Stages 2 and 3 (cc:31-55) for one joint of 128 consecutive problems, one thread per problem,
-// no shared memory and no barrier: arg-max over the dof end times stage 1 left in the scratch
-// (strict '>': lowest joint index wins ties, NaN never wins), then what the joint needs --
-// nothing (it is the slowest one: the record stage 1 wrote stands), the rare brake-only exit
-// (settled on the spot), or the cruise-speed search: first candidate (closed form, one sqrt) and
-// the cc:119 test at that speed. The majority (normal jerk profile, ~80 % of the searching
-// joints) runs its nested phase solve right here with only that branch compiled in; a joint that
-// has to slow down first is appended to queue B, one the first candidate does not settle to
-// queue C, and those are finished by full warps of their own kind in the two kernels below.
-__global__ void __launch_bounds__(kJointCta, LTP_SCALE_MINB)
-ltp_solve_scale_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_goal,
-                       const double* __restrict__ q_0, const double* __restrict__ v_0,
-                       const double* __restrict__ a_0, DeviceSolution S, SolveScratch X) {
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Stages 1-3 (cc:14-55) for one joint of 128 consecutive problems at a time, one thread per
+// problem. blockIdx = team * dof + joint; team t takes the tiles t, t + teams, t + 2 teams, ...
+// Per tile:
+//  1. stage 1 for the thread's (problem, joint); the end time and the flags go to the team's
+//     exchange buffer (parity of the tile count: a member that is already a tile ahead writes
+//     the other half);
+//  2. the team meets: every CTA adds one to the team's arrival counter and waits until all dof
+//     members have done so for this tile (one thread polls, the rest wait at the barrier);
+//  3. arg-max over the dof end times (strict '>': lowest joint index wins ties, NaN never wins),
+//     then what the joint needs -- nothing more (it is the slowest one: its time-optimal times,
+//     still in registers, are the result), the rare brake-only exit (settled on the spot), or
+//     the cruise-speed search: first candidate (closed form, one sqrt) and the cc:119 test at
+//     that speed. The majority (normal jerk profile, ~80 % of the searching joints) runs its
+//     nested phase solve right here with only that branch compiled in; a joint that has to slow
+//     down first is appended to queue B, one the first candidate does not settle to queue C.
+// Every (problem, joint) record is written exactly once, by the thread that settles it.
+__global__ void __launch_bounds__(kJointCta, LTP_TILE_MINB)
+ltp_solve_tile_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_goal,
+                      const double* __restrict__ q_0, const double* __restrict__ v_0,
+                      const double* __restrict__ a_0, DeviceSolution S, SolveScratch X) {
   const int dof = P.dof;
-  const unsigned tile = blockIdx.x / (unsigned)dof;
-  const int jt = (int)(blockIdx.x - tile * (unsigned)dof);
-  const int64_t p = (int64_t)tile * kJointCta + threadIdx.x;
+  const int team = blockIdx.x / (unsigned)dof;
+  const int jt = (int)(blockIdx.x - (unsigned)team * (unsigned)dof);
+  const int teams = gridDim.x / (unsigned)dof;
+  const int tid = threadIdx.x;
   const JointLimits& L = P.lim[jt];
   const double Ts = P.ts;
-  bool to_b = false, to_c = false;
-  ScaleItem it;
-  it.t_req = it.V = it.v0m = it.a0m = it.dist = 0.0;
-  it.meta = 0;
-  if (p < n) {
+  const int64_t tiles = (n + kJointCta - 1) / kJointCta;
+  int* const arrive = X.counters + kCountTeam + team;
+  int round = 0;
+  for (int64_t tile = team; tile < tiles; tile += teams, ++round) {
+    const int64_t p = tile * kJointCta + tid;
+    const bool valid = p < n;
     const int64_t at = (int64_t)jt * n + p;
-    // everything the thread may need is requested before the first value is looked at: one trip
-    // to memory instead of two (the slowest joint's lanes read their start state for nothing)
-    const double qg = q_goal[at], q0 = q_0[at], v0 = v_0[at], a0 = a_0[at], dir = S.dir[at];
-    double t_req = -1;
-    int slowest = -1;
-    unsigned any = 0, my_flag = 0;
-#pragma unroll 4
-    for (int i = 0; i < dof; ++i) {
-      const unsigned f = X.jflag[(int64_t)i * n + p];
-      const double ti = X.t_end[(int64_t)i * n + p];
-      any |= f;
-      my_flag = i == jt ? f : my_flag;
-      if (ti > t_req) {
-        t_req = ti;
-        slowest = i;
+    double qg = 0, q0 = 0, v0 = 0, a0 = 0;
+    if (valid) {
+      qg = q_goal[at]; q0 = q_0[at]; v0 = v_0[at]; a0 = a_0[at];
+    }
+    Stage1Out o;
+    stage1_joint(L, Ts, qg, q0, v0, a0, o);
+    const size_t half = ((size_t)team * 2 + (round & 1)) * (size_t)dof * kJointCta;
+    __stcg(X.t_end + half + (size_t)jt * kJointCta + tid, o.t_opt[6]);
+    X.jflag[half + (size_t)jt * kJointCta + tid] = valid ? o.flags : (unsigned char)0;
+    if (valid) {
+      store_joint_opt(S, dof, jt, n, p, o.t_opt, o.dir, o.opt_case);
+      if (jt == 0) S.traj_len[p] = 0;
+    }
+    // ---- the team meets
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(arrive, 1);
+      const int want = dof * (round + 1);
+      // (a member that never arrives would mean the grid is not fully resident -- impossible by
+      // construction; fail loudly after a few seconds rather than hang the device)
+      unsigned spins = 0;
+      while (ld_acquire(arrive) < want) {
+        __nanosleep(40);
+        if (++spins > (1u << 25)) __trap();
       }
     }
-    const bool reached = !(any & JF_FAIL) && slowest != -1;
-    if (jt == 0) {
-      S.slowest[p] = slowest;
-      S.reached[p] = (uint8_t)reached;
-    }
-    if (any & JF_DEFER) {  // a joint without time-optimal times yet: the whole problem is deferred
-      if (jt == 0) defer_problem(S, X, p);
-    } else if (!reached) {  // aborted before time scaling (cc:15,29,39): the record says so
+    __syncthreads();
+    bool to_b = false, to_c = false;
+    ScaleItem it;
+    it.t_req = it.V = it.v0m = it.a0m = it.dist = 0.0;
+    it.meta = 0;
+    if (valid) {
+      double t_req = -1;
+      int slowest = -1;
+      unsigned any = 0;
+#pragma unroll 8
+      for (int i = 0; i < dof; ++i) {
+        const unsigned f = __ldcg(X.jflag + half + (size_t)i * kJointCta + tid);
+        const double ti = __ldcg(X.t_end + half + (size_t)i * kJointCta + tid);
+        any |= f;
+        if (ti > t_req) {
+          t_req = ti;
+          slowest = i;
+        }
+      }
+      const bool reached = !(any & JF_FAIL) && slowest != -1;
+      if (jt == 0) {
+        S.slowest[p] = slowest;
+        S.reached[p] = (uint8_t)reached;
+      }
+      JointResult R;
+      R.v_drive = L.v_max;
+      R.mod = o.mod;
+      bool settled = false;
+      if (any & JF_DEFER) {  // a joint without time-optimal times yet: the whole problem is deferred
+        if (jt == 0) defer_problem(S, X, p);
+      } else if (!reached) {  // aborted before time scaling (cc:15,29,39): the record says so
+        zero7(R.t);
+        R.ts_case = 255;
+        R.final_case = 255;
+        store_joint_scaled(S, dof, jt, n, p, R.t, R.v_drive, R.mod, R.ts_case, R.final_case);
+      } else if (jt == slowest) {  // cc:44-46, then the cc:50-55 fallback (t_scaled stays zero)
 #pragma unroll
-      for (int k = 0; k < 7; ++k) S.t_scaled[((int64_t)k * dof + jt) * n + p] = 0.0;
-      if (S.ts_case) S.ts_case[at] = 255;
-      if (S.final_case) S.final_case[at] = 255;
-    } else if (jt == slowest) {  // cc:44-46 + cc:50-55: the record stage 1 wrote stands
-      const int len = joint_samples_from_end(t_req, Ts);
-      if (len < 0) defer_problem(S, X, p);
-      else atomicMax(S.traj_len + p, len);
-    } else {
-      if (my_flag & JF_BRAKE_ONLY) {
+        for (int k = 0; k < 7; ++k) R.t[k] = o.t_opt[k];
+        R.ts_case = 0;
+        R.final_case = o.opt_case;
+        settled = true;
+      } else if (o.flags & JF_BRAKE_ONLY) {
         const Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0);
-        double t_opt[7];
-#pragma unroll
-        for (int k = 0; k < 7; ++k) t_opt[k] = S.t_scaled[((int64_t)k * dof + jt) * n + p];
-        JointResult R;
-        if (stage3_brake_only(L, Ts, pro, qg, q0, v0, a0, t_req, t_opt, CASE_BRAKE_ONLY, R) == S3_SETTLED)
-          settle_joint(S, X, dof, jt, n, p, Ts, R);
-        else
-          defer_problem(S, X, p);
-      } else if (stage3_classify(L, qg, q0, v0, a0, dir, t_req, it) == S3_QUEUE_A) {
-        JointResult R;
+        if (stage3_brake_only(L, Ts, pro, qg, q0, v0, a0, t_req, o.t_opt, o.opt_case, R) == S3_SETTLED) settled = true;
+        else defer_problem(S, X, p);
+      } else if (stage3_classify(L, qg, q0, v0, a0, o.dir, t_req, it) == S3_QUEUE_A) {
         const int r = scale_attempt1_class_a(L, Ts, it, R);
-        if (r == SA_ACCEPT) settle_joint(S, X, dof, jt, n, p, Ts, R);
+        if (r == SA_ACCEPT) settled = true;
         else if (r == SA_DEFER) defer_problem(S, X, p);
         else to_c = true;
       } else {
@@ -417,12 +444,13 @@ ltp_solve_scale_kernel(const __grid_constant__ PlannerParams P, int64_t n, const
         to_b = v_ok;
         to_c = !v_ok;
       }
+      if (settled) settle_joint(S, X, dof, jt, n, p, Ts, R);
     }
+    const int sub = jt * kStripes + (int)(tile % kStripes);
+    const int64_t sub_base = (int64_t)sub * X.q_cap;
+    queue_push(X.queue_b, X.counters + kCountB + sub, sub_base, to_b, it, p);
+    queue_push(X.queue_c, X.counters + kCountC + sub, sub_base, to_c, it, p);
   }
-  const int sub = jt * kStripes + (int)(tile % (unsigned)kStripes);
-  const int64_t sub_base = (int64_t)sub * X.q_cap;
-  queue_push(X.queue_b, X.counters + kCountB + sub, sub_base, to_b, it, p);
-  queue_push(X.queue_c, X.counters + kCountC + sub, sub_base, to_c, it, p);
 }
 
 // Queue B: the first candidate's nested solve for the joints that have to slow down first
@@ -434,12 +462,17 @@ __global__ void __launch_bounds__(kJointCta, LTP_SCALE_MINB)
 ltp_solve_modified_kernel(const __grid_constant__ PlannerParams P, int64_t n, DeviceSolution S, SolveScratch X) {
   const int dof = P.dof;
   const double Ts = P.ts;
+  // the sub-queue lengths, fetched once (walking them in global memory is a chain of dof * kStripes
+  // dependent loads per CTA)
+  __shared__ int s_count[LTP_MAX_DOF * kStripes];
+  for (int i = threadIdx.x; i < dof * kStripes; i += kJointCta) s_count[i] = X.counters[kCountB + i];
+  __syncthreads();
   int w = blockIdx.x;  // tile of the current sub-queue this CTA takes next
   for (int jt = 0; jt < dof; ++jt) {
     const JointLimits& L = P.lim[jt];
     for (int st = 0; st < kStripes; ++st) {
       const int sub = jt * kStripes + st;
-      const int count = X.counters[kCountB + sub];
+      const int count = s_count[sub];
       const int tiles = (count + kJointCta - 1) / kJointCta;
       const int64_t sub_base = (int64_t)sub * X.q_cap;
       for (; w < tiles; w += gridDim.x) {
@@ -471,12 +504,15 @@ __global__ void __launch_bounds__(kJointCta, LTP_SCALE_MINB)
 ltp_solve_second_kernel(const __grid_constant__ PlannerParams P, int64_t n, DeviceSolution S, SolveScratch X) {
   const int dof = P.dof;
   const double Ts = P.ts;
+  __shared__ int s_count[LTP_MAX_DOF * kStripes];
+  for (int i = threadIdx.x; i < dof * kStripes; i += kJointCta) s_count[i] = X.counters[kCountC + i];
+  __syncthreads();
   int w = blockIdx.x;
   for (int jt = 0; jt < dof; ++jt) {
     const JointLimits& L = P.lim[jt];
     for (int st = 0; st < kStripes; ++st) {
       const int sub = jt * kStripes + st;
-      const int count = X.counters[kCountC + sub];
+      const int count = s_count[sub];
       const int tiles = (count + kJointCta - 1) / kJointCta;
       const int64_t sub_base = (int64_t)sub * X.q_cap;
       for (; w < tiles; w += gridDim.x) {
@@ -1240,6 +1276,7 @@ struct ltp_planner {
   int d_work_dof;
   int solve_mode;  // LTP_SOLVE_AUTO / LTP_SOLVE_GENERIC
   int sm_count;
+  int tile_ctas_per_sm;  // resident CTAs of ltp_solve_tile_kernel per SM (occupancy query)
   // optional per-kernel timing (ltp_set_profiling): CUDA events recorded on the launching
   // stream directly around the hot kernels, read back by ltp_profile_read
   bool profiling;
@@ -1427,6 +1464,7 @@ int ltp_create(ltp_planner** out, int device, int dof, double t_sample, const do
   p->d_work_dof = 0;
   p->solve_mode = LTP_SOLVE_AUTO;
   p->sm_count = 148;
+  p->tile_ctas_per_sm = 1;
   p->profiling = false;
   std::memset(p->timed, 0, sizeof p->timed);
   for (int i = 0; i < 2; ++i) {
@@ -1448,6 +1486,10 @@ int ltp_create(ltp_planner** out, int device, int dof, double t_sample, const do
     cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaStreamCreate"); }
     cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ltp_solve_tile_kernel, kJointCta, 0);
+    if (e != cudaSuccess || per_sm < 1) { cudaStreamDestroy(p->stream); delete p; return cuda_fail(e, "occupancy(ltp_solve_tile_kernel)"); }
+    p->tile_ctas_per_sm = per_sm;
   }
   *out = p;
   return LTP_OK;
@@ -1577,8 +1619,12 @@ int ltp_time_scaling_batch(ltp_planner* p, int64_t n, const double* q_goal, cons
 
 // launches of stages 1-3 on `st`. work: device buffer of n + 1 ints ([0] = count), only
 // touched in LTP_SOLVE_AUTO mode.
+// grid_share: how many solves of this planner may be in flight on different streams (the host
+// pipeline runs two): each gets that fraction of the resident-CTA capacity for its teams, so
+// that all teams of all of them are resident together whatever order the CTAs are dispatched in.
 static int solve_launch(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0, const double* v_0,
-                        const double* a_0, const ltp_solution* sol, void* scratch, cudaStream_t st) {
+                        const double* a_0, const ltp_solution* sol, void* scratch, cudaStream_t st,
+                        int grid_share = 1) {
   const int dof = p->params.dof;
   const dim3 block(kTile, dof);
   const unsigned tiles = (unsigned)((n + kTile - 1) / kTile);
@@ -1604,23 +1650,27 @@ static int solve_launch(ltp_planner* p, int64_t n, const double* q_goal, const d
   } else {
     LTP_CUDA(cudaMemsetAsync(X.counters, 0, kCounterBytes, st));
     const int64_t jtiles = (n + kJointCta - 1) / kJointCta * dof;  // one CTA per (tile of problems, joint)
-    if (jtiles > 0x7fffffff) return LTP_ERR_ARG;
     {
-      ProfScope ps(p, LTP_PROFILE_SOLVE_STAGE1, st);
-      ltp_solve_stage1_kernel<<<(unsigned)jtiles, kJointCta, 0, st>>>(p->params, n, q_goal, q_0, v_0, a_0, ds, X);
-      p->launches++;
-    }
-    {
-      ProfScope ps(p, LTP_PROFILE_SOLVE_SCALE, st);
-      ltp_solve_scale_kernel<<<(unsigned)jtiles, kJointCta, 0, st>>>(p->params, n, q_goal, q_0, v_0, a_0, ds, X);
+      // whole teams only, all of them resident at once (the teams meet at a spin-wait)
+      int64_t teams = (int64_t)p->sm_count * p->tile_ctas_per_sm / grid_share / dof;
+      if (teams > kMaxTeams) teams = kMaxTeams;
+      if (teams > jtiles / dof) teams = jtiles / dof;
+      if (teams < 1) return LTP_ERR_ARG;
+      ProfScope ps(p, LTP_PROFILE_SOLVE_TILE, st);
+      ltp_solve_tile_kernel<<<(unsigned)(teams * dof), kJointCta, 0, st>>>(p->params, n, q_goal, q_0, v_0, a_0, ds, X);
       p->launches++;
     }
     if (dof > 1) {  // the two queues (a single joint is its problem's slowest one)
-      ProfScope ps(p, LTP_PROFILE_SOLVE_QUEUES, st);
       const int64_t cap = (int64_t)p->sm_count * LTP_QUEUE_CTAS_PER_SM;
       const unsigned gq = (unsigned)(jtiles < cap ? jtiles : cap);
-      ltp_solve_modified_kernel<<<gq, kJointCta, 0, st>>>(p->params, n, ds, X);
-      ltp_solve_second_kernel<<<gq, kJointCta, 0, st>>>(p->params, n, ds, X);
+      {
+        ProfScope ps(p, LTP_PROFILE_SOLVE_MODIFIED, st);
+        ltp_solve_modified_kernel<<<gq, kJointCta, 0, st>>>(p->params, n, ds, X);
+      }
+      {
+        ProfScope ps(p, LTP_PROFILE_SOLVE_SECOND, st);
+        ltp_solve_second_kernel<<<gq, kJointCta, 0, st>>>(p->params, n, ds, X);
+      }
       p->launches += 2;
     }
     // the work list is drained by a fixed-size grid-stride launch: its length never leaves the device
@@ -1823,7 +1873,7 @@ int ltp_solve_host(ltp_planner* p, int64_t n, const double* q_goal, const double
     for (int i = 0; i < 4; ++i)
       LTP_CUDA(cudaMemcpy2DAsync(d_in[s][i], (size_t)c * 8, h_in[i] + p0, (size_t)n * 8, (size_t)c * 8, dof,
                                  cudaMemcpyHostToDevice, st));
-    int rc = solve_launch(p, c, d_in[s][0], d_in[s][1], d_in[s][2], d_in[s][3], &d, d_work[s], st);
+    int rc = solve_launch(p, c, d_in[s][0], d_in[s][1], d_in[s][2], d_in[s][3], &d, d_work[s], st, slots);
     if (rc != LTP_OK) return rc;
 #define LTP_OUT2D(FIELD, ROWS, ELEM)                                                                   \
   LTP_CUDA(cudaMemcpy2DAsync(hs->FIELD + p0, (size_t)n * (ELEM), d.FIELD, (size_t)c * (ELEM),           \
@@ -1922,7 +1972,7 @@ int ltp_plan_stream(ltp_planner* p, int64_t n, const double* q_goal, const doubl
     for (int i = 0; i < 4; ++i)
       LTP_CUDA(cudaMemcpy2DAsync(d_in[s][i], (size_t)c * 8, src[i] + p0, (size_t)n * 8, (size_t)c * 8, dof,
                                  cudaMemcpyDeviceToDevice, st));
-    int rc = solve_launch(p, c, d_in[s][0], d_in[s][1], d_in[s][2], d_in[s][3], &ds[s], d_work[s], st);
+    int rc = solve_launch(p, c, d_in[s][0], d_in[s][1], d_in[s][2], d_in[s][3], &ds[s], d_work[s], st, slots);
     if (rc != LTP_OK) return rc;
     rc = sample_tm_launch(p, c, d_in[s][1], d_in[s][2], d_in[s][3], &ds[s], horizon, capacity, d_traj[s][0],
                           d_traj[s][1], d_traj[s][2], d_traj[s][3], d_succ[s],
