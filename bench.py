@@ -420,11 +420,11 @@ def main():
     for k in range(args.steps):
         ltp.solve(*dev_in, out=sol)
     per_kernel = {}
-    for kname in ("solve_tile", "solve_modified", "solve_second", "solve_generic"):
+    for kname in ("solve_fast", "solve_attempt2", "solve_generic"):
         k_ms, k_cnt = ltp.kernelTime(kname)
         per_kernel[kname] = k_ms / max(k_cnt, 1)
     ltp.setProfiling(False)
-    kernel_ms = per_kernel["solve_tile"]
+    kernel_ms = per_kernel["solve_fast"]
     generic_kernel_ms = per_kernel["solve_generic"]
 
     # ---- end to end through the host-buffer C-ABI entry point ------------------------------
@@ -541,15 +541,15 @@ def main():
         ncu = ncu_facts()
         alg_gbs = (n * (224 + 534) / (kernel_ms * 1e-3)) / 1e9
         extra["roofline"] = {
-            "kernel": "ltp_solve_tile_kernel", "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
+            "kernel": "ltp_solve_fast_kernel", "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
             "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
-            "traffic": ncu.get("ltp_solve_tile_kernel", {}).get("dram_bytes_per_launch"),
+            "traffic": ncu.get("ltp_solve_fast_kernel", {}).get("dram_bytes_per_launch"),
             "peak_source": "live DFMA probe (csrc/ltp_probe.cu); no FP64 figure in MEASURED_PEAKS.json",
             "algorithmic_flop_per_plan": FLOP_PER_PLAN_7DOF, "kernel_ms": kernel_ms,
             "kernel_share_of_step": kernel_ms / (total_ms / args.steps),
             "work_list_kernel_ms": generic_kernel_ms, "kernels_ms": per_kernel,
             "timing": "CUDA events on the launching stream around each launch, mean of K launches",
-            "ncu_fp64_pipe_pct": ncu.get("ltp_solve_tile_kernel", {}).get("fp64_pipe_pct"),
+            "ncu_fp64_pipe_pct": ncu.get("ltp_solve_fast_kernel", {}).get("fp64_pipe_pct"),
             "hbm": {"achieved": alg_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": alg_gbs / hbm_peak,
                     "algorithmic_bytes_per_plan": 224 + 534, "peak_source": hbm_src}}
 

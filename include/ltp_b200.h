@@ -68,13 +68,12 @@ int ltp_set_solve_mode(ltp_planner* p, int mode);
  * bracketed by a CUDA event pair on the launching stream. ltp_profile_read waits for the
  * recorded launches of one kernel, returns the sum of their durations in ms and their number
  * since the last reset. Off by default; results do not depend on it. */
-#define LTP_PROFILE_SOLVE_TILE 0     /* stage 1 + team meeting + first candidate (every problem) */
-#define LTP_PROFILE_SOLVE_GENERIC 1  /* every-branch kernel (work list, or all problems in GENERIC mode) */
+#define LTP_PROFILE_SOLVE_FAST 0      /* closed-form kernel: stages 1-2 + first candidate (every problem) */
+#define LTP_PROFILE_SOLVE_GENERIC 1   /* every-branch kernel (work list, or all problems in GENERIC mode) */
 #define LTP_PROFILE_SAMPLE_TIME_MAJOR 2
 #define LTP_PROFILE_SAMPLE_ROWS 3
-#define LTP_PROFILE_SOLVE_MODIFIED 4 /* queue B: modified-profile nested solve */
-#define LTP_PROFILE_SOLVE_SECOND 5   /* queue C: second candidate */
-#define LTP_PROFILE_KERNELS 6
+#define LTP_PROFILE_SOLVE_ATTEMPT2 4  /* second candidate for the queued joints */
+#define LTP_PROFILE_KERNELS 5
 int ltp_set_profiling(ltp_planner* p, int on);
 int ltp_profile_read(ltp_planner* p, int kernel, double* ms_sum, int64_t* launches, int reset);
 int ltp_get_dof(const ltp_planner* p);
@@ -136,8 +135,8 @@ typedef struct {
  * stream, or separated by events); for concurrent streams or host threads create one planner
  * per stream -- a planner is a few hundred bytes plus its scratch. (The reference's
  * planTrajectory is re-entrant on one object; the drop-in class is not, for the same reason.)
- * The solve scratch (about n * (4 + 97 * dof) bytes: work list, stage hand-over and the two
- * item queues) is allocated on the first call and whenever n grows,
+ * The solve scratch (about n * (4 + 48 * (dof - 1)) bytes: work list and the queue of the second
+ * cruise-speed candidate) is allocated on the first call and whenever n grows,
  * which must not happen inside a CUDA-graph capture: call ltp_reserve first. */
 int ltp_reserve(ltp_planner* p, int64_t n); /* scratch for solves of up to n problems, now */
 int ltp_solve_batch(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,

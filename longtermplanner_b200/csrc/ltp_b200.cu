@@ -20,7 +20,6 @@
 
 #include "../../include/ltp_b200.h"
 #include "ltp_math.cuh"
-#include "ltp_pipeline.cuh"
 
 namespace {
 
@@ -49,43 +48,39 @@ struct DeviceSolution {  // ltp_solution, by value
 constexpr int kTile = 32;  // problems per CTA
 
 // ------------------------------------------------------------------------------------
-// Stages 1-3 (reference cc:14-55) run as four kernels on one stream:
+// Stages 1-3 (reference cc:14-55) run as two kernels on one stream:
 //
-//   ltp_solve_tile_kernel    every (problem, joint). A CTA is ONE joint of 128 consecutive
-//                            problems; the dof CTAs that share a tile of problems form a team.
-//                            Stage 1 (input check, braking solution, time-optimal phase solve,
-//                            closed form, no quartic tail) -> the team exchanges its end times
-//                            through an L2-resident buffer and meets at a device-scope arrival
-//                            counter -> slowest-joint arg-max -> first cruise-speed candidate ->
-//                            the majority (normal jerk profile) runs its nested phase solve on
-//                            the spot; the joints that have to slow down first are appended to
-//                            queue B, those the first candidate does not settle to queue C.
-//   ltp_solve_modified_kernel  queue B: nested solve with only the modified-profile branch.
-//   ltp_solve_second_kernel    queue C: second candidate + nested solve.
+//   ltp_solve_fast_kernel    every problem. Closed-form work only: the phase solve without
+//                            the quartic tail, the slowest-joint reduction, and attempts 1
+//                            and 2 of the time-scaling search (both closed form). A problem
+//                            in which any joint needs a polynomial root solve is appended to
+//                            a work list and left for the second kernel.
 //   ltp_solve_generic_kernel the work list (or, in generic-only mode, every problem): every
 //                            branch of the reference evaluated in-thread, including the
-//                            Francis-QR root finder. It overwrites whatever the others stored
-//                            for a deferred problem.
+//                            Francis-QR root finder. It overwrites whatever the fast kernel
+//                            stored for a deferred problem.
 //
-// The joint being a function of the block index, the limit set sits in uniform registers /
-// constant-bank operands instead of sixteen vector registers per thread, and a warp runs one
-// branch of the reference's control flow wherever the branches are expensive.
-//
-// The tile kernel is persistent: the grid is a whole number of teams that are all resident at
-// once (occupancy query at planner creation), every team walks the tiles round robin. That is
-// what makes the meeting point safe -- a team only ever waits for CTAs that are running.
-//
-// The split changes no result: every step is the same per-item function the every-branch
-// kernel evaluates (csrc/ltp_pipeline.cuh; tests/host_shadow.cc replays the hand-overs on the
-// CPU), and a deferred problem is recomputed from its inputs.
+// Keeping the root solver out of the first kernel keeps its code small and its warps
+// converged; grouping the root-solve problems keeps the lanes of the second kernel busy.
+// The split changes no result: a deferred problem is recomputed from its inputs by exactly
+// the code that handles it in generic-only mode.
 // ------------------------------------------------------------------------------------
+// Queue of the joints whose first cruise-speed candidate was rejected: filled by the
+// closed-form kernel, drained (regrouped into full warps) by ltp_solve_attempt2_kernel.
+// Structure of arrays, so that both sides access it fully coalesced; the start state travels
+// with the entry (the producer has it in registers, a gather in the consumer costs more).
+struct Attempt2Queue {
+  double *t_req, *q_goal, *q_0, *v_0, *a_0;
+  int2* where;  // (problem, joint)
+};
+
 constexpr int kDeferredMark = 0x7fffffff;  // traj_len of a problem that sits in the work list
 
 struct SolveShared {
   double* t6;            // [dof][32]
   int* len;              // [dof][32]
   int* arrived;          // [32]
-  int* warp_items;       // [dof + 2]   (unused by the every-branch kernel)
+  int* warp_items;       // [dof + 2]   queued joints per warp, then their total and queue base
   unsigned char* flag;   // [dof][32]  bit0 fail, bit1 defer
 };
 
@@ -103,86 +98,37 @@ __device__ __forceinline__ SolveShared carve_shared(unsigned char* raw, int dof)
   return s;
 }
 
-// Device scratch of one solve: counters (the lengths of the work sub-lists, then of the B and C
-// sub-queues, then the arrival counters of the teams), the work list (kStripes sub-lists of q_cap
-// problem indices), the teams' exchange buffers (per team, double-buffered by tile parity: dof x
-// 128 end times and flag bytes -- 1.5 MB in all, it never leaves L2) and the two item queues
-// (structure of arrays).
-//
-// A queue is cut into kStripes sub-queues per joint, each with its own counter: an append is one
-// atomicAdd per warp, and atomics on ONE address retire at ~200 M/s on this part (measured: with
-// one counter per joint the 39 k appends of the modified-profile kernel alone took 0.2 ms). The
-// CTA of problem tile t appends to stripe t % kStripes, so a stripe can receive at most
-// ceil(tiles / kStripes) * 128 items = q_cap, whatever the mix of classes.
-struct ItemQueue {
-  double *t_req, *V, *v0m, *a0m, *dist;
-  int* where;  // problem index, top bit: dir < 0
-};
-
-#ifndef LTP_QUEUE_STRIPES
-#define LTP_QUEUE_STRIPES 32
-#endif
-constexpr int kStripes = LTP_QUEUE_STRIPES;
-constexpr int kMaxTeams = 2048;  // >= resident CTAs of the tile kernel / dof on any part
-constexpr int kCountW = 0, kCountB = kStripes, kCountC = kCountB + LTP_MAX_DOF * kStripes,
-              kCountTeam = kCountC + LTP_MAX_DOF * kStripes, kCounters = kCountTeam + kMaxTeams;
-constexpr size_t kCounterBytes = ((kCounters * sizeof(int) + 255) / 256) * 256;
-
+// Device scratch of one solve: [0] work-list length, [1] attempt-2 queue length, then the
+// work list (n problem indices) and the queue (at most (dof - 1) * n entries).
 struct SolveScratch {
   int* counters;
   int* work_list;
-  double* t_end;         // [team][parity][dof][128]
-  unsigned char* jflag;  // [team][parity][dof][128]
-  ItemQueue queue_b, queue_c;
-  int q_cap;         // items per sub-queue
-  int64_t q_stride;  // items per joint = kStripes * q_cap
+  Attempt2Queue queue;
 };
 
-inline size_t scratch_round(size_t x) { return (x + 255) / 256 * 256; }
-
-constexpr int kJointCta = 128;  // problems per CTA of the stage-1 and scaling kernels
-
-inline int queue_cap(int64_t n) {
-  const int64_t tiles = (n + kJointCta - 1) / kJointCta;
-  return (int)((tiles + kStripes - 1) / kStripes) * kJointCta;
-}
-
 inline size_t solve_scratch_bytes(int dof, int64_t n) {
-  const size_t dn = (size_t)kMaxTeams * 2 * (size_t)dof * kJointCta;
-  const size_t dq = (size_t)dof * (size_t)kStripes * (size_t)queue_cap(n);
-  return kCounterBytes + scratch_round((size_t)kStripes * queue_cap(n) * sizeof(int)) + scratch_round(dn * 8) +
-         scratch_round(dn) +
-         2 * (5 * scratch_round(dq * 8) + scratch_round(dq * 4));
+  const size_t lists = 16 + (((size_t)n * sizeof(int) + 15) / 16) * 16;
+  const size_t cap = (size_t)(dof > 1 ? dof - 1 : 0) * (size_t)n;
+  return lists + cap * (5 * sizeof(double) + sizeof(int2));
 }
 
 inline SolveScratch carve_scratch(void* base, int dof, int64_t n) {
   SolveScratch s;
   unsigned char* b = static_cast<unsigned char*>(base);
-  const size_t dn = (size_t)kMaxTeams * 2 * (size_t)dof * kJointCta;
-  s.q_cap = queue_cap(n);
-  s.q_stride = (int64_t)kStripes * s.q_cap;
-  const size_t dq = (size_t)dof * (size_t)s.q_stride;
-  auto take = [&](size_t bytes) {
-    unsigned char* r = b;
-    b += scratch_round(bytes);
-    return r;
-  };
-  s.counters = reinterpret_cast<int*>(take(kCounterBytes));
-  s.work_list = reinterpret_cast<int*>(take((size_t)s.q_stride * sizeof(int)));
-  s.t_end = reinterpret_cast<double*>(take(dn * 8));
-  s.jflag = take(dn);
-  for (ItemQueue* q : {&s.queue_b, &s.queue_c}) {
-    q->t_req = reinterpret_cast<double*>(take(dq * 8));
-    q->V = reinterpret_cast<double*>(take(dq * 8));
-    q->v0m = reinterpret_cast<double*>(take(dq * 8));
-    q->a0m = reinterpret_cast<double*>(take(dq * 8));
-    q->dist = reinterpret_cast<double*>(take(dq * 8));
-    q->where = reinterpret_cast<int*>(take(dq * 4));
-  }
+  s.counters = reinterpret_cast<int*>(b);
+  s.work_list = reinterpret_cast<int*>(b + 16);
+  const size_t cap = (size_t)(dof > 1 ? dof - 1 : 0) * (size_t)n;
+  double* q = reinterpret_cast<double*>(b + 16 + (((size_t)n * sizeof(int) + 15) / 16) * 16);
+  s.queue.t_req = q;
+  s.queue.q_goal = q + cap;
+  s.queue.q_0 = q + 2 * cap;
+  s.queue.v_0 = q + 3 * cap;
+  s.queue.a_0 = q + 4 * cap;
+  s.queue.where = reinterpret_cast<int2*>(q + 5 * cap);
   return s;
 }
 
-// per-joint stores shared by the kernels: the part known after the time-optimal solve ...
+// per-joint stores shared by both kernels: the part known after the time-optimal solve ...
 __device__ __forceinline__ void store_joint_opt(const DeviceSolution& S, int dof, int jt, int64_t n, int64_t p,
                                                 const double* t_opt, double dir, unsigned char opt_case) {
   const int64_t at = (int64_t)jt * n + p;
@@ -217,18 +163,16 @@ __device__ __forceinline__ void store_joint(const DeviceSolution& S, int dof, in
 
 // cc:718 for one joint, -1 when a switching time is not finite / not representable
 __device__ __forceinline__ int joint_samples(const double* t_sc, double Ts) {
-  return joint_sample_count(t_sc, Ts);
-}
-
-// The same from the end time alone. Switching times are running sums (cumsum7) or all zero, and a
-// running sum that went non-finite stays non-finite, so a finite t[6] implies seven finite times.
-__device__ __forceinline__ int joint_samples_from_end(double t6, double Ts) {
-  return (isfinite(t6) && t6 / Ts <= 2.0e9) ? samples_for(t6, Ts) : -1;
+  bool fin = true;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) fin &= (bool)isfinite(t_sc[k]);
+  return (fin && t_sc[6] / Ts <= 2.0e9) ? samples_for(t_sc[6], Ts) : -1;
 }
 
 // The last of a problem's dof threads to get here reduces the per-joint lengths and writes
 // the per-problem outputs; no CTA-wide barrier, so a warp that is still busy with a slow
-// joint does not hold the others back. (every-branch kernel)
+// joint does not hold the others back. Returns true in that last thread if the problem
+// must be appended to the work list.
 __device__ __forceinline__ bool finish_problem(const SolveShared& sh, const DeviceSolution& S, int dof,
                                                int lane, int jt, int64_t p, int my_len, bool my_defer,
                                                bool reached, int slowest) {
@@ -252,282 +196,198 @@ __device__ __forceinline__ bool finish_problem(const SolveShared& sh, const Devi
   return defer;
 }
 
+// Register budget: the kernel is bound by FP64 dependency latency, so it is compiled for
+// ~28 resident warps per SM (measured on B200, 2^20 Franka problems: 7 joints 1.12 ms at
+// 128 registers / 14 warps, 1.04 ms at 80 / 21, 0.95 ms at 72 / 28; 12 joints 2.10 ms at
+// 128 / 12, 1.51 ms at 80 / 24, 1.52 ms at 56 / 36, 1.88 ms at 40 / 48).
+#ifndef LTP_FAST_WARPS
+#define LTP_FAST_WARPS 28
+#endif
+constexpr int fast_min_blocks(int maxw) {
+  return (LTP_FAST_WARPS + maxw / 2) / maxw > 0 ? (LTP_FAST_WARPS + maxw / 2) / maxw : 1;
+}
+template <int MAXW>
+__global__ void __launch_bounds__(kTile * MAXW, fast_min_blocks(MAXW))
+ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_goal,
+                      const double* __restrict__ q_0, const double* __restrict__ v_0,
+                      const double* __restrict__ a_0, DeviceSolution S, SolveScratch X) {
+  extern __shared__ unsigned char smem_raw[];
+  const int dof = P.dof;
+  const SolveShared sh = carve_shared(smem_raw, dof);
+  int* const work_list = X.work_list;
+  int* const work_count = X.counters;
+  const int lane = threadIdx.x, jt = threadIdx.y;
+  const int64_t p = (int64_t)blockIdx.x * kTile + lane;
+  const bool valid = p < n;
+  const JointLimits L = P.lim[jt];
+  const double Ts = P.ts;
+  const int64_t at = (int64_t)jt * n + p;
+
+  double qg = 0, q0 = 0, v0 = 0, a0 = 0;
+  if (valid) {
+    qg = q_goal[at]; q0 = q_0[at]; v0 = v_0[at]; a0 = a_0[at];
+  }
+  if (jt == 0) sh.arrived[lane] = 0;
+  // stage 1 (cc:14-30)
+  const bool in_ok = check_joint_input(L, q0, v0, a0);
+  const Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0);
+  double t_opt[7];
+  zero7(t_opt);
+  unsigned char mod = 0, opt_case = 255;
+  const int st1 = ost_body_t<false>(L, Ts, pro, qg, q0, L.v_max, t_opt, mod, opt_case);
+  sh.t6[jt * kTile + lane] = t_opt[6];
+  sh.flag[jt * kTile + lane] = (unsigned char)((!(in_ok && st1 != OST_FAIL) ? 1 : 0) | (st1 == OST_DEFER ? 2 : 0));
+  __syncthreads();
+  // stage 2 (cc:31-39): strict '>' so the lowest joint index wins ties, NaN never wins
+  double t_req = -1;
+  int slowest = -1;
+  unsigned char any = 0;
+  for (int i = 0; i < dof; ++i) {
+    any |= sh.flag[i * kTile + lane];
+    const double ti = sh.t6[i * kTile + lane];
+    if (ti > t_req) {
+      t_req = ti;
+      slowest = i;
+    }
+  }
+  // a joint that needs the quartic tail has no t_opt yet: the whole problem is deferred
+  const bool defer1 = (any & 2) != 0;
+  const bool reached = !(any & 1) && slowest != -1;
+  // stage 3 (cc:42-55), closed-form attempts only. Attempt 1 runs here; the joints it does
+  // not settle (about a third) are queued for ltp_solve_attempt2_kernel, which runs attempt 2
+  // on full warps of such joints ("grouped by case").
+  double t_sc[7];
+  zero7(t_sc);
+  double v_drive = L.v_max;
+  unsigned char ts_case = 255, final_case = 255;
+  bool my_defer = false, need2 = false;
+  if (reached && !defer1) {
+    if (jt == slowest) {
+      ts_case = 0;
+      final_case = opt_case;
+    } else {
+      const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
+      const int c = time_scaling_attempt1(L, Ts, pro, I, t_sc, v_drive, mod, final_case);
+      my_defer = (c == 0);
+      need2 = (c == -1) && valid;
+      ts_case = (unsigned char)c;
+      if (c == 9) final_case = opt_case;
+    }
+    if (!need2) {
+      double m = t_sc[0];
+#pragma unroll
+      for (int k = 1; k < 7; ++k)
+        if (m < t_sc[k]) m = t_sc[k];
+      if (m <= 0.0) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t_sc[k] = t_opt[k];
+      }
+    }
+  }
+  // queue slot = base of this CTA (one atomic per CTA) + joints queued by the warps before
+  // mine + those of the lanes before mine
+  const unsigned need_mask = __ballot_sync(0xffffffffu, need2);
+  if (lane == 0) sh.warp_items[jt] = __popc(need_mask);
+  __syncthreads();
+  int before = 0, total = 0;
+  for (int w = 0; w < dof; ++w) {
+    const int c = sh.warp_items[w];
+    before += (w < jt) ? c : 0;
+    total += c;
+  }
+  if (total > 0) {  // uniform over the CTA
+    if (jt == 0 && lane == 0) sh.warp_items[dof + 1] = atomicAdd(X.counters + 1, total);
+    __syncthreads();
+    if (need2) {
+      const int e = sh.warp_items[dof + 1] + before + __popc(need_mask & ((1u << lane) - 1u));
+      X.queue.t_req[e] = t_req;
+      X.queue.q_goal[e] = qg;
+      X.queue.q_0[e] = q0;
+      X.queue.v_0[e] = v0;
+      X.queue.a_0[e] = a0;
+      X.queue.where[e] = make_int2((int)p, jt);
+    }
+  }
+  if (!valid) return;
+  store_joint_opt(S, dof, jt, n, p, t_opt, pro.dir, opt_case);
+  // a queued joint contributes length 0 here; its length arrives by atomicMax later
+  const int my_len = (reached && !defer1 && !my_defer && !need2) ? joint_samples(t_sc, Ts) : 0;
+  if (finish_problem(sh, S, dof, lane, jt, p, my_len, my_defer, reached, slowest)) {
+    const int slot = atomicAdd(work_count, 1);
+    work_list[slot] = (int)p;
+  }
+  if (!need2) store_joint_scaled(S, dof, jt, n, p, t_sc, v_drive, mod, ts_case, final_case);
+}
+
+// Attempt 2 of the cruise-speed search (reference cc:408-446) for the queued joints: one
+// thread per entry, consecutive entries in consecutive lanes, so every lane of every warp
+// has the same work whatever the mix of joints that needed it. The start state comes with the
+// entry and the prologue is recomputed; results go straight to the solution arrays, the
+// sample count joins the problem's by atomicMax. A joint that attempt 2 does not settle
+// either sends its problem to the work list of the generic kernel (once per problem: the
+// exchange on traj_len elects the sender).
 #ifndef LTP_TM_BUILD_EARLY_EXIT
 #define LTP_TM_BUILD_EARLY_EXIT 1
 #endif
-
-// Register budgets (ptxas -v, sm_100a): stage 1 needs 64 registers unconstrained and spills
-// 56 bytes at 48; the scaling kernel is larger.
-#ifndef LTP_TILE_MINB
-#define LTP_TILE_MINB 8
+#ifndef LTP_A2_MINB
+#define LTP_A2_MINB 2
 #endif
-#ifndef LTP_SCALE_MINB
-#define LTP_SCALE_MINB 8
-#endif
-#ifndef LTP_QUEUE_CTAS_PER_SM
-#define LTP_QUEUE_CTAS_PER_SM 8
-#endif
-
-// The work list is striped like the queues (by problem tile): the exchange on traj_len elects one
-// sender per problem, so a sub-list receives at most the problems behind its stripe (q_cap).
-__device__ __forceinline__ void defer_problem(const DeviceSolution& S, const SolveScratch& X, int64_t p) {
-  if (atomicExch(S.traj_len + p, kDeferredMark) != kDeferredMark) {
-    const int st = (int)((p / kJointCta) % kStripes);
-    const int slot = atomicAdd(X.counters + kCountW + st, 1);
-    X.work_list[(int64_t)st * X.q_cap + slot] = (int)p;
-  }
-}
-
-// a settled joint: results to the solution arrays, the sample count joins its problem's
-__device__ __forceinline__ void settle_joint(const DeviceSolution& S, const SolveScratch& X, int dof, int jt,
-                                             int64_t n, int64_t p, double Ts, const JointResult& R) {
-  const int len = joint_sample_count(R.t, Ts);
-  if (len < 0) return defer_problem(S, X, p);
-  store_joint_scaled(S, dof, jt, n, p, R.t, R.v_drive, R.mod, R.ts_case, R.final_case);
-  atomicMax(S.traj_len + p, len);
-}
-
-// Append the item of every lane with want != 0 to the sub-queue of `Q` that starts at sub_base
-// (one atomic per warp; the lanes of a warp share joint and stripe, so its items are contiguous). The problem index travels in
-// the low 31 bits of `where`, dir < 0 in the top bit.
-__device__ __forceinline__ void queue_push(const ItemQueue& Q, int* counter, int64_t sub_base, bool want,
-                                           const ScaleItem& it, int64_t p) {
-  const unsigned m = __ballot_sync(0xffffffffu, want);
-  if (!m) return;
-  const int lane = threadIdx.x & 31;
-  int base = 0;
-  if (lane == __ffs(m) - 1) base = atomicAdd(counter, __popc(m));
-  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-  if (!want) return;
-  const int64_t e = sub_base + base + __popc(m & ((1u << lane) - 1u));
-  Q.t_req[e] = it.t_req;
-  Q.V[e] = it.V;
-  Q.v0m[e] = it.v0m;
-  Q.a0m[e] = it.a0m;
-  Q.dist[e] = it.dist;
-  Q.where[e] = (int)p | ((it.meta & 0x100) ? (int)0x80000000u : 0);
-}
-
-__device__ __forceinline__ ScaleItem queue_load(const ItemQueue& Q, int64_t e, int64_t& p) {
-  ScaleItem it;
-  const int w = Q.where[e];
-  it.t_req = Q.t_req[e];
-  it.V = Q.V[e];
-  it.v0m = Q.v0m[e];
-  it.a0m = Q.a0m[e];
-  it.dist = Q.dist[e];
-  it.meta = w < 0 ? 0x100 : 0;
-  p = (int64_t)(w & 0x7fffffff);
-  return it;
-}
-
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// Stages 1-3 (cc:14-55) for one joint of 128 consecutive problems at a time, one thread per
-// problem. blockIdx = team * dof + joint; team t takes the tiles t, t + teams, t + 2 teams, ...
-// Per tile:
-//  1. stage 1 for the thread's (problem, joint); the end time and the flags go to the team's
-//     exchange buffer (parity of the tile count: a member that is already a tile ahead writes
-//     the other half);
-//  2. the team meets: every CTA adds one to the team's arrival counter and waits until all dof
-//     members have done so for this tile (one thread polls, the rest wait at the barrier);
-//  3. arg-max over the dof end times (strict '>': lowest joint index wins ties, NaN never wins),
-//     then what the joint needs -- nothing more (it is the slowest one: its time-optimal times,
-//     still in registers, are the result), the rare brake-only exit (settled on the spot), or
-//     the cruise-speed search: first candidate (closed form, one sqrt) and the cc:119 test at
-//     that speed. The majority (normal jerk profile, ~80 % of the searching joints) runs its
-//     nested phase solve right here with only that branch compiled in; a joint that has to slow
-//     down first is appended to queue B, one the first candidate does not settle to queue C.
-// Every (problem, joint) record is written exactly once, by the thread that settles it.
-__global__ void __launch_bounds__(kJointCta, LTP_TILE_MINB)
-ltp_solve_tile_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_goal,
-                      const double* __restrict__ q_0, const double* __restrict__ v_0,
-                      const double* __restrict__ a_0, DeviceSolution S, SolveScratch X) {
+__global__ void __launch_bounds__(256, LTP_A2_MINB)
+ltp_solve_attempt2_kernel(const __grid_constant__ PlannerParams P, int64_t n, DeviceSolution S, SolveScratch X) {
   const int dof = P.dof;
-  const int team = blockIdx.x / (unsigned)dof;
-  const int jt = (int)(blockIdx.x - (unsigned)team * (unsigned)dof);
-  const int teams = gridDim.x / (unsigned)dof;
-  const int tid = threadIdx.x;
-  const JointLimits& L = P.lim[jt];
   const double Ts = P.ts;
-  const int64_t tiles = (n + kJointCta - 1) / kJointCta;
-  int* const arrive = X.counters + kCountTeam + team;
-  int round = 0;
-  for (int64_t tile = team; tile < tiles; tile += teams, ++round) {
-    const int64_t p = tile * kJointCta + tid;
-    const bool valid = p < n;
-    const int64_t at = (int64_t)jt * n + p;
-    double qg = 0, q0 = 0, v0 = 0, a0 = 0;
-    if (valid) {
-      qg = q_goal[at]; q0 = q_0[at]; v0 = v_0[at]; a0 = a_0[at];
+  const int count = X.counters[1];
+  const int step = gridDim.x * blockDim.x;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= count) return;
+  // software pipeline: the next entry's six loads are in flight while this one is evaluated
+  // (the kernel was waiting on memory for half of its cycles, four warps per scheduler)
+  int2 where = X.queue.where[e];
+  double t_req = X.queue.t_req[e], qg = X.queue.q_goal[e], q0 = X.queue.q_0[e], v0 = X.queue.v_0[e],
+         a0 = X.queue.a_0[e];
+  while (true) {
+    const int en = e + step;
+    const bool more = en < count;
+    int2 where_n = where;
+    double t_req_n = 0, qg_n = 0, q0_n = 0, v0_n = 0, a0_n = 0;
+    if (more) {
+      where_n = X.queue.where[en];
+      t_req_n = X.queue.t_req[en]; qg_n = X.queue.q_goal[en]; q0_n = X.queue.q_0[en];
+      v0_n = X.queue.v_0[en]; a0_n = X.queue.a_0[en];
     }
-    Stage1Out o;
-    stage1_joint(L, Ts, qg, q0, v0, a0, o);
-    const size_t half = ((size_t)team * 2 + (round & 1)) * (size_t)dof * kJointCta;
-    __stcg(X.t_end + half + (size_t)jt * kJointCta + tid, o.t_opt[6]);
-    X.jflag[half + (size_t)jt * kJointCta + tid] = valid ? o.flags : (unsigned char)0;
-    if (valid) {
-      store_joint_opt(S, dof, jt, n, p, o.t_opt, o.dir, o.opt_case);
-      if (jt == 0) S.traj_len[p] = 0;
-    }
-    // ---- the team meets
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      atomicAdd(arrive, 1);
-      const int want = dof * (round + 1);
-      // (a member that never arrives would mean the grid is not fully resident -- impossible by
-      // construction; fail loudly after a few seconds rather than hang the device)
-      unsigned spins = 0;
-      while (ld_acquire(arrive) < want) {
-        __nanosleep(40);
-        if (++spins > (1u << 25)) __trap();
-      }
-    }
-    __syncthreads();
-    bool to_b = false, to_c = false;
-    ScaleItem it;
-    it.t_req = it.V = it.v0m = it.a0m = it.dist = 0.0;
-    it.meta = 0;
-    if (valid) {
-      double t_req = -1;
-      int slowest = -1;
-      unsigned any = 0;
-#pragma unroll 8
-      for (int i = 0; i < dof; ++i) {
-        const unsigned f = __ldcg(X.jflag + half + (size_t)i * kJointCta + tid);
-        const double ti = __ldcg(X.t_end + half + (size_t)i * kJointCta + tid);
-        any |= f;
-        if (ti > t_req) {
-          t_req = ti;
-          slowest = i;
-        }
-      }
-      const bool reached = !(any & JF_FAIL) && slowest != -1;
-      if (jt == 0) {
-        S.slowest[p] = slowest;
-        S.reached[p] = (uint8_t)reached;
-      }
-      JointResult R;
-      R.v_drive = L.v_max;
-      R.mod = o.mod;
-      bool settled = false;
-      if (any & JF_DEFER) {  // a joint without time-optimal times yet: the whole problem is deferred
-        if (jt == 0) defer_problem(S, X, p);
-      } else if (!reached) {  // aborted before time scaling (cc:15,29,39): the record says so
-        zero7(R.t);
-        R.ts_case = 255;
-        R.final_case = 255;
-        store_joint_scaled(S, dof, jt, n, p, R.t, R.v_drive, R.mod, R.ts_case, R.final_case);
-      } else if (jt == slowest) {  // cc:44-46, then the cc:50-55 fallback (t_scaled stays zero)
+    const int64_t p = where.x;
+    const int jt = where.y;
+    // (a problem that is already on its way to the generic kernel is not skipped: what is
+    // stored here is overwritten there, and a look at traj_len first costs a second trip to
+    // memory per entry)
+    const JointLimits L = P.lim[jt];
+    const Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0);
+    const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
+    double t[7];
+    zero7(t);
+    double v_drive = L.v_max;
+    unsigned char mod = 0, final_case = 255;
+    const int c = time_scaling_attempt2(L, Ts, pro, I, t, v_drive, mod, final_case);
+    double m = t[0];
 #pragma unroll
-        for (int k = 0; k < 7; ++k) R.t[k] = o.t_opt[k];
-        R.ts_case = 0;
-        R.final_case = o.opt_case;
-        settled = true;
-      } else if (o.flags & JF_BRAKE_ONLY) {
-        const Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0);
-        if (stage3_brake_only(L, Ts, pro, qg, q0, v0, a0, t_req, o.t_opt, o.opt_case, R) == S3_SETTLED) settled = true;
-        else defer_problem(S, X, p);
-      } else if (stage3_classify(L, qg, q0, v0, a0, o.dir, t_req, it) == S3_QUEUE_A) {
-        const int r = scale_attempt1_class_a(L, Ts, it, R);
-        if (r == SA_ACCEPT) settled = true;
-        else if (r == SA_DEFER) defer_problem(S, X, p);
-        else to_c = true;
-      } else {
-        // an unusable first candidate skips the attempt (cc:398): straight to the second one
-        const bool v_ok = !isnan(it.V) && it.V > 0;
-        to_b = v_ok;
-        to_c = !v_ok;
+    for (int k = 1; k < 7; ++k)
+      if (m < t[k]) m = t[k];
+    // an accepted solve with no positive time falls back to the time-optimal times (cc:50-55),
+    // which are not at hand here: that (degenerate) problem goes to the generic kernel too
+    const int len = (c == 0 || m <= 0.0) ? -1 : joint_samples(t, Ts);
+    if (len < 0) {
+      if (atomicExch(S.traj_len + p, kDeferredMark) != kDeferredMark) {
+        const int slot = atomicAdd(X.counters, 1);
+        X.work_list[slot] = (int)p;
       }
-      if (settled) settle_joint(S, X, dof, jt, n, p, Ts, R);
+    } else {
+      store_joint_scaled(S, dof, jt, n, p, t, v_drive, mod, (unsigned char)c, final_case);
+      atomicMax(S.traj_len + p, len);
     }
-    const int sub = jt * kStripes + (int)(tile % kStripes);
-    const int64_t sub_base = (int64_t)sub * X.q_cap;
-    queue_push(X.queue_b, X.counters + kCountB + sub, sub_base, to_b, it, p);
-    queue_push(X.queue_c, X.counters + kCountC + sub, sub_base, to_c, it, p);
-  }
-}
-
-// Queue B: the first candidate's nested solve for the joints that have to slow down first
-// (modified jerk profile, cc:119-122), 32 of them per warp. The queue lengths never leave the
-// device, so the grid is fixed (a few CTAs per SM) and the CTAs walk the concatenation of the
-// per-joint queues in tiles of 128 items, round robin; the joint is the counter of the outer
-// loop, i.e. uniform, and the limits stay in uniform registers like in the other kernels.
-__global__ void __launch_bounds__(kJointCta, LTP_SCALE_MINB)
-ltp_solve_modified_kernel(const __grid_constant__ PlannerParams P, int64_t n, DeviceSolution S, SolveScratch X) {
-  const int dof = P.dof;
-  const double Ts = P.ts;
-  // the sub-queue lengths, fetched once (walking them in global memory is a chain of dof * kStripes
-  // dependent loads per CTA)
-  __shared__ int s_count[LTP_MAX_DOF * kStripes];
-  for (int i = threadIdx.x; i < dof * kStripes; i += kJointCta) s_count[i] = X.counters[kCountB + i];
-  __syncthreads();
-  int w = blockIdx.x;  // tile of the current sub-queue this CTA takes next
-  for (int jt = 0; jt < dof; ++jt) {
-    const JointLimits& L = P.lim[jt];
-    for (int st = 0; st < kStripes; ++st) {
-      const int sub = jt * kStripes + st;
-      const int count = s_count[sub];
-      const int tiles = (count + kJointCta - 1) / kJointCta;
-      const int64_t sub_base = (int64_t)sub * X.q_cap;
-      for (; w < tiles; w += gridDim.x) {
-        const int k = w * kJointCta + threadIdx.x;
-        bool to_c = false;
-        int64_t p = 0;
-        ScaleItem it;
-        it.t_req = it.V = it.v0m = it.a0m = it.dist = 0.0;
-        it.meta = 0;
-        if (k < count) {
-          it = queue_load(X.queue_b, sub_base + k, p);
-          JointResult R;
-          const int r = scale_attempt1_class_b(L, Ts, it, R);
-          if (r == SA_ACCEPT) settle_joint(S, X, dof, jt, n, p, Ts, R);
-          else if (r == SA_DEFER) defer_problem(S, X, p);
-          else to_c = true;
-        }
-        // same stripe: what a stripe can receive is bounded by the problems behind it (q_cap)
-        queue_push(X.queue_c, X.counters + kCountC + sub, sub_base, to_c, it, p);
-      }
-      w -= tiles;
-    }
-  }
-}
-
-// Queue C: the second candidate (cc:408-446) and its nested solve for what the first one did not
-// settle. A joint that is still open needs a polynomial root: its problem goes to the work list.
-__global__ void __launch_bounds__(kJointCta, LTP_SCALE_MINB)
-ltp_solve_second_kernel(const __grid_constant__ PlannerParams P, int64_t n, DeviceSolution S, SolveScratch X) {
-  const int dof = P.dof;
-  const double Ts = P.ts;
-  __shared__ int s_count[LTP_MAX_DOF * kStripes];
-  for (int i = threadIdx.x; i < dof * kStripes; i += kJointCta) s_count[i] = X.counters[kCountC + i];
-  __syncthreads();
-  int w = blockIdx.x;
-  for (int jt = 0; jt < dof; ++jt) {
-    const JointLimits& L = P.lim[jt];
-    for (int st = 0; st < kStripes; ++st) {
-      const int sub = jt * kStripes + st;
-      const int count = s_count[sub];
-      const int tiles = (count + kJointCta - 1) / kJointCta;
-      const int64_t sub_base = (int64_t)sub * X.q_cap;
-      for (; w < tiles; w += gridDim.x) {
-        const int k = w * kJointCta + threadIdx.x;
-        if (k < count) {
-          int64_t p;
-          const ScaleItem it = queue_load(X.queue_c, sub_base + k, p);
-          JointResult R;
-          const int r = scale_attempt2(L, Ts, it, R);
-          if (r == SA_ACCEPT) settle_joint(S, X, dof, jt, n, p, Ts, R);
-          else defer_problem(S, X, p);
-        }
-      }
-      w -= tiles;
-    }
+    if (!more) break;
+    e = en;
+    where = where_n;
+    t_req = t_req_n; qg = qg_n; q0 = q0_n; v0 = v0_n; a0 = a0_n;
   }
 }
 
@@ -538,25 +398,18 @@ __global__ void __launch_bounds__(kTile * MAXW)
 ltp_solve_generic_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_goal,
                          const double* __restrict__ q_0, const double* __restrict__ v_0,
                          const double* __restrict__ a_0, DeviceSolution S, const int* __restrict__ work_list,
-                         const int* __restrict__ work_count, int q_cap) {
+                         const int* __restrict__ work_count) {
   extern __shared__ unsigned char smem_raw[];
   const int dof = P.dof;
   const SolveShared sh = carve_shared(smem_raw, dof);
   const int lane = threadIdx.x, jt = threadIdx.y;
   const JointLimits L = P.lim[jt];
   const double Ts = P.ts;
-  // tiles of 32 problems, grid-stride: over all n problems, or over the concatenation of the work
-  // sub-lists (each rounded up to whole tiles)
-  const int lists = work_list ? kStripes : 1;
-  int64_t tile = blockIdx.x;
-  for (int st = 0; st < lists; ++st) {
-  const int64_t count = work_list ? (int64_t)work_count[st] : n;
-  const int* list = work_list ? work_list + (int64_t)st * q_cap : nullptr;
-  const int64_t tiles_here = (count + kTile - 1) / kTile;
-  for (; tile < tiles_here; tile += gridDim.x) {
+  const int64_t count = work_list ? (int64_t)*work_count : n;
+  for (int64_t tile = blockIdx.x; tile * kTile < count; tile += gridDim.x) {
     const int64_t w = tile * kTile + lane;
     const bool valid = w < count;
-    const int64_t p = valid ? (list ? (int64_t)list[w] : w) : 0;
+    const int64_t p = valid ? (work_list ? (int64_t)work_list[w] : w) : 0;
     const int64_t at = (int64_t)jt * n + p;
     double qg = 0, q0 = 0, v0 = 0, a0 = 0;
     if (valid) {
@@ -615,8 +468,6 @@ ltp_solve_generic_kernel(const __grid_constant__ PlannerParams P, int64_t n, con
       store_joint(S, dof, jt, n, p, t_sc, t_opt, pro.dir, v_drive, mod, opt_case, ts_case, final_case);
     }
     __syncthreads();  // shared arrays are reused by the next tile
-  }
-  tile -= tiles_here;
   }
 }
 
@@ -1276,7 +1127,6 @@ struct ltp_planner {
   int d_work_dof;
   int solve_mode;  // LTP_SOLVE_AUTO / LTP_SOLVE_GENERIC
   int sm_count;
-  int tile_ctas_per_sm;  // resident CTAs of ltp_solve_tile_kernel per SM (occupancy query)
   // optional per-kernel timing (ltp_set_profiling): CUDA events recorded on the launching
   // stream directly around the hot kernels, read back by ltp_profile_read
   bool profiling;
@@ -1464,7 +1314,6 @@ int ltp_create(ltp_planner** out, int device, int dof, double t_sample, const do
   p->d_work_dof = 0;
   p->solve_mode = LTP_SOLVE_AUTO;
   p->sm_count = 148;
-  p->tile_ctas_per_sm = 1;
   p->profiling = false;
   std::memset(p->timed, 0, sizeof p->timed);
   for (int i = 0; i < 2; ++i) {
@@ -1486,10 +1335,6 @@ int ltp_create(ltp_planner** out, int device, int dof, double t_sample, const do
     cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaStreamCreate"); }
     cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ltp_solve_tile_kernel, kJointCta, 0);
-    if (e != cudaSuccess || per_sm < 1) { cudaStreamDestroy(p->stream); delete p; return cuda_fail(e, "occupancy(ltp_solve_tile_kernel)"); }
-    p->tile_ctas_per_sm = per_sm;
   }
   *out = p;
   return LTP_OK;
@@ -1619,12 +1464,10 @@ int ltp_time_scaling_batch(ltp_planner* p, int64_t n, const double* q_goal, cons
 
 // launches of stages 1-3 on `st`. work: device buffer of n + 1 ints ([0] = count), only
 // touched in LTP_SOLVE_AUTO mode.
-// grid_share: how many solves of this planner may be in flight on different streams (the host
-// pipeline runs two): each gets that fraction of the resident-CTA capacity for its teams, so
-// that all teams of all of them are resident together whatever order the CTAs are dispatched in.
+// launches of stages 1-3 on `st`. work: device buffer of n + 1 ints ([0] = count), only
+// touched in LTP_SOLVE_AUTO mode.
 static int solve_launch(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0, const double* v_0,
-                        const double* a_0, const ltp_solution* sol, void* scratch, cudaStream_t st,
-                        int grid_share = 1) {
+                        const double* a_0, const ltp_solution* sol, void* scratch, cudaStream_t st) {
   const int dof = p->params.dof;
   const dim3 block(kTile, dof);
   const unsigned tiles = (unsigned)((n + kTile - 1) / kTile);
@@ -1641,44 +1484,43 @@ static int solve_launch(ltp_planner* p, int64_t n, const double* q_goal, const d
     else KERNEL<32><<<GRID, block, smem, st>>>(__VA_ARGS__);                                \
     p->launches++;                                                                          \
   } while (0)
+  // the closed-form kernel is compiled for the exact CTA size of the common arm sizes so that
+  // its register budget is the largest that still fits the intended number of CTAs per SM
+#define LTP_DISPATCH_FAST(GRID, ...)                                                        \
+  do {                                                                                      \
+    if (dof == 6) ltp_solve_fast_kernel<6><<<GRID, block, smem, st>>>(__VA_ARGS__);         \
+    else if (dof == 7) ltp_solve_fast_kernel<7><<<GRID, block, smem, st>>>(__VA_ARGS__);    \
+    else if (dof == 12) ltp_solve_fast_kernel<12><<<GRID, block, smem, st>>>(__VA_ARGS__);  \
+    else { LTP_DISPATCH_W(ltp_solve_fast_kernel, GRID, __VA_ARGS__); break; }               \
+    p->launches++;                                                                          \
+  } while (0)
   // a single tile is one CTA whichever way it is run: the every-branch kernel alone (one launch
   // instead of a memset and three) gives the same results sooner
   if (p->solve_mode == LTP_SOLVE_GENERIC || n <= kTile) {
     ProfScope ps(p, LTP_PROFILE_SOLVE_GENERIC, st);
     LTP_DISPATCH_W(ltp_solve_generic_kernel, tiles, p->params, n, q_goal, q_0, v_0, a_0, ds,
-                   (const int*)nullptr, (const int*)nullptr, 0);
+                   (const int*)nullptr, (const int*)nullptr);
   } else {
-    LTP_CUDA(cudaMemsetAsync(X.counters, 0, kCounterBytes, st));
-    const int64_t jtiles = (n + kJointCta - 1) / kJointCta * dof;  // one CTA per (tile of problems, joint)
+    LTP_CUDA(cudaMemsetAsync(X.counters, 0, 2 * sizeof(int), st));
     {
-      // whole teams only, all of them resident at once (the teams meet at a spin-wait)
-      int64_t teams = (int64_t)p->sm_count * p->tile_ctas_per_sm / grid_share / dof;
-      if (teams > kMaxTeams) teams = kMaxTeams;
-      if (teams > jtiles / dof) teams = jtiles / dof;
-      if (teams < 1) return LTP_ERR_ARG;
-      ProfScope ps(p, LTP_PROFILE_SOLVE_TILE, st);
-      ltp_solve_tile_kernel<<<(unsigned)(teams * dof), kJointCta, 0, st>>>(p->params, n, q_goal, q_0, v_0, a_0, ds, X);
+      ProfScope ps(p, LTP_PROFILE_SOLVE_FAST, st);
+      LTP_DISPATCH_FAST(tiles, p->params, n, q_goal, q_0, v_0, a_0, ds, X);
+    }
+    // the queue and the work list are drained by fixed-size grid-stride launches: their
+    // lengths never leave the device
+    if (dof > 1) {
+      ProfScope ps(p, LTP_PROFILE_SOLVE_ATTEMPT2, st);
+      const int64_t want = ((int64_t)(dof - 1) * n + 255) / 256;
+      const int64_t cap = (int64_t)p->sm_count * 16;
+      ltp_solve_attempt2_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(p->params, n, ds, X);
       p->launches++;
     }
-    if (dof > 1) {  // the two queues (a single joint is its problem's slowest one)
-      const int64_t cap = (int64_t)p->sm_count * LTP_QUEUE_CTAS_PER_SM;
-      const unsigned gq = (unsigned)(jtiles < cap ? jtiles : cap);
-      {
-        ProfScope ps(p, LTP_PROFILE_SOLVE_MODIFIED, st);
-        ltp_solve_modified_kernel<<<gq, kJointCta, 0, st>>>(p->params, n, ds, X);
-      }
-      {
-        ProfScope ps(p, LTP_PROFILE_SOLVE_SECOND, st);
-        ltp_solve_second_kernel<<<gq, kJointCta, 0, st>>>(p->params, n, ds, X);
-      }
-      p->launches += 2;
-    }
-    // the work list is drained by a fixed-size grid-stride launch: its length never leaves the device
     const unsigned g2 = tiles < (unsigned)(p->sm_count * 4) ? tiles : (unsigned)(p->sm_count * 4);
     ProfScope ps(p, LTP_PROFILE_SOLVE_GENERIC, st);
     LTP_DISPATCH_W(ltp_solve_generic_kernel, g2, p->params, n, q_goal, q_0, v_0, a_0, ds,
-                   (const int*)X.work_list, (const int*)(X.counters + kCountW), X.q_cap);
+                   (const int*)X.work_list, (const int*)X.counters);
   }
+#undef LTP_DISPATCH_FAST
 #undef LTP_DISPATCH_W
   LTP_CUDA(cudaGetLastError());
   return LTP_OK;
@@ -1873,7 +1715,7 @@ int ltp_solve_host(ltp_planner* p, int64_t n, const double* q_goal, const double
     for (int i = 0; i < 4; ++i)
       LTP_CUDA(cudaMemcpy2DAsync(d_in[s][i], (size_t)c * 8, h_in[i] + p0, (size_t)n * 8, (size_t)c * 8, dof,
                                  cudaMemcpyHostToDevice, st));
-    int rc = solve_launch(p, c, d_in[s][0], d_in[s][1], d_in[s][2], d_in[s][3], &d, d_work[s], st, slots);
+    int rc = solve_launch(p, c, d_in[s][0], d_in[s][1], d_in[s][2], d_in[s][3], &d, d_work[s], st);
     if (rc != LTP_OK) return rc;
 #define LTP_OUT2D(FIELD, ROWS, ELEM)                                                                   \
   LTP_CUDA(cudaMemcpy2DAsync(hs->FIELD + p0, (size_t)n * (ELEM), d.FIELD, (size_t)c * (ELEM),           \
@@ -1972,7 +1814,7 @@ int ltp_plan_stream(ltp_planner* p, int64_t n, const double* q_goal, const doubl
     for (int i = 0; i < 4; ++i)
       LTP_CUDA(cudaMemcpy2DAsync(d_in[s][i], (size_t)c * 8, src[i] + p0, (size_t)n * 8, (size_t)c * 8, dof,
                                  cudaMemcpyDeviceToDevice, st));
-    int rc = solve_launch(p, c, d_in[s][0], d_in[s][1], d_in[s][2], d_in[s][3], &ds[s], d_work[s], st, slots);
+    int rc = solve_launch(p, c, d_in[s][0], d_in[s][1], d_in[s][2], d_in[s][3], &ds[s], d_work[s], st);
     if (rc != LTP_OK) return rc;
     rc = sample_tm_launch(p, c, d_in[s][1], d_in[s][2], d_in[s][3], &ds[s], horizon, capacity, d_traj[s][0],
                           d_traj[s][1], d_traj[s][2], d_traj[s][3], d_succ[s],

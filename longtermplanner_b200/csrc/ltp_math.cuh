@@ -89,15 +89,15 @@ LTP_HD double div_by(double x, double d, double rd) {
   const double r = fma(-q, d, x);
   const double f = fma(r, rd, q);
   // biased exponent of the result in [64, 1982] (|f| in ~[1e-289, 1e289]): integer test on
-  // the high word, like the one the compiler's own division uses
+  // the exponent field of the high word, in place (mask, subtract, one unsigned compare)
 #ifdef __CUDA_ARCH__
-  const unsigned e = ((unsigned)__double2hiint(f) << 1) >> 21;
+  const unsigned hi = (unsigned)__double2hiint(f);
 #else
   unsigned long long bits;
   memcpy(&bits, &f, 8);
-  const unsigned e = (unsigned)((bits >> 52) & 0x7ff);
+  const unsigned hi = (unsigned)(bits >> 32);
 #endif
-  if (e - 64u > 1918u) return div_slow(x, d);
+  if (((hi & 0x7ff00000u) - (64u << 20)) > (1918u << 20)) return div_slow(x, d);
   return f;
 }
 LTP_HD double div3(double x) { return div_by(x, 3.0, 1.0 / 3.0); }
@@ -109,7 +109,11 @@ LTP_HD void derive_limits(JointLimits& L) {
   L.a_over_j = L.a_max / L.j_max;
 }
 
-LTP_HD double sgn(double x) { return (double)((0.0 < x) - (x < 0.0)); }  // h:54-56
+// h:54-56: (double)((0 < x) - (x < 0)), written as two selects (no int -> double conversion);
+// +1, -1, and +0.0 for zeros and NaN, like the reference's expression
+LTP_HD double sgn(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0); }
+// -sign(x) of cc:660-667: the reference negates the INT, so a zero stays +0.0
+LTP_HD double neg_sgn(double x) { return x > 0.0 ? -1.0 : (x < 0.0 ? 1.0 : 0.0); }
 
 // ------------------------------------------------------------------------------------
 // cc:650-701. Returns the signed stop displacement; T[0..2] are the three durations.
@@ -117,13 +121,11 @@ LTP_HD double sgn(double x) { return (double)((0.0 < x) - (x < 0.0)); }  // h:54
 LTP_HD double brake_profile(const JointLimits& L, double Ts, double v_0, double a_0,
                             double& T0, double& T1, double& T2, double& dir) {
   const double A = L.a_max, J = L.j_max;
-  if (v_0 * a_0 > 0) {
-    dir = -sgn(v_0);
-  } else if (fabs(v_0) > div_by(1.0 / 2.0 * sq(a_0), J, L.r_j)) {
-    dir = -sgn(v_0);
-  } else {
-    dir = -sgn(a_0);
-  }
+  // cc:658-664 without the three-way branch: both tests are evaluated, one select picks the
+  // operand whose sign decides (same values; a warp does not split three ways here)
+  const bool same_sign = v_0 * a_0 > 0;
+  const bool fast_enough = fabs(v_0) > div_by(1.0 / 2.0 * sq(a_0), J, L.r_j);
+  dir = neg_sgn((same_sign | fast_enough) ? v_0 : a_0);
   if (dir < 0) {
     a_0 = -a_0;
     v_0 = -v_0;
@@ -538,19 +540,7 @@ LTP_HD_NOINLINE unsigned char ost_quartic_tail(const JointLimits& L, const Prolo
 // and the caller must hand the problem to the generic kernel.
 enum { OST_FAIL = 0, OST_OK = 1, OST_DEFER = 2 };
 
-// The cc:119 test (does the joint have to slow down first, i.e. the modified jerk profile?)
-// as a function of its own, because the regrouping kernels evaluate it ahead of the solve to
-// decide which warp an item joins; same operations as inside ost_body_t, hence the same bits.
-LTP_HD bool ost_needs_mod_profile(const JointLimits& L, double v0m, double a0m, double V) {
-  return v0m + div_by(0.5 * a0m * fabs(a0m), L.j_max, L.r_j) > V;
-}
-
-// MODE: OST_ANY evaluates the cc:119 test; OST_NORMAL / OST_MODIFIED are for callers that have
-// evaluated it already (ost_needs_mod_profile on the same operands) and compile only the branch
-// that is taken -- the warps of the regrouped kernels run one branch each.
-enum { OST_ANY = 0, OST_NORMAL = 1, OST_MODIFIED = 2 };
-
-template <bool ALLOW_TAIL, int MODE = OST_ANY>
+template <bool ALLOW_TAIL>
 LTP_HD int ost_body_t(const JointLimits& L, double Ts, const Prologue& P, double q_goal, double q_0,
                       double V, double* t, unsigned char& mod, unsigned char& kase) {
   const double A = L.a_max, J = L.j_max;
@@ -566,8 +556,7 @@ LTP_HD int ost_body_t(const JointLimits& L, double Ts, const Prologue& P, double
   }
   const double v_0 = P.v0m, a_0 = P.a0m;
   double q_brake = 0.0;
-  const bool slow_down_first = MODE == OST_ANY ? ost_needs_mod_profile(L, v_0, a_0, V) : MODE == OST_MODIFIED;
-  if (slow_down_first) {  // cc:119-122
+  if (v_0 + div_by(0.5 * a_0 * fabs(a_0), J, L.r_j) > V) {  // cc:119-122
     mod = 1;
     flags |= F_MOD;
     double unused;
@@ -705,16 +694,15 @@ LTP_HD double ts_candidate1(const JointLimits& L, const TsInput& I) {
                 J, L.r_j);
 }
 
-// dq = dir * (q_0 - q_goal), the only way the two positions enter (cc:413)
-LTP_HD double ts_candidate2_core(const JointLimits& L, double a_0, double v_0, double tr, double dq) {
-  const double A = L.a_max, J = L.j_max;
+LTP_HD double ts_candidate2(const JointLimits& L, const TsInput& I) {
+  const double A = L.a_max, J = L.j_max, a_0 = I.a_0, v_0 = I.v_0, tr = I.tr, dir = I.dir;
   // w, h, g: sub-expressions the reference writes out repeatedly (cc:413-431)
   const double w = (v_0 + (a_0 * (a_0 - A)) / (2.0 * J)) / A;
   const double h = A / (2.0 * J);
   const double g = (a_0 - A) / (2.0 * J);
   const double sA = a_0 + A;
   const double J3 = pow3(J);
-  return -(dq -
+  return -(dir * (I.q_0 - I.q_goal) -
            J * (pow3(sA) / (6 * J3) - pow3(A) / (6 * J3) + (sq(A) * sA) / (2.0 * J3) +
                 (sq(sA) * (w + h + g)) / (2.0 * sq(J))) +
            a_0 * (sq(sA) / (2.0 * sq(J)) + sq(A) / (2.0 * sq(J)) + (sA * (w + h + g)) / J) -
@@ -722,10 +710,6 @@ LTP_HD double ts_candidate2_core(const JointLimits& L, double a_0, double v_0, d
          (h - v_0 / A + A * ((w - h + g) / A + 1.0 / J) -
           (sq(a_0) + 2.0 * a_0 * A + 4 * sq(A) - 2.0 * J * tr * A + 2.0 * J * v_0) / (2.0 * A * J) +
           sq(sA) / (2.0 * A * J) - (a_0 * sA) / (A * J));
-}
-
-LTP_HD double ts_candidate2(const JointLimits& L, const TsInput& I) {
-  return ts_candidate2_core(L, I.a_0, I.v_0, I.tr, I.dir * (I.q_0 - I.q_goal));
 }
 
 // candidates 3..8 need a polynomial root (quartic, quartic, quintic, quartic, quartic, sextic)

@@ -10,7 +10,6 @@
 #include <vector>
 
 #include "../longtermplanner_b200/csrc/ltp_math.cuh"
-#include "../longtermplanner_b200/csrc/ltp_pipeline.cuh"
 
 using namespace ltp;
 
@@ -227,156 +226,6 @@ int64_t shadow_solve_batch_auto(void* h, int64_t n, const double* q_goal, const 
     reached[p] = rch;
   }
   return deferred;
-}
-
-
-// Mirrors the regrouped solve of ltp_b200.cu (ltp_solve_stage1_kernel -> ltp_solve_scale_kernel with
-// its class-A / class-B / second-candidate slots -> every-branch kernel for what is deferred): the
-// same per-item functions (csrc/ltp_pipeline.cuh) and the same hand-overs, with std::vector lists
-// in place of the shared-memory lists. stats[0..4] = joints settled without a search, class A,
-// class B, second-candidate items, problems deferred.
-int64_t shadow_solve_batch_pipeline(void* h, int64_t n, const double* q_goal, const double* q_0, const double* v_0,
-                                    const double* a_0, double* t_opt, double* t_scaled, double* dir, double* v_drive,
-                                    unsigned char* mod, unsigned char* opt_case, unsigned char* ts_case,
-                                    unsigned char* final_case, int* slowest, int* traj_len, unsigned char* reached,
-                                    int64_t* stats) {
-  Shadow* s = static_cast<Shadow*>(h);
-  const int dof = s->dof;
-  const int kMark = 0x7fffffff;
-  struct Queued { ScaleItem it; int64_t p; };
-  std::vector<std::vector<Queued>> qa(dof), qb(dof), qc(dof);
-  std::vector<unsigned char> jflag((size_t)n * dof);
-  std::vector<int64_t> work;
-  int64_t settled = 0;
-  auto put = [&](int64_t p, int j, const JointResult& R) {
-    const int64_t o = p * dof + j;
-    std::memcpy(t_scaled + 7 * o, R.t, 56);
-    v_drive[o] = R.v_drive;
-    mod[o] = R.mod;
-    ts_case[o] = R.ts_case;
-    final_case[o] = R.final_case;
-  };
-  // kernel 1: every joint's record as if it were the slowest one of its problem
-  for (int64_t p = 0; p < n; ++p)
-    for (int j = 0; j < dof; ++j) {
-      const int64_t o = p * dof + j;
-      Stage1Out S1;
-      stage1_joint(s->lim[j], s->ts, q_goal[o], q_0[o], v_0[o], a_0[o], S1);
-      std::memcpy(t_opt + 7 * o, S1.t_opt, 56);
-      std::memcpy(t_scaled + 7 * o, S1.t_opt, 56);
-      dir[o] = S1.dir;
-      v_drive[o] = s->lim[j].v_max;
-      mod[o] = S1.mod;
-      opt_case[o] = S1.opt_case;
-      ts_case[o] = 0;
-      final_case[o] = S1.opt_case;
-      jflag[o] = S1.flags;
-    }
-  auto defer_problem = [&](int64_t p) {
-    if (traj_len[p] != kMark) {
-      traj_len[p] = kMark;
-      work.push_back(p);
-    }
-  };
-  auto join_len = [&](int64_t p, const double* t) {
-    const int li = joint_sample_count(t, s->ts);
-    if (li < 0) return defer_problem(p);
-    if (traj_len[p] < li) traj_len[p] = li;  // atomicMax
-  };
-  // kernel 2, first part: slowest joint, then every joint decides what happens to it
-  for (int64_t p = 0; p < n; ++p) {
-    const int64_t o = p * dof;
-    double t_req = -1;
-    int sl = -1;
-    unsigned char any = 0;
-    for (int j = 0; j < dof; ++j) {
-      any |= jflag[o + j];
-      if (t_scaled[7 * (o + j) + 6] > t_req) { t_req = t_scaled[7 * (o + j) + 6]; sl = j; }
-    }
-    const bool rch = !(any & JF_FAIL) && sl != -1;
-    slowest[p] = sl;
-    reached[p] = rch;
-    traj_len[p] = 0;
-    if (any & JF_DEFER) {
-      defer_problem(p);
-      continue;
-    }
-    for (int j = 0; j < dof; ++j) {
-      const int64_t oj = o + j;
-      if (!rch) {  // aborted before time scaling (cc:15,29,39): the record says so
-        JointResult R;
-        zero7(R.t);
-        R.v_drive = s->lim[j].v_max;
-        R.mod = mod[oj];
-        R.ts_case = 255;
-        R.final_case = 255;
-        put(p, j, R);
-        continue;
-      }
-      if (j == sl) {
-        join_len(p, t_scaled + 7 * oj);
-        ++settled;
-      } else if (jflag[oj] & JF_BRAKE_ONLY) {
-        const Prologue pro = ost_prologue(s->lim[j], s->ts, q_goal[oj], q_0[oj], v_0[oj], a_0[oj]);
-        JointResult R;
-        const int act = stage3_brake_only(s->lim[j], s->ts, pro, q_goal[oj], q_0[oj], v_0[oj], a_0[oj], t_req,
-                                          t_opt + 7 * oj, opt_case[oj], R);
-        if (act == S3_SETTLED) {
-          put(p, j, R);
-          join_len(p, R.t);
-          ++settled;
-        } else {
-          defer_problem(p);
-        }
-      } else {
-        Queued Q;
-        Q.p = p;
-        const int act = stage3_classify(s->lim[j], q_goal[oj], q_0[oj], v_0[oj], a_0[oj], dir[oj], t_req, Q.it);
-        (act == S3_QUEUE_A ? qa : qb)[j].push_back(Q);
-      }
-    }
-  }
-  auto finish = [&](int j, const Queued& Q, const JointResult& R) {
-    if (joint_sample_count(R.t, s->ts) < 0) return defer_problem(Q.p);
-    put(Q.p, j, R);
-    join_len(Q.p, R.t);
-  };
-  int64_t na = 0, nb = 0, nc = 0;
-  for (int j = 0; j < dof; ++j) {
-    na += (int64_t)qa[j].size();
-    nb += (int64_t)qb[j].size();
-    for (const Queued& Q : qa[j]) {
-      JointResult R;
-      const int r = scale_attempt1_class_a(s->lim[j], s->ts, Q.it, R);
-      if (r == SA_ACCEPT) finish(j, Q, R);
-      else if (r == SA_DEFER) defer_problem(Q.p);
-      else qc[j].push_back(Q);
-    }
-    for (const Queued& Q : qb[j]) {
-      JointResult R;
-      const int r = scale_attempt1_class_b(s->lim[j], s->ts, Q.it, R);
-      if (r == SA_ACCEPT) finish(j, Q, R);
-      else if (r == SA_DEFER) defer_problem(Q.p);
-      else qc[j].push_back(Q);
-    }
-    nc += (int64_t)qc[j].size();
-    for (const Queued& Q : qc[j]) {
-      JointResult R;
-      const int r = scale_attempt2(s->lim[j], s->ts, Q.it, R);
-      if (r == SA_ACCEPT) finish(j, Q, R);
-      else defer_problem(Q.p);
-    }
-  }
-  for (int64_t p : work) {
-    const int64_t o = p * dof;
-    shadow_solve_batch(h, 1, q_goal + o, q_0 + o, v_0 + o, a_0 + o, t_opt + 7 * o, t_scaled + 7 * o, dir + o,
-                       v_drive + o, mod + o, opt_case + o, ts_case + o, final_case + o, slowest + p, traj_len + p,
-                       reached + p, 0);
-  }
-  if (stats) {
-    stats[0] = settled; stats[1] = na; stats[2] = nb; stats[3] = nc; stats[4] = (int64_t)work.size();
-  }
-  return (int64_t)work.size();
 }
 
 int shadow_get_trajectory(void* h, const double* t7, const double* dir, const unsigned char* mod,

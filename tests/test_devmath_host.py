@@ -20,8 +20,8 @@ SHADOW = os.path.join(HERE, "_build", "libltp_shadow.so")
 def _shadow_lib():
     os.makedirs(os.path.dirname(SHADOW), exist_ok=True)
     src = os.path.join(HERE, "host_shadow.cc")
-    hdrs = [os.path.join(HERE, "..", "longtermplanner_b200", "csrc", f) for f in ("ltp_math.cuh", "ltp_pipeline.cuh")]
-    if (not os.path.exists(SHADOW)) or max(os.path.getmtime(f) for f in [src] + hdrs) > os.path.getmtime(SHADOW):
+    hdr = os.path.join(HERE, "..", "longtermplanner_b200", "csrc", "ltp_math.cuh")
+    if (not os.path.exists(SHADOW)) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(SHADOW):
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", src, "-o", SHADOW],
                        check=True)
 
@@ -44,48 +44,6 @@ class ShadowAuto(Shadow):
                 self.deferred = f(*a)
             return call
         return super()._fn(name, restype)
-
-
-class ShadowPipeline(Shadow):
-    """the regrouped solve (stage kernel -> class A / class B / second candidate -> every-branch
-    kernel), replayed on the host with the per-item functions of csrc/ltp_pipeline.cuh"""
-
-    def _fn(self, name, restype=None):
-        if name == "solve_batch":
-            import ctypes
-            f = getattr(self.lib, "shadow_solve_batch_pipeline")
-            f.restype = ctypes.c_int64
-            self.stats = np.zeros(5, np.int64)
-
-            def call(*a):
-                self.deferred = f(*a[:-1], ctypes.c_void_p(self.stats.ctypes.data))
-            return call
-        return super()._fn(name, restype)
-
-
-def _states(lim, n, seed, kind):
-    return W.random_states(lim, n, seed) if kind == "random" else W.edge_states(lim, n, seed)
-
-
-@pytest.mark.parametrize("lim,n,seed,kind", [
-    (W.FRANKA7, 60_000, 231, "random"), (W.FRANKA12, 20_000, 232, "random"), (W.REF_RANDOM6, 40_000, 233, "random"),
-    (W.REF_GRID, 50_000, 234, "random"), (W.FRANKA7, 30_000, 235, "edge"), (W.REF_RANDOM6, 30_000, 236, "edge"),
-    (W.random_limits(5, 17), 30_000, 237, "random"), (W.random_limits(9, 18), 20_000, 238, "edge")])
-def test_regrouped_pipeline_equals_generic(lim, n, seed, kind):
-    qg, q0, v0, a0 = _states(lim, n, seed, kind)
-    gen = Shadow.from_limits(lim).solve(qg, q0, v0, a0)
-    S = ShadowPipeline.from_limits(lim)
-    pipe = S.solve(qg, q0, v0, a0)
-    for k in gen:
-        a, b = gen[k], pipe[k]
-        assert np.array_equal(a, b, equal_nan=True) if a.dtype.kind == "f" else np.array_equal(a, b), k
-    settled, na, nb, nc, deferred = (int(x) for x in S.stats)
-    assert deferred == S.deferred and 0 <= deferred < n
-    if lim.dof > 1 and kind == "random":
-        assert na > 0 and nb > 0 and nc > 0
-    if lim is W.FRANKA7 and kind == "random":
-        assert deferred < 0.02 * n
-        assert settled + na + nb <= n * lim.dof
 
 
 @pytest.mark.parametrize("lim,n,seed", [(W.FRANKA7, 30_000, 221), (W.REF_RANDOM6, 30_000, 222), (W.REF_GRID, 50_000, 223)])

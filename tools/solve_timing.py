@@ -27,12 +27,12 @@ step_ms = e0.elapsed_time(e1) / 20
 ltp.setProfiling(True)
 for _ in range(20):
     ltp.solve(*ins, out=sol)
-ms, cnt = ltp.kernelTime("solve_tile")
+ms, cnt = ltp.kernelTime("solve_fast")
 ms2, cnt2 = ltp.kernelTime("solve_generic")
 chk = int(sol.traj_len.sum().item())
-ms3, cnt3 = ltp.kernelTime("solve_modified")
+ms3, cnt3 = ltp.kernelTime("solve_attempt2")
 try:
-    ms4, cnt4 = ltp.kernelTime("solve_second")
+    ms4, cnt4 = ltp.kernelTime("solve_queues")
 except Exception:
     ms4, cnt4 = 0.0, 0
 print(f"{os.environ.get('LTP_B200_LIB', 'default')}: dof {lim.dof} step {step_ms:.4f} ms = {n / step_ms / 1e3:.1f} M plans/s; kernel slot0 {ms / cnt:.4f} ms + slot4 {ms3 / max(cnt3, 1):.4f} ms + slot5 {ms4 / max(cnt4, 1):.4f} ms; "

@@ -25,7 +25,7 @@ t0 = time.perf_counter()
 stats = ltp.planStream(*ins, chunk=chunk, capacity=4096)
 dt = time.perf_counter() - t0
 k_ms, k_cnt = ltp.kernelTime("sample_time_major")
-s_ms, s_cnt = ltp.kernelTime("solve_tile")
+s_ms, s_cnt = ltp.kernelTime("solve_fast")
 print(json.dumps({"workload": f"2^{log2n} random 12-DoF problems (FRANKA12), exact-length dense sampling, chunk {chunk}",
                   "seconds": dt, "plans_per_s": n / dt, "write_gbs": stats["bytes"] / dt / 1e9,
                   "sampler_kernel_gbs": stats["bytes"] / (k_ms * 1e-3) / 1e9, "sampler_kernel_ms_total": k_ms,
