@@ -482,3 +482,58 @@ def test_sorted_slot_sampling_equals_problem_order_sampling(lim, n):
         for slot in range(0, n, 7):
             p = oc[slot]
             assert np.array_equal(a[:tlc[p], p, :], b[:tlc[p], slot, :]), (k, slot, p)
+
+
+@pytest.mark.parametrize("lim,n", [(W.FRANKA7, 1024), (W.FRANKA12, 257), (W.random_limits(1, 71), 3000),
+                                   (W.random_limits(3, 72), 700), (W.random_limits(17, 73), 130)])
+@pytest.mark.parametrize("mode", ["exact", "fixed_odd", "clipped"])
+def test_rows_layout_through_shared_memory_equals_time_major(lim, n, mode):
+    """batches in the rows layout go through the shared-memory tile + bulk-copy kernel
+    (ltp_sample_rows_bulk_kernel, n * dof >= 1024): same samples, bit for bit, as the time-major
+    kernel and the oracle -- exact lengths (odd and even), an odd fixed horizon, rows clipped by a
+    capacity below their length; problems that were not planned hold their start position in
+    fixed-horizon mode and are left alone in exact-length mode"""
+    assert n * lim.dof >= 1024
+    qg, q0, v0, a0 = W.random_states(lim, n, 77)
+    q0[3, 0] = lim.q_max[0] + 1.0     # rejected by checkInputs: reached = 0
+    qg[5, 0] = lim.q_max[0] + 0.5     # reached, but ends outside the joint range: success = 0
+    ltp = _planner(lim)
+    ins = [_dev(jm(x)) for x in (qg, q0, v0, a0)]
+    sol = ltp.solve(*ins)
+    tl = sol.traj_len.cpu().numpy()
+    longest = int(tl.max())
+    if mode == "exact":
+        kw, cap = dict(horizon=0), longest
+    elif mode == "fixed_odd":
+        kw, cap = dict(horizon=longest // 2 * 2 + 1), longest // 2 * 2 + 1
+    else:
+        kw, cap = dict(horizon=0), max(int(np.median(tl[tl > 0])) // 4 * 4, 4)
+    out_r = ltp.alloc_trajectories(n, cap, "rows")
+    out_t = ltp.alloc_trajectories(n, cap, "time_major")
+    for o in (out_r, out_t):
+        for k in "qvaj":
+            getattr(o, k).fill_(-777.0)
+    r = ltp.sample(ins[1], ins[2], ins[3], sol, out=out_r, **kw)
+    t = ltp.sample(ins[1], ins[2], ins[3], sol, out=out_t, **kw)
+    torch.cuda.synchronize()
+    assert np.array_equal(r.success.cpu().numpy(), t.success.cpu().numpy())
+    assert r.success[3].item() == 0 and r.success[5].item() == 0 and sol.reached[3].item() == 0
+    rr, tt = _rows(r), _rows(t)
+    H = kw["horizon"]
+    for k in "qvaj":
+        for i in range(n):
+            m = H if H > 0 else min(int(tl[i]), cap)
+            assert np.array_equal(rr[k][i, :, :m], tt[k][i, :, :m]), (k, i)
+            assert np.all(rr[k][i, :, m:cap] == -777.0), (k, i)   # nothing written behind the row
+    if H > 0:   # the unplanned problem holds (q_0, 0, 0, 0)
+        assert np.array_equal(rr["q"][3, :, :H], np.broadcast_to(q0[3][:, None], (lim.dof, H)))
+        assert np.all(rr["v"][3, :, :H] == 0) and np.all(rr["a"][3, :, :H] == 0) and np.all(rr["j"][3, :, :H] == 0)
+    else:
+        assert np.all(rr["q"][3] == -777.0)
+    # against the oracle's own sampler on a few problems
+    P = OraclePort.from_limits(lim)
+    for i in (0, 1, 5, n - 1):
+        full = P.plan(qg[i], q0[i], v0[i], a0[i], stride=max(longest, 8))
+        m = min(full["length"], cap) if H == 0 else min(full["length"], H)
+        for k in "qvaj":
+            assert count_bad(rr[k][i, :, :m], full[k][:, :m]) == 0, (k, i)
