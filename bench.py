@@ -108,28 +108,60 @@ def _close(got, ref):
     return ok | (got == ref) | (np.isnan(got) & np.isnan(ref))
 
 
-def parity_counts(sol, ref, only=None):
+def parity_counts(sol, ref, t_sample, cases=None):
     """Counts of disagreement between a BatchSolution (joint-major CUDA tensors, with case bytes and
     t_opt) and the CPU checker's solve of the same problems (problem-major numpy). exact_mismatch:
-    reached, slowest, traj_len, dir, mod and the three case bytes; numeric_mismatch: switching times
-    and v_drive outside 1e-9 rel / 1e-12 abs; bitdiff: values that are not bit-identical."""
-    idx = slice(None) if only is None else only
+    reached, slowest, traj_len, dir, mod (and, against `cases` = the C restatement's result, the
+    three case bytes -- the reference itself emits no case ids); numeric_mismatch: switching times
+    and v_drive outside 1e-9 rel / 1e-12 abs; bitdiff: values that are not bit-identical.
+    The unmodified reference returns no trajectory length from the solve: it is derived from its
+    switching times with the reference's own formula (cc:716-719), for reached problems."""
+    ref = dict(ref)
+    if "traj_len" not in ref:
+        t6 = ref["t_scaled"][:, :, 6]
+        with np.errstate(invalid="ignore"):
+            ln = (np.ceil(t6 / t_sample) + 1).max(axis=1)
+        ref["traj_len"] = np.where(ref["reached"] != 0, ln, 0).astype(np.int32)
     exact = {}
     for k in ("reached", "slowest", "traj_len"):
-        exact[k] = int((getattr(sol, k).cpu().numpy()[idx] != ref[k]).sum())
-    for k in ("mod", "opt_case", "ts_case", "final_case"):
-        exact[k] = int((getattr(sol, k).cpu().numpy().T[idx] != ref[k]).sum())
-    exact["dir"] = int((sol.dir.cpu().numpy().T[idx] != ref["dir"]).sum())
+        exact[k] = int((getattr(sol, k).cpu().numpy() != ref[k]).sum())
+    exact["dir"] = int((sol.dir.cpu().numpy().T != ref["dir"]).sum())
+    exact["mod"] = int((sol.mod.cpu().numpy().T != ref["mod"]).sum())
+    if cases is not None:
+        for k in ("opt_case", "ts_case", "final_case"):
+            exact[k] = int((getattr(sol, k).cpu().numpy().T != cases[k]).sum())
     numeric, bits, values = {}, 0, 0
     for k in ("t_scaled", "t_opt", "v_drive"):
         got = getattr(sol, k).cpu().numpy()
-        got = (got.transpose(2, 1, 0) if got.ndim == 3 else got.T)[idx]
+        got = got.transpose(2, 1, 0) if got.ndim == 3 else got.T
         numeric[k] = int((~_close(got, ref[k])).sum())
         bits += int((~((got == ref[k]) | (np.isnan(got) & np.isnan(ref[k])))).sum())
         values += got.size
     return {"checked": int(ref["reached"].shape[0]), "exact_mismatch": int(sum(exact.values())),
             "numeric_mismatch": int(sum(numeric.values())), "bitdiff": bits, "values_compared": values,
             "exact_by_field": exact, "numeric_by_field": numeric, "tolerance": {"rel": RTOL, "abs": ATOL}}
+
+
+def full_parity(ltp, lim, dev_in, states, threads):
+    """all problems of a workload: the CUDA solve against the reference build (values, flags) and
+    the C restatement (case ids)"""
+    import torch
+    from oracle.bindings import OraclePort
+    chk, kind = cpu_checker(lim)
+    t0 = time.perf_counter()
+    ref = chk.solve(*states, threads=threads)
+    cpu_s = time.perf_counter() - t0
+    cases = ref if kind == "port" else OraclePort.from_limits(lim).solve(*states, threads=threads)
+    full = ltp.solve(*dev_in, with_opt=True, with_cases=True)
+    torch.cuda.synchronize()
+    par = parity_counts(full, ref, lim.t_sample, cases)
+    par.update({"against": kind + (" (values, flags) + C restatement (case ids)" if kind != "port" else ""),
+                "cpu_seconds": cpu_s, "cpu_threads": threads})
+    return par, full, n_per_s(states, cpu_s)
+
+
+def n_per_s(states, seconds):
+    return states[0].shape[0] / seconds
 
 
 def run_reference_arm(args):
@@ -194,13 +226,166 @@ def bind_to_gpu_numa_node(index):
         return None
 
 
+def kernel_source_hash():
+    """sha256 over the CUDA sources the kernels are built from (stamped into profiles/ncu_facts.json
+    by tools/ncu_summary.py --json, compared here: numbers read off a capture of OTHER code are not
+    printed)"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("ltp_b200.cu", "ltp_math.cuh"):
+        h.update(open(os.path.join(ROOT, "longtermplanner_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def ncu_facts():
     """per-launch facts read off the committed ncu --set full capture (profiles/ncu_facts.json,
-    written by tools/ncu_summary.py --json); {} if the capture has not been made"""
+    written by tools/ncu_summary.py --json); {} if the capture has not been made or was taken from
+    other kernel sources than the ones this run was built from"""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "ncu_facts.json")))
+        facts = json.load(open(os.path.join(ROOT, "profiles", "ncu_facts.json")))
     except Exception:
-        return {}
+        return {}, "no capture"
+    if facts.get("source_sha") != kernel_source_hash():
+        return {}, f"stale (capture of source {facts.get('source_sha')}, built from {kernel_source_hash()})"
+    return facts, f"profiles/ncu_facts.json ({facts.get('captured', '?')})"
+
+
+def pcie_probe(host_in, host_out_t, dev, iters, barrier, max_over_ranks):
+    """The ceiling of the end-to-end path: the step's input bytes go host->device on one stream while
+    its output bytes go device->host on another, as flat copies between pinned buffers and nothing
+    else. Returns seconds per step (max over ranks)."""
+    import torch
+    d_in = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in host_in]
+    d_out = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in host_out_t]
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def step():
+        with torch.cuda.stream(s_in):
+            for d, h in zip(d_in, host_in):
+                d.copy_(h, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            for d, h in zip(d_out, host_out_t):
+                h.copy_(d, non_blocking=True)
+
+    step()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        step()
+    torch.cuda.synchronize()
+    return max_over_ranks(time.perf_counter() - t0) / iters
+
+
+ROW_STATS = ("sum_q", "sum_v", "sum_a", "sum_j", "max_abs_v", "max_abs_a", "q_last", "v_last")
+
+
+class StreamParity:
+    """Consumer of the streamed configs[4] run: of every `stride`-th problem of the GLOBAL index
+    space it reduces the sampled rows on the device (sums, maxima and the last sample of q, v, a,
+    j per joint) and keeps traj_len and the success flag; after the run the same problems are
+    planned by the CPU checker and compared. No synchronisation inside the callback."""
+
+    def __init__(self, lim, seed, global_first, stride, dev):
+        self.lim, self.seed, self.g0, self.stride, self.dev = lim, seed, global_first, stride, dev
+        self.kept = []
+
+    def __call__(self, view, stream):
+        import torch
+        first, cnt, cap = view["first"], view["count"], view["capacity"]
+        g = self.g0 + first
+        k0 = (-g) % self.stride
+        if k0 >= cnt:
+            return
+        ks = list(range(k0, cnt, self.stride))
+        idx = torch.tensor(ks, device=self.dev)
+        tl = view["traj_len"][idx].long()
+        live = (torch.arange(cap, device=self.dev)[:, None] < tl[None, :])[:, :, None]
+        f = {k: view[k][:, idx, :] for k in "qvaj"}          # (cap, m, dof) copies of the selected slots
+        z = {k: torch.where(live, f[k], torch.zeros((), dtype=torch.float64, device=self.dev)) for k in "qvaj"}
+        last = (tl - 1).clamp(min=0)
+        cols = torch.arange(len(ks), device=self.dev)
+        stats = torch.stack([z["q"].sum(0), z["v"].sum(0), z["a"].sum(0), z["j"].sum(0), z["v"].abs().amax(0),
+                             z["a"].abs().amax(0), f["q"][last, cols, :], f["v"][last, cols, :]])
+        self.kept.append(([g + k for k in ks], stats, tl, view["success"][idx].clone()))
+
+    def compare(self, checker):
+        """-> counts against the CPU checker's plan of the same problems"""
+        n_prob = exact_bad = numeric_bad = values = 0
+        for gids, stats, tl, succ in self.kept:
+            stats, tl, succ = stats.cpu().numpy(), tl.cpu().numpy(), succ.cpu().numpy()
+            for c, gid in enumerate(gids):
+                qg, q0, v0, a0 = W.random_states(self.lim, 1, self.seed, start=gid)
+                ref = checker.plan(qg[0], q0[0], v0[0], a0[0], stride=16384)
+                n_prob += 1
+                ln = ref["length"]
+                exact_bad += int(ln != tl[c]) + int(bool(ref["success"]) != bool(succ[c]))
+                if ln != tl[c] or ln <= 0:
+                    continue
+                r = {k: ref[k][:, :ln] for k in "qvaj"}
+                want = np.stack([r["q"].sum(1), r["v"].sum(1), r["a"].sum(1), r["j"].sum(1), np.abs(r["v"]).max(1),
+                                 np.abs(r["a"]).max(1), r["q"][:, -1], r["v"][:, -1]])
+                scale = np.stack([np.abs(r["q"]).sum(1), np.abs(r["v"]).sum(1), np.abs(r["a"]).sum(1),
+                                  np.abs(r["j"]).sum(1), np.abs(r["v"]).max(1), np.abs(r["a"]).max(1),
+                                  np.abs(r["q"][:, -1]), np.abs(r["v"][:, -1])])
+                bad = np.abs(stats[:, c, :] - want) > ATOL + RTOL * scale
+                numeric_bad += int(bad.sum())
+                values += bad.size
+        return n_prob, exact_bad, numeric_bad, values
+
+
+def generic_section(LongTermPlanner, local, dev, steps, cores):
+    """The every-branch (root-solving) kernel under load: 2^20 random 6-DoF problems under the
+    reference's own toy limits (REF_RANDOM6: a fifth of the problems needs a polynomial root), the
+    AUTO pipeline and the every-branch kernel alone, all problems checked against the CPU checker,
+    whose own time on the same problems is the CPU baseline of this workload."""
+    import torch
+    lim = W.REF_RANDOM6
+    n = 1 << 20
+    ltp6 = LongTermPlanner(lim.dof, lim.t_sample, *lim.arrays(), device=local)
+    qg, q0, v0, a0 = W.random_states(lim, n, W.SEEDS[2])
+    ins = [torch.from_numpy(W.to_joint_major(x)).to(dev) for x in (qg, q0, v0, a0)]
+    sol = ltp6.alloc_solution(n, with_opt=True, with_cases=True)
+    out = {"workload": "2^20 random 6-DoF problems, reference test limits (REF_RANDOM6: v 1, a 2, j 4, t_sample "
+                       "1 ms), solve only"}
+    for mode, generic_only in (("auto", False), ("every_branch_kernel_only", True)):
+        ltp6.setSolveMode(generic_only)
+        for _ in range(2):
+            ltp6.solve(*ins, out=sol)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            ltp6.solve(*ins, out=sol)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        ltp6.setProfiling(True)
+        for k in ("solve_fast", "solve_attempt2", "solve_generic"):
+            ltp6.kernelTime(k)
+        for _ in range(steps):
+            ltp6.solve(*ins, out=sol)
+        kern = {}
+        for k in ("solve_fast", "solve_attempt2", "solve_generic"):
+            k_ms, k_cnt = ltp6.kernelTime(k)
+            kern[k] = k_ms / max(k_cnt, 1)
+        ltp6.setProfiling(False)
+        out[mode] = {"ms_per_step": ms, "plans_per_s": n / (ms * 1e-3), "kernels_ms": kern}
+    ltp6.setSolveMode(False)
+    ltp6.solve(*ins, out=sol)
+    torch.cuda.synchronize()
+    tc, oc = sol.ts_case.cpu().numpy(), sol.opt_case.cpu().numpy()
+    rooty = ((tc >= 3) & (tc <= 9)).any(axis=0) | np.isin(oc & 15, (6, 7, 8)).any(axis=0)
+    out["problems_with_a_root_solve_or_failed_search"] = float(rooty.mean())
+    try:
+        par, _, cpu_rate = full_parity(ltp6, lim, ins, (qg, q0, v0, a0), cores)
+        out["cpu_baseline"] = {"value": cpu_rate, "unit": "plans/s", "cores": cores,
+                               "kind": cpu_checker(lim)[1], "sample": "all 2^20 problems, solve only"}
+        out["parity"] = par
+    except Exception as e:
+        out["parity"] = {"checked": 0, "unavailable": str(e)}
+    return out
+
 
 
 def replan_loop(ltp, lim, dev, hbm_peak, n_env=4096, horizon=2001, tick=9, ticks=50):
@@ -338,6 +523,7 @@ def main():
     ap.add_argument("--no-replan", action="store_true")
     ap.add_argument("--no-single", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-generic", action="store_true")
     ap.add_argument("--stream-log2n", type=int, default=26, help="configs[4]: total problems = 2^k over all GPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -429,52 +615,59 @@ def main():
 
     # ---- end to end through the host-buffer C-ABI entry point ------------------------------
     host_np = [t.numpy() for t in host_in]
-    host_out = {k: torch.empty(s, dtype=d).pin_memory().numpy() for k, s, d in (
+    host_out_t = {k: torch.empty(s, dtype=d).pin_memory() for k, s, d in (
         ("t_scaled", (7, lim.dof, n), torch.float64), ("dir", (lim.dof, n), torch.float64),
         ("v_drive", (lim.dof, n), torch.float64), ("mod", (lim.dof, n), torch.uint8),
         ("slowest", (n,), torch.int32), ("traj_len", (n,), torch.int32), ("reached", (n,), torch.uint8))}
+    host_out = {k: t.numpy() for k, t in host_out_t.items()}
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        ltp.solve_host(*host_np, out=host_out)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ltp.solve_host(*host_np, out=host_out)  # synchronises internally; result lands in host memory
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+
+    def time_host_calls(out):
+        for _ in range(2):
+            ltp.solve_host(*host_np, out=out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ltp.solve_host(*host_np, out=out)  # synchronises internally; result lands in host memory
+        torch.cuda.synchronize()
+        return max_over_ranks(time.perf_counter() - t0)
+
+    e2e_s = time_host_calls(host_out)
     e2e_value = world * n * e2e_steps / e2e_s
+    assert np.array_equal(host_out["traj_len"], sol.traj_len.cpu().numpy())  # what was timed is what was solved
     h2d = sum(x.nbytes for x in host_np)
     d2h = sum(x.nbytes for x in host_out.values())
+    # the same call with the output mask a caller sets who goes on to sample on the device or only
+    # needs the durations: switching times, lengths and flags (ltp_solve_host: NULL = not copied)
+    lean_out = {k: host_out[k] for k in ("t_scaled", "traj_len", "reached")}
+    lean_s = time_host_calls(lean_out)
+    lean_d2h = sum(x.nbytes for x in lean_out.values())
+    # the ceiling: the same bytes as bare pinned copies in both directions at once
+    probe_s = pcie_probe(host_in, list(host_out_t.values()), dev, 5, barrier, max_over_ranks)
+    probe_lean_s = pcie_probe(host_in, [host_out_t[k] for k in lean_out], dev, 5, barrier, max_over_ranks)
     clock_info = clocks.stop() if rank == 0 else None
     os.sched_setaffinity(0, all_cpus)  # the CPU baseline below uses every host core
 
     # a cheap integrity check on what was timed
     reached_frac = float(sol.reached.double().mean().item())
     assert reached_frac > 0.99, reached_frac
-    assert np.array_equal(host_out["traj_len"], sol.traj_len.cpu().numpy())
 
     # ---- parity of the timed workload at its full size: every one of this rank's 2^20 problems
     # against the reference's own CPU code (oracle/_ref; the checker, never the thing measured)
     parity = None
     if rank == 0 and not args.no_parity:
         try:
-            chk, kind = cpu_checker(lim)
-            t0 = time.perf_counter()
-            ref = chk.solve(qg, q0, v0, a0, threads=len(all_cpus))
-            cpu_s = time.perf_counter() - t0
-            full = ltp.solve(*dev_in, with_opt=True, with_cases=True)
-            torch.cuda.synchronize()
-            parity = parity_counts(full, ref)
-            parity.update({"against": kind, "cpu_seconds": cpu_s, "workload": "configs[1], all problems of rank 0",
+            parity, full, _ = full_parity(ltp, lim, dev_in, (qg, q0, v0, a0), len(all_cpus))
+            parity.update({"workload": "configs[1], all problems of rank 0",
                            "matches_timed_output": bool(torch.equal(full.t_scaled, sol.t_scaled)
                                                         and torch.equal(full.traj_len, sol.traj_len))})
-            del full, ref
+            del full
         except Exception as e:  # the checker is test infrastructure; never fail the bench on it
             parity = {"checked": 0, "unavailable": str(e)}
 
     extra = {}
     # free the configs[1] buffers before the memory-hungry sections
-    del dev_in, host_in, host_np, host_out
+    del dev_in, host_in, host_np, host_out, host_out_t, lean_out
     torch.cuda.empty_cache()
 
     # ---- configs[4]: 2^26 random 12-DoF problems, full dense sampling, sharded over the ranks --
@@ -488,12 +681,15 @@ def main():
         ins12 = devtools.random_states_device(lim12, n_rank, W.SEEDS[5], start=rank * n_rank, device=local)
         ltp12.planStream(*[t[:, :2 * chunk + 7].contiguous() for t in ins12], chunk=chunk, capacity=cap)  # warm-up
         runs = {}
+        # the problem-order run carries the parity consumer: every (2^k / 1024)-th problem of the run
+        watch = StreamParity(lim12, W.SEEDS[5], rank * n_rank, max(n_total // 1024, 1), dev)
         for mode in ("sorted_slots", "problem_order"):
             launches12 = ltp12.launches
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
             s0.record()
-            st12 = ltp12.planStream(*ins12, chunk=chunk, capacity=cap, sorted_slots=(mode == "sorted_slots"))
+            st12 = ltp12.planStream(*ins12, chunk=chunk, capacity=cap, sorted_slots=(mode == "sorted_slots"),
+                                    consumer=watch if (mode == "problem_order" and not args.no_parity) else None)
             s1.record()
             barrier()
             stream_ms = max_over_ranks(s0.elapsed_time(s1))
@@ -505,6 +701,22 @@ def main():
         stream_ms, tot, launches_stream = runs["sorted_slots"]
         assert tot == runs["problem_order"][1], "both slot orders must produce the same totals"
         po_ms = runs["problem_order"][0]
+        stream_parity = None
+        if not args.no_parity:
+            try:
+                chk12, kind12 = cpu_checker(lim12)
+                cnt = torch.tensor(watch.compare(chk12), dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(cnt)
+                cnt = [int(x) for x in cnt.tolist()]
+                stream_parity = {"checked": cnt[0], "exact_mismatch": cnt[1], "numeric_mismatch": cnt[2],
+                                 "values_compared": cnt[3], "against": kind12,
+                                 "what": "every (n/1024)-th problem of the run: traj_len and success exact; per joint "
+                                         "the sums of q, v, a, j over the row, max |v|, max |a| and the last q, v "
+                                         "(reduced on the device inside the stream consumer) within 1e-9 rel / "
+                                         "1e-12 abs of the same reductions of the CPU checker's plan"}
+            except Exception as e:
+                stream_parity = {"checked": 0, "unavailable": str(e)}
         extra_stream = {
             "workload": f"configs[4]: 2^{args.stream_log2n} random 12-DoF dual-arm problems (FRANKA12), solve + "
                         "exact-length dense q/v/a/j sampling, contiguous problem-index shards, each rank streams its "
@@ -517,8 +729,9 @@ def main():
                               "write_gbs": tot[1] / (po_ms * 1e-3) / 1e9,
                               "write_gbs_per_gpu": tot[1] / (po_ms * 1e-3) / 1e9 / world},
             "bytes_written": tot[1], "problems": tot[0], "reached": tot[4], "success": tot[2], "clipped": tot[3],
-            "gpu_launches": launches_stream,
-            "timing": "CUDA events around the call (it synchronises its two streams), max over ranks"}
+            "gpu_launches": launches_stream, "parity": stream_parity,
+            "timing": "CUDA events around the call (it synchronises its two streams), max over ranks; the "
+                      "problem-order run carries the parity consumer (a Python callback per chunk)"}
         del ins12, ltp12
         torch.cuda.empty_cache()
     if rank == 0:
@@ -538,7 +751,7 @@ def main():
         probe.ltp_probe_hbm_write_gbs(local, 3, C.byref(wgbs))
         fp64_peak = tf.value if tf.value > 0 else 37.0
         achieved_tf = (n / (kernel_ms * 1e-3)) * FLOP_PER_PLAN_7DOF / 1e12
-        ncu = ncu_facts()
+        ncu, ncu_src = ncu_facts()
         alg_gbs = (n * (224 + 534) / (kernel_ms * 1e-3)) / 1e9
         extra["roofline"] = {
             "kernel": "ltp_solve_fast_kernel", "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
@@ -550,6 +763,7 @@ def main():
             "work_list_kernel_ms": generic_kernel_ms, "kernels_ms": per_kernel,
             "timing": "CUDA events on the launching stream around each launch, mean of K launches",
             "ncu_fp64_pipe_pct": ncu.get("ltp_solve_fast_kernel", {}).get("fp64_pipe_pct"),
+            "ncu_capture": ncu_src,
             "hbm": {"achieved": alg_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": alg_gbs / hbm_peak,
                     "algorithmic_bytes_per_plan": 224 + 534, "peak_source": hbm_src}}
 
@@ -609,15 +823,33 @@ def main():
         if not args.no_single and world == 1:
             extra["single_plan"] = single_plan_latency(ltp, lim)
 
+        # ---- the root-solving path under load (reference test limits) ------------------------
+        if not args.no_generic and world == 1:
+            extra["generic"] = generic_section(LongTermPlanner, local, dev, max(3, min(args.steps, 10)),
+                                               os.cpu_count() or 1)
+
         # ---- CPU baseline: the reference's code on this box's host cores ---------------------
         if not args.no_cpu and world == 1:
             cores = os.cpu_count() or 1
             try:
                 r_all, kind = cpu_solve_rate(1 << 19, cores, W.SEEDS[2])
                 r_one, _ = cpu_solve_rate(1 << 16, 1, W.SEEDS[2])
+                o0 = None
+                try:  # the reference's shipped flags (-std=c++17 only, CMakeLists.txt:5), labelled as such
+                    from oracle.bindings import ReferenceO0
+                    if ReferenceO0.available():
+                        c0 = ReferenceO0.from_limits(W.FRANKA7)
+                        s_qg, s_q0, s_v0, s_a0 = W.random_states(W.FRANKA7, 1 << 17, W.SEEDS[2])
+                        c0.solve(s_qg[:2048], s_q0[:2048], s_v0[:2048], s_a0[:2048], threads=cores)
+                        t0 = time.perf_counter()
+                        c0.solve(s_qg, s_q0, s_v0, s_a0, threads=cores)
+                        o0 = {"value": (1 << 17) / (time.perf_counter() - t0), "unit": "plans/s", "cores": cores,
+                              "flags": ReferenceO0.flags, "sample": "first 2^17 problems"}
+                except Exception as e:
+                    o0 = {"unavailable": str(e)}
                 extra["cpu_baseline"] = {
                     "value": r_all, "unit": "plans/s", "cores": cores, "kind": kind,
-                    "single_thread_value": r_one,
+                    "single_thread_value": r_one, "shipped_flags": o0,
                     "sample": f"first 2^19 of the 2^20 problems with {cores} threads (and 2^16 with 1 thread), "
                               "solve only = reference cc:14-55; "
                               + ("reference .cc unmodified + Eigen shim" if kind == "reference" else "C restatement")
@@ -636,12 +868,26 @@ def main():
                        "l2": "inputs 235 MB + outputs 560 MB per step, larger than the 126 MB L2",
                        "sharding": "contiguous problem-index shards, no collective on the data path"},
             "e2e": {"value": e2e_value, "unit": "plans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "ltp_solve_host (pinned host buffers in and out)",
-                    "host_numa_node": numa},
+                    "steps": e2e_steps, "api": "ltp_solve_host (pinned host buffers in and out), every solver output",
+                    "host_numa_node": numa,
+                    "achieved_gbs": world * (h2d + d2h) * e2e_steps / e2e_s / 1e9,
+                    "pcie_peak_gbs": world * (h2d + d2h) / probe_s / 1e9,
+                    "frac": probe_s / (e2e_s / e2e_steps),
+                    "bound": "host<->device copies: the same bytes as bare concurrent pinned copies (both directions "
+                             "at once, all ranks at once) take pcie_probe_ms per step; frac = that / the call",
+                    "pcie_probe_ms": probe_s * 1e3,
+                    "lean": {"value": world * n * e2e_steps / lean_s, "unit": "plans/s",
+                             "outputs": "t_scaled, traj_len, reached (output mask: the other fields NULL)",
+                             "d2h_bytes_per_step": lean_d2h, "pcie_probe_ms": probe_lean_s * 1e3,
+                             "frac": probe_lean_s / (lean_s / e2e_steps)}},
             "gpu_launches": int(gpu_launches), "clocks": clock_info, "reached_frac": reached_frac,
             "parity": parity,
         }
         line.update(extra)
+        if "stream" in extra:  # configs[4] at the top level, so that a per-N table shows the strong scaling
+            line["stream_seconds"] = extra["stream"]["seconds"]
+            line["stream_plans_per_s"] = extra["stream"]["plans_per_s"]
+            line["stream_write_gbs"] = extra["stream"]["write_gbs"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

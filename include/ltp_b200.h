@@ -260,8 +260,10 @@ int ltp_advance_batch(ltp_planner* p, int64_t n, int32_t tick, int32_t clamp, in
 
 /* Stages 1-3 with HOST buffers: copies the four inputs in, solves, copies the requested
  * outputs back, and synchronises. Same layouts as ltp_solve_batch; the ltp_solution
- * holds HOST pointers here (optional ones may be NULL). Pinned host memory makes the
- * copies asynchronous and lets chunks overlap. */
+ * holds HOST pointers here. Output mask: every field except traj_len and reached may be NULL
+ * and is then not copied back -- the device->host transfer is what bounds this call (520 B per
+ * 7-DoF plan for the full solution, 397 B for t_scaled + traj_len + reached, 5 B for the
+ * durations alone). Pinned host memory makes the copies asynchronous and lets chunks overlap. */
 int ltp_solve_host(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
                    const double* v_0, const double* a_0, const ltp_solution* host_sol);
 

@@ -564,18 +564,8 @@ __global__ void ltp_time_scaling_kernel(const __grid_constant__ PlannerParams P,
 // per-problem limit check is a warp vote and the grid (n*dof/28 CTAs for 7 joints) spreads
 // evenly over the SMs even for a few thousand problems.
 // ------------------------------------------------------------------------------------
-// The batch samplers walk a row with the current piece in registers (PieceCursorT); the
-// per-sample table walk (SegCursorT) is kept for A/B timing (-DLTP_PIECE_CURSOR=0).
-#ifndef LTP_PIECE_CURSOR
-#define LTP_PIECE_CURSOR 1
-#endif
-#if LTP_PIECE_CURSOR
-using RowCursor = PieceCursorT<64>;
-__device__ __forceinline__ void cursor_begin(RowCursor& C, const RowSampler& R, const SegTableT<64>& T) { C.begin(R, T); }
-#else
 using RowCursor = SegCursorT<64>;
 __device__ __forceinline__ void cursor_begin(RowCursor& C, const RowSampler& R, const SegTableT<64>&) { C.begin(R); }
-#endif
 
 __device__ __forceinline__ void store4(double* dst, double x0, double x1, double x2, double x3) {
   asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(x0), "d"(x1), "d"(x2), "d"(x3)
@@ -973,143 +963,6 @@ ltp_sample_tm_kernel(const __grid_constant__ PlannerParams P, int64_t n, const d
 }
 
 // ------------------------------------------------------------------------------------
-// Rows layout through shared memory: q[(problem * dof + joint) * stride + sample], the layout of
-// Trajectory::q[joint][sample] (reference h:41-44). A thread that stores its row directly writes
-// one 32-byte sector per field every four samples, and the 32 lanes of a warp do so in 32
-// different DRAM pages: the memory system sees n*dof*4 interleaved streams of single sectors and
-// tops out at ~3.5 TB/s. Here every lane collects K samples of its row per field in a shared
-// tile (row pitch K + 2 doubles: the 128-bit shared stores of a quarter-warp fall into distinct
-// banks, and every row segment stays 16-byte aligned) and hands the four segments to the bulk
-// copy engine (cp.async.bulk.global.shared::cta, SASS UBLKCP): one K*8-byte burst per row, field
-// and tile instead of K/4 scattered sectors. A lane fills, fences and copies only its own rows of
-// the tile, and bulk groups are tracked per thread, so there is no synchronisation between lanes
-// at all; with NBUF > 1 tiles the copy of one tile overlaps the arithmetic of the next.
-// Lane l of CTA b owns row 32 b + l of the flattened (problem, joint) index (every lane busy for
-// any dof); success[] must have been initialised with reached[] (as for the time-major kernel).
-#ifndef LTP_ROWS_K
-#define LTP_ROWS_K 32
-#endif
-#ifndef LTP_ROWS_BULK
-#define LTP_ROWS_BULK 1
-#endif
-#ifndef LTP_ROWS_NBUF
-#define LTP_ROWS_NBUF 1
-#endif
-__device__ __forceinline__ void bulk_store(double* dst, const double* src_smem, unsigned bytes) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(src_smem);
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(s), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-// generic-proxy writes to shared memory -> visible to the async proxy that executes the copy
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-template <int K, int NBUF>
-__global__ void __launch_bounds__(32)
-ltp_sample_rows_bulk_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_0,
-                            const double* __restrict__ v_0, const double* __restrict__ a_0, DeviceSolution S,
-                            int horizon, int64_t stride, double* __restrict__ q, double* __restrict__ v,
-                            double* __restrict__ a, double* __restrict__ j, uint8_t* success) {
-  constexpr int kPitch = K + 2;
-  __shared__ __align__(16) double s_tab[kMaxSeg][32][2];  // per-lane segment table, [entry][lane][word]
-  extern __shared__ __align__(16) double s_tile[];        // [NBUF][4 fields][32 rows][kPitch]
-  const int dof = P.dof;
-  const int lane = threadIdx.x;
-  const SegTableT<64> T{&s_tab[0][lane][0]};
-  const int64_t rows = n * dof;
-  const int64_t r = (int64_t)blockIdx.x * 32 + lane;
-  if (r >= rows) return;
-  const int64_t p = r / dof;
-  const int jt = (int)(r - p * dof);
-  const int64_t at = (int64_t)jt * n + p;
-  double* qo = q + r * stride;
-  double* vo = v + r * stride;
-  double* ao = a + r * stride;
-  double* jo = j + r * stride;
-  const bool planned = S.reached[p] != 0;
-  const int len = planned ? S.traj_len[p] : 0;
-  if (len <= 0) {
-    if (planned) clear_flag(success, p);
-    if (horizon > 0) {  // fixed horizon: a problem without a plan holds its start position (ltp_b200.h)
-      const double hold = q_0[at];
-      for (int i = 0; i < horizon; ++i) {
-        qo[i] = hold; vo[i] = 0.0; ao[i] = 0.0; jo[i] = 0.0;
-      }
-    }
-    return;
-  }
-  const JointLimits L = P.lim[jt];
-  double t[7];
-#pragma unroll
-  for (int k = 0; k < 7; ++k) t[k] = S.t_scaled[((int64_t)k * dof + jt) * n + p];
-  const int n_out = horizon > 0 ? horizon : (len < stride ? len : (int)stride);  // samples stored
-  const int n_run = n_out > len ? n_out : len;                                    // samples computed
-  RowCursor C;
-  {
-    RowSampler R;
-    R.init(P.ts, L.j_max, t, S.dir[at], S.mod[at], q_0[at], v_0[at], a_0[at], S.v_drive[at], n_run);
-    T.build(R, n_run, true);
-    cursor_begin(C, R, T);
-  }
-  double* const mine = s_tile + lane * kPitch;
-  int i = 0, buf = 0;
-  while (i < n_out) {
-    const int cnt = (n_out - i) < K ? (n_out - i) : K;
-    const int even = cnt & ~1;
-    bulk_wait_read<NBUF - 1>();  // the copies that read this tile last time are done with it
-    double* tq = mine + (buf * 4 + 0) * 32 * kPitch;
-    double* tv = mine + (buf * 4 + 1) * 32 * kPitch;
-    double* ta = mine + (buf * 4 + 2) * 32 * kPitch;
-    double* tj = mine + (buf * 4 + 3) * 32 * kPitch;
-#pragma unroll 2
-    for (int u = 0; u < even; u += 2) {
-      double j0, a0s, v0s, q0s, j1, a1s, v1s, q1s;
-      C.step(T, i + u, j0, a0s, v0s, q0s);
-      C.step(T, i + u + 1, j1, a1s, v1s, q1s);
-      *reinterpret_cast<double2*>(tq + u) = make_double2(q0s, q1s);
-      *reinterpret_cast<double2*>(tv + u) = make_double2(v0s, v1s);
-      *reinterpret_cast<double2*>(ta + u) = make_double2(a0s, a1s);
-      *reinterpret_cast<double2*>(tj + u) = make_double2(j0, j1);
-    }
-    if (even) {
-      fence_async_smem();
-      const unsigned bytes = (unsigned)even * 8u;
-      bulk_store(qo + i, tq, bytes);
-      bulk_store(vo + i, tv, bytes);
-      bulk_store(ao + i, ta, bytes);
-      bulk_store(jo + i, tj, bytes);
-    }
-    bulk_commit();
-    if (cnt & 1) {  // the last sample of a row with an odd number of samples
-      double jj, aa, vv, qq;
-      C.step(T, i + even, jj, aa, vv, qq);
-      qo[i + even] = qq; vo[i + even] = vv; ao[i + even] = aa; jo[i + even] = jj;
-    }
-    i += cnt;
-    buf = (buf + 1 == NBUF) ? 0 : buf + 1;
-  }
-  // cc:60, as in the time-major kernel: the position is constant from the last switching sample
-  // on; a clipped row jumps to its end with the per-piece closed form and only steps through the
-  // remaining samples if that lands within 1e-9 of a limit
-  double q_end = C.q;
-  if (i < n_run) {
-    q_end = C.peek_position(T, i, n_run);
-    const double band = 1e-9;
-    if (!(fabs(q_end - L.q_min) > band && fabs(q_end - L.q_max) > band)) {
-      double jj, aa, vv, qq;
-      for (; i < n_run; ++i) C.step(T, i, jj, aa, vv, qq);
-      q_end = C.q;
-    }
-  }
-  if (q_end < L.q_min || q_end > L.q_max) clear_flag(success, p);
-  bulk_wait_read<0>();  // the tile must outlive the copies that read it
-}
-
-// ------------------------------------------------------------------------------------
 // Problems ordered by trajectory length, longest first, for the exact-length time-major
 // sampler: a counting sort over kOrderBins buckets of 2^shift samples (three small kernels,
 // everything stays on the device). The order inside a bucket is whatever the atomics produce;
@@ -1277,7 +1130,6 @@ struct ltp_planner {
   int d_work_dof;
   int solve_mode;  // LTP_SOLVE_AUTO / LTP_SOLVE_GENERIC
   int sm_count;
-  int rows_bulk_ok;  // the shared-memory-staged rows sampler got its dynamic shared memory
   // optional per-kernel timing (ltp_set_profiling): CUDA events recorded on the launching
   // stream directly around the hot kernels, read back by ltp_profile_read
   bool profiling;
@@ -1465,7 +1317,6 @@ int ltp_create(ltp_planner** out, int device, int dof, double t_sample, const do
   p->d_work_dof = 0;
   p->solve_mode = LTP_SOLVE_AUTO;
   p->sm_count = 148;
-  p->rows_bulk_ok = 0;
   p->profiling = false;
   std::memset(p->timed, 0, sizeof p->timed);
   for (int i = 0; i < 2; ++i) {
@@ -1487,9 +1338,6 @@ int ltp_create(ltp_planner** out, int device, int dof, double t_sample, const do
     cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaStreamCreate"); }
     cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
-    constexpr int tile_bytes = LTP_ROWS_NBUF * 4 * 32 * (LTP_ROWS_K + 2) * (int)sizeof(double);
-    p->rows_bulk_ok = cudaFuncSetAttribute(ltp_sample_rows_bulk_kernel<LTP_ROWS_K, LTP_ROWS_NBUF>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, tile_bytes) == cudaSuccess;
   }
   *out = p;
   return LTP_OK;
@@ -1797,23 +1645,6 @@ int ltp_sample_batch(ltp_planner* p, int64_t n, const double* q_0, const double*
   const int ppb = 32 / dof > 0 ? 32 / dof : 1;  // whole problems per one-warp CTA (dof <= 32)
   const unsigned grid = (unsigned)((n + ppb - 1) / ppb);
   const bool vec = (stride % 4 == 0) && aligned32(q) && aligned32(v) && aligned32(a) && aligned32(j);
-  // batches: rows staged through shared memory and written by the bulk copy engine (needs
-  // 16-byte aligned row segments); a handful of rows keeps the direct-store kernel (no set-up)
-  const bool bulk = (stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(v) |
-                                            reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(j)) & 15u) == 0 &&
-                    n * dof >= 1024 && p->rows_bulk_ok && LTP_ROWS_BULK;
-  if (bulk) {
-    LTP_CUDA(cudaMemcpyAsync(success, sol->reached, (size_t)n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    const int64_t rows = n * dof;
-    constexpr size_t tile_bytes = (size_t)LTP_ROWS_NBUF * 4 * 32 * (LTP_ROWS_K + 2) * sizeof(double);
-    ProfScope ps(p, LTP_PROFILE_SAMPLE_ROWS, (cudaStream_t)stream);
-    ltp_sample_rows_bulk_kernel<LTP_ROWS_K, LTP_ROWS_NBUF><<<(unsigned)((rows + 31) / 32), 32, tile_bytes,
-                                                             (cudaStream_t)stream>>>(
-        p->params, n, q_0, v_0, a_0, to_dev(sol), horizon, stride, q, v, a, j, success);
-    p->launches++;
-    LTP_CUDA(cudaGetLastError());
-    return LTP_OK;
-  }
   ProfScope ps(p, LTP_PROFILE_SAMPLE_ROWS, (cudaStream_t)stream);
   if (vec)
     ltp_sample_kernel<true><<<grid, 32, 0, (cudaStream_t)stream>>>(p->params, n, ppb, q_0, v_0, a_0, to_dev(sol),
@@ -1836,9 +1667,9 @@ static const int64_t kHostChunk = 1 << 16;
 int ltp_solve_host(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
                    const double* v_0, const double* a_0, const ltp_solution* hs) {
   if (!p || n < 0 || !q_goal || !q_0 || !v_0 || !a_0 || !hs || p->params.dof < 1) return LTP_ERR_ARG;
-  if (!hs->t_scaled || !hs->dir || !hs->v_drive || !hs->mod || !hs->slowest || !hs->traj_len ||
-      !hs->reached)
-    return LTP_ERR_ARG;
+  // output mask: any field may be NULL and is then not copied back (the transfer out is what
+  // bounds this call); traj_len and reached are always delivered
+  if (!hs->traj_len || !hs->reached) return LTP_ERR_ARG;
   if (n == 0) return LTP_OK;
   if (n > 0x7fffffff) return LTP_ERR_ARG;
   DeviceGuard g(p->device);
@@ -1892,11 +1723,11 @@ int ltp_solve_host(ltp_planner* p, int64_t n, const double* q_goal, const double
 #define LTP_OUT2D(FIELD, ROWS, ELEM)                                                                   \
   LTP_CUDA(cudaMemcpy2DAsync(hs->FIELD + p0, (size_t)n * (ELEM), d.FIELD, (size_t)c * (ELEM),           \
                              (size_t)c * (ELEM), (ROWS), cudaMemcpyDeviceToHost, st))
-    LTP_OUT2D(t_scaled, 7 * dof, 8);
-    LTP_OUT2D(dir, dof, 8);
-    LTP_OUT2D(v_drive, dof, 8);
-    LTP_OUT2D(mod, dof, 1);
-    LTP_OUT2D(slowest, 1, 4);
+    if (hs->t_scaled) LTP_OUT2D(t_scaled, 7 * dof, 8);
+    if (hs->dir) LTP_OUT2D(dir, dof, 8);
+    if (hs->v_drive) LTP_OUT2D(v_drive, dof, 8);
+    if (hs->mod) LTP_OUT2D(mod, dof, 1);
+    if (hs->slowest) LTP_OUT2D(slowest, 1, 4);
     LTP_OUT2D(traj_len, 1, 4);
     LTP_OUT2D(reached, 1, 1);
     if (hs->t_opt) LTP_OUT2D(t_opt, 7 * dof, 8);

@@ -1215,60 +1215,4 @@ struct SegCursorT {
   }
 };
 
-// The same stream with the current piece held in registers: the table is read only where a
-// piece ends (a dozen times per row) instead of once per sample, and Ts * jerk -- the product the
-// reference forms for every sample -- is formed once per piece (same operands, same bits). What
-// is left per sample is the recurrence itself: three dependent additions, two products and the
-// selects of the pinned values, which the compiler can overlap across the samples of an unrolled
-// loop. Same results as SegCursorT::step, bit for bit (tests/test_devmath_host.py).
-template <int ENTRY_STRIDE>
-struct PieceCursorT {
-  double Ts, vcruise, a, v, q;
-  double jv, c;  // jerk of the current piece, Ts * jerk
-  int m, next;
-  bool vc, live;
-
-  LTP_HD void load(const SegTableT<ENTRY_STRIDE>& T) {
-    const double* e = T.base + m * ENTRY_STRIDE;
-#ifdef __CUDA_ARCH__
-    const double2 w = *reinterpret_cast<const double2*>(e);
-    jv = w.x;
-    seg_unpack(w.y, next, vc, live);
-#else
-    jv = e[0];
-    seg_unpack(e[1], next, vc, live);
-#endif
-    c = Ts * jv;
-  }
-
-  LTP_HD void begin(const RowSampler& R, const SegTableT<ENTRY_STRIDE>& T) {
-    Ts = R.Ts; vcruise = R.vcruise; a = R.a; v = R.v; q = R.q;
-    m = 0;
-    load(T);
-  }
-
-  LTP_HD void step(const SegTableT<ENTRY_STRIDE>& T, int i, double& jo, double& ao, double& vo, double& qo) {
-    if (i == next) {  // rare: a piece ends here
-      ++m;
-      load(T);
-    }
-    const double a1 = a + c;
-    a = live ? a1 : 0.0;
-    const double v1 = v + Ts * a;
-    v = vc ? vcruise : (live ? v1 : 0.0);
-    q = q + Ts * v;
-    jo = jv; ao = a; vo = v; qo = q;
-  }
-
-  // see SegCursorT::peek_position; the state before sample i is this cursor's
-  LTP_HD double peek_position(const SegTableT<ENTRY_STRIDE>& T, int i, int end) const {
-    SegCursorT<ENTRY_STRIDE> C;
-    C.Ts = Ts; C.vcruise = vcruise; C.a = a; C.v = v; C.q = q;
-    // (the walk re-reads entry m, or moves on to m + 1 if sample i is where this piece ends)
-    C.m = m;
-    C.next = next;
-    return C.peek_position(T, i, end);
-  }
-};
-
 }  // namespace ltp

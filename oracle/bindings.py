@@ -173,6 +173,7 @@ class Reference(_Base):
     prefix = "ref_"
     libname = "libltp_ref.so"
     kind = "reference"
+    flags = "-O2 -ffp-contract=off"
 
     def build_info(self):
         return self._fn("build_info", C.c_char_p)().decode()
@@ -265,3 +266,10 @@ class Reference(_Base):
         s = self._fn("plan_batch", C.c_double)(self.h, C.c_int64(n), _vp(q_goal), _vp(q_0), _vp(v_0), _vp(a_0),
                                                _vp(ok), _vp(ln), C.c_int(threads))
         return dict(success=ok, length=ln, checksum=s)
+
+
+class ReferenceO0(Reference):
+    """the same sources at the reference's shipped flags (-std=c++17 only, i.e. -O0)"""
+    libname = "libltp_ref_O0.so"
+    kind = "reference"
+    flags = "-O0 (shipped flags, CMakeLists.txt:5)"

@@ -253,37 +253,6 @@ int shadow_get_trajectory(void* h, const double* t7, const double* dir, const un
   return len;
 }
 
-// the register-resident piece cursor (PieceCursorT) the batch samplers use; must reproduce
-// shadow_get_trajectory bit for bit. peek_from >= 0: additionally returns, through peek_out[jt],
-// the closed-form jump from sample peek_from to the end taken from THIS cursor's state.
-int shadow_get_trajectory_piece(void* h, const double* t7, const double* dir, const unsigned char* mod,
-                                const double* q_0, const double* v_0, const double* a_0, const double* v_drive,
-                                int64_t stride, double* q, double* v, double* a, double* j, int peek_from,
-                                double* peek_out) {
-  Shadow* s = static_cast<Shadow*>(h);
-  const int dof = s->dof;
-  int len = 0;
-  for (int i = 0; i < dof; ++i) {
-    int li = samples_for(t7[7 * i + 6], s->ts);
-    len = li > len ? li : len;
-  }
-  if (len > stride) return -len;
-  for (int jt = 0; jt < dof; ++jt) {
-    RowSampler R;
-    R.init(s->ts, s->lim[jt].j_max, t7 + 7 * jt, dir[jt], mod[jt], q_0[jt], v_0[jt], a_0[jt], v_drive[jt], len);
-    alignas(16) double table[2 * kMaxSeg];
-    SegTableT<2> T{table};
-    T.build(R, len, true);
-    PieceCursorT<2> C;
-    C.begin(R, T);
-    for (int i = 0; i < len; ++i) {
-      if (i == peek_from && peek_out) peek_out[jt] = C.peek_position(T, i, len);
-      C.step(T, i, j[jt * stride + i], a[jt * stride + i], v[jt * stride + i], q[jt * stride + i]);
-    }
-  }
-  return len;
-}
-
 // largest |peek_position(i -> len) - q[len-1]| over all joints and a set of start samples i:
 // the closed-form jump the time-major kernel uses for the limit check of clipped rows
 double shadow_peek_error(void* h, const double* t7, const double* dir, const unsigned char* mod,

@@ -162,35 +162,3 @@ def test_device_math_on_random_limit_sets(dof):
     for k in ("t_scaled", "v_drive"):
         assert count_bad(got[k][r], ref[k][r]) == 0, k
 
-
-def test_piece_cursor_equals_per_sample_cursor_and_oracle():
-    """PieceCursorT (current piece in registers, Ts * jerk formed once per piece -- what the batch
-    samplers run) gives the same samples as the per-sample table walk and as the oracle, bit for
-    bit; its closed-form jump to the end of the row starts from the right state"""
-    import ctypes
-    f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
-    u8p = np.ctypeslib.ndpointer(np.uint8, flags="C")
-    for lim, n, seed, kind in ((W.FRANKA7, 60, 241, "random"), (W.REF_RANDOM6, 200, 242, "random"),
-                               (W.FRANKA7, 60, 243, "edge"), (W.random_limits(4, 19), 80, 244, "random")):
-        qg, q0, v0, a0 = W.random_states(lim, n, seed) if kind == "random" else W.edge_states(lim, n, seed)
-        P, S = OraclePort.from_limits(lim), Shadow.from_limits(lim)
-        fn = S.lib.shadow_get_trajectory_piece
-        fn.restype = ctypes.c_int
-        fn.argtypes = [ctypes.c_void_p, f64p, f64p, u8p, f64p, f64p, f64p, f64p, ctypes.c_int64, f64p, f64p, f64p,
-                       f64p, ctypes.c_int, f64p]
-        s = P.solve(qg, q0, v0, a0)
-        for i in range(n):
-            if not s["reached"][i] or s["traj_len"][i] <= 0:
-                continue
-            ref = P.get_trajectory(s["t_scaled"][i], s["dir"][i], s["mod"][i], q0[i], v0[i], a0[i], s["v_drive"][i])
-            ln, stride = ref["length"], ref["q"].shape[1]
-            out = [np.zeros((lim.dof, stride)) for _ in range(4)]
-            peek = np.zeros(lim.dof)
-            start = (i * 37) % ln
-            got = fn(S.h, np.ascontiguousarray(s["t_scaled"][i]), np.ascontiguousarray(s["dir"][i]),
-                     np.ascontiguousarray(s["mod"][i]), np.ascontiguousarray(q0[i]), np.ascontiguousarray(v0[i]),
-                     np.ascontiguousarray(a0[i]), np.ascontiguousarray(s["v_drive"][i]), stride, *out, start, peek)
-            assert got == ln
-            for k, o in zip("qvaj", out):
-                assert bitdiff(o[:, :ln], ref[k][:, :ln]) == 0, (lim.name, i, k)
-            assert np.max(np.abs(peek - ref["q"][:, ln - 1])) < 1e-11, (lim.name, i)

@@ -487,9 +487,8 @@ def test_sorted_slot_sampling_equals_problem_order_sampling(lim, n):
 @pytest.mark.parametrize("lim,n", [(W.FRANKA7, 1024), (W.FRANKA12, 257), (W.random_limits(1, 71), 3000),
                                    (W.random_limits(3, 72), 700), (W.random_limits(17, 73), 130)])
 @pytest.mark.parametrize("mode", ["exact", "fixed_odd", "clipped"])
-def test_rows_layout_through_shared_memory_equals_time_major(lim, n, mode):
-    """batches in the rows layout go through the shared-memory tile + bulk-copy kernel
-    (ltp_sample_rows_bulk_kernel, n * dof >= 1024): same samples, bit for bit, as the time-major
+def test_rows_layout_equals_time_major_on_batches(lim, n, mode):
+    """batches in the rows layout: same samples, bit for bit, as the time-major
     kernel and the oracle -- exact lengths (odd and even), an odd fixed horizon, rows clipped by a
     capacity below their length; problems that were not planned hold their start position in
     fixed-horizon mode and are left alone in exact-length mode"""

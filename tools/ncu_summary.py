@@ -71,7 +71,18 @@ def main(path, json_out=None):
                 "registers": r[hdr.index("launch__registers_per_thread")],
                 "source": "ncu --set full --clock-control none, " + path.split("/")[-1] + " (longest launch of the kernel)"}
     if json_out:
+        # stamp: hash of the kernel sources the capture belongs to (bench.py refuses to quote a
+        # capture of other code) -- so run this right after the capture, before editing csrc/
+        import datetime
+        import hashlib
         import json
+        import os
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        h = hashlib.sha256()
+        for f in ("ltp_b200.cu", "ltp_math.cuh"):
+            h.update(open(os.path.join(root, "longtermplanner_b200", "csrc", f), "rb").read())
+        facts["source_sha"] = h.hexdigest()[:16]
+        facts["captured"] = datetime.date.today().isoformat() + ", " + path.split("/")[-1]
         json.dump(facts, open(json_out, "w"), indent=1)
 
 
