@@ -256,6 +256,13 @@ int ltp_advance_batch(ltp_planner* p, int64_t n, int32_t tick, int32_t clamp, in
                       const int32_t* traj_len, const uint8_t* valid, const double* q, const double* v,
                       const double* a, double* q_0, double* v_0, double* a_0, void* stream);
 
+/* Layout bridge: dst[c][r] = src[r][c] for a rows x cols matrix of doubles on the device
+ * (shared-memory tiled, both sides coalesced). A vectorised environment keeps its state
+ * problem-major, x[problem][joint]; ltp_transpose(p, n, dof, x_pm, x_jm, stream) gives the
+ * joint-major [dof][n] layout the entry points above take, and (p, dof, n, ...) goes back.
+ * (The time-major trajectories already are (samples, n, dof), i.e. problem-major per sample.) */
+int ltp_transpose(ltp_planner* p, int64_t rows, int64_t cols, const double* src, double* dst, void* stream);
+
 /* ---- host-buffer entry points (what a caller without device buffers uses) ------------ */
 
 /* Stages 1-3 with HOST buffers: copies the four inputs in, solves, copies the requested

@@ -40,7 +40,7 @@ EXPORTS = [
     "ltp_create", "ltp_set_limits", "ltp_set_sample_time", "ltp_set_dof", "ltp_set_solve_mode", "ltp_set_stream_sorted", "ltp_set_profiling", "ltp_profile_read", "ltp_get_dof", "ltp_get_device",
     "ltp_destroy", "ltp_status_string", "ltp_last_cuda_error", "ltp_launch_count",
     "ltp_opt_braking_batch", "ltp_opt_switch_times_batch", "ltp_time_scaling_batch", "ltp_reserve", "ltp_solve_batch",
-    "ltp_sample_batch", "ltp_sample_batch_sorted", "ltp_plan_stream", "ltp_advance_batch", "ltp_solve_host", "ltp_plan_host", "ltp_plan_one_view", "ltp_opt_braking_host",
+    "ltp_sample_batch", "ltp_sample_batch_sorted", "ltp_plan_stream", "ltp_advance_batch", "ltp_transpose", "ltp_solve_host", "ltp_plan_host", "ltp_plan_one_view", "ltp_opt_braking_host",
     "ltp_opt_switch_times_host", "ltp_time_scaling_host", "ltp_get_trajectory_host",
 ]
 
@@ -88,6 +88,7 @@ plan_stream = _sig("ltp_plan_stream", C.c_int, vp, i64, vp, vp, vp, vp, i64, i32
                    C.POINTER(StreamStats), vp)
 advance_batch = _sig("ltp_advance_batch", C.c_int, vp, i64, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp)
 reserve = _sig("ltp_reserve", C.c_int, vp, i64)
+transpose = _sig("ltp_transpose", C.c_int, vp, i64, i64, vp, vp, vp)
 solve_host = _sig("ltp_solve_host", C.c_int, vp, i64, vp, vp, vp, vp, C.POINTER(Solution))
 plan_host = _sig("ltp_plan_host", C.c_int, vp, i64, vp, vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, vp,
                  C.POINTER(i64))

@@ -1104,6 +1104,32 @@ ltp_advance_kernel(const __grid_constant__ PlannerParams P, int64_t n, int tick,
 }
 
 
+// ------------------------------------------------------------------------------------
+// Layout bridge for callers that keep their state problem-major, x[problem][joint] -- what a
+// vectorised environment holds (n_env x dof), while the kernels want joint-major x[joint][problem]
+// (one joint of 32 consecutive problems per warp, every access a full 256-byte piece).
+// dst[c][r] = src[r][c] for a rows x cols matrix of doubles, through a 32 x 33 shared tile so
+// that both the reads and the writes are coalesced.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ltp_transpose_kernel(int64_t rows, int64_t cols, int64_t dst_pitch, const double* __restrict__ src,
+                     double* __restrict__ dst) {
+  __shared__ double tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int64_t r = r0 + ty + k, c = c0 + tx;
+    if (r < rows && c < cols) tile[ty + k][tx] = src[r * cols + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int64_t c = c0 + ty + k, r = r0 + tx;
+    if (r < rows && c < cols) dst[c * dst_pitch + r] = tile[tx][ty + k];
+  }
+}
+
 }  // namespace
 
 // ======================================================================================
@@ -1855,6 +1881,27 @@ int ltp_plan_stream(ltp_planner* p, int64_t n, const double* q_goal, const doubl
     stats->chunks = k;
     stats->bytes = h.samples * 32;
   }
+  return LTP_OK;
+}
+
+int ltp_transpose(ltp_planner* p, int64_t rows, int64_t cols, const double* src, double* dst, void* stream) {
+  if (!p || rows < 0 || cols < 0) return LTP_ERR_ARG;
+  if (rows == 0 || cols == 0) return LTP_OK;
+  if (!src || !dst || src == dst) return LTP_ERR_ARG;
+  DeviceGuard g(p->device);
+  const int64_t gx = (cols + 31) / 32, gy = (rows + 31) / 32;
+  if (gx > 0x7fffffff) return LTP_ERR_ARG;
+  // grid.y holds at most 65535 tiles: walk the rows in slabs (a slab of rows of src is contiguous,
+  // its transpose is a block of columns of dst with pitch `rows`)
+  for (int64_t y0 = 0; y0 < gy; y0 += 65535) {
+    const int64_t slab = (gy - y0) < 65535 ? (gy - y0) : 65535;
+    const int64_t r_off = y0 * 32;
+    const int64_t r_cnt = (rows - r_off) < slab * 32 ? (rows - r_off) : slab * 32;
+    ltp_transpose_kernel<<<dim3((unsigned)gx, (unsigned)slab), 256, 0, (cudaStream_t)stream>>>(
+        r_cnt, cols, rows, src + r_off * cols, dst + r_off);
+    p->launches++;
+  }
+  LTP_CUDA(cudaGetLastError());
   return LTP_OK;
 }
 

@@ -75,6 +75,17 @@ class BatchTrajectories:
     order: Optional[torch.Tensor] = None  # [n] i32: slot k holds problem order[k] (sorted-slot sampling)
 
 
+def as_tensor(x) -> torch.Tensor:
+    """a torch tensor, or any DLPack producer (CuPy, JAX, Numba, Warp ... arrays): imported zero-copy.
+    Everything the batched entry points return is a torch CUDA tensor, i.e. itself a DLPack producer
+    (x.__dlpack__()), so results travel the other way without a copy as well."""
+    if isinstance(x, torch.Tensor):
+        return x
+    if hasattr(x, "__dlpack__"):
+        return torch.from_dlpack(x)
+    raise TypeError(f"expected a torch tensor or a DLPack producer, got {type(x).__name__}")
+
+
 class _DevMem:
     """a device allocation owned by someone else, exposed through __cuda_array_interface__ so that
     torch.as_tensor can alias it without copying"""
@@ -253,7 +264,8 @@ class LongTermPlanner:
         return tr
 
     # ---- batched entry points over SoA device buffers --------------------------------------
-    def _chk(self, t: torch.Tensor, n: int, name: str) -> torch.Tensor:
+    def _chk(self, t, n: int, name: str) -> torch.Tensor:
+        t = as_tensor(t)
         if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == (self.dof_, n)):
             raise ValueError(f"{name}: expected contiguous float64 CUDA tensor of shape ({self.dof_}, {n})")
         if t.device.index != self.device:
@@ -262,6 +274,30 @@ class LongTermPlanner:
 
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def transpose(self, x, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[r, c] float64 CUDA matrix -> its transpose [c, r], contiguous (ltp_transpose): the bridge
+        between a vectorised environment's problem-major state [n, dof] and the joint-major
+        [dof, n] layout of the entry points below"""
+        x = as_tensor(x)
+        if not (x.is_cuda and x.dtype == torch.float64 and x.dim() == 2 and x.is_contiguous()):
+            raise ValueError("transpose: expected a contiguous 2-D float64 CUDA tensor")
+        r, c = x.shape
+        if out is None:
+            out = torch.empty(c, r, dtype=torch.float64, device=x.device)
+        elif tuple(out.shape) != (c, r) or not out.is_contiguous() or out.dtype != torch.float64:
+            raise ValueError("transpose: out must be a contiguous float64 tensor of the transposed shape")
+        capi.check(capi.transpose(self._h, r, c, x.data_ptr(), out.data_ptr(), self._stream()), "ltp_transpose")
+        return out
+
+    def planEnvs(self, q_goal, q_0, v_0, a_0, horizon: int = 0, layout: str = "time_major"):
+        """planTrajectories for callers whose state is problem-major: four [n, dof] float64 CUDA tensors
+        (or DLPack producers), e.g. the observation tensors of a vectorised environment. Returns
+        (BatchSolution, BatchTrajectories, joint-major copies of (q_goal, q_0, v_0, a_0)); the
+        time-major trajectories are (samples, n, dof), i.e. already in the caller's layout."""
+        jm = [self.transpose(x) for x in (q_goal, q_0, v_0, a_0)]
+        sol = self.solve(*jm)
+        return sol, self.sample(jm[1], jm[2], jm[3], sol, horizon, layout=layout), jm
 
     def reserve(self, n: int) -> None:
         """allocate the solve scratch for up to n problems now (ltp_reserve), so that no later

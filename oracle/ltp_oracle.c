@@ -270,8 +270,28 @@ static int real_schur(double a[RN][RN], int n) {
   return total <= max_iters;
 }
 
+/* Trace of the polynomials handed to the root finder (single-threaded use: tests and
+ * tools/root_crosscheck.py compare every one of them with LAPACK). Record layout: 8 doubles =
+ * degree, up to 7 coefficients (highest power first, the rest 0). */
+static double* g_trace = 0;
+static int64_t g_trace_cap = 0, g_trace_len = 0;
+void ltpo_trace_roots(double* buf, int64_t capacity) {
+  g_trace = buf;
+  g_trace_cap = capacity;
+  g_trace_len = 0;
+}
+int64_t ltpo_trace_count(void) { return g_trace_len; }
+
 double ltpo_roots(const double* coeffs, int deg, double* re, double* im) {
   const int n = deg;
+  if (g_trace) {
+    if (g_trace_len < g_trace_cap && deg >= 1 && deg <= 6) {
+      double* rec = g_trace + 8 * g_trace_len;
+      rec[0] = (double)deg;
+      for (int i = 0; i < 7; ++i) rec[1 + i] = i <= deg ? coeffs[i] : 0.0;
+    }
+    g_trace_len++;
+  }
   double a[RN][RN];
   double out_re[RN], out_im[RN];
   for (int i = 0; i < n; ++i) { out_re[i] = NAN; out_im[i] = NAN; }

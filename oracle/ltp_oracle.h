@@ -58,6 +58,10 @@ int ltpo_time_scaling(const ltpo_planner* L, int joint, double q_goal, double q_
                       unsigned char* final_case);
 /* roots.h:22-50; coeffs highest power first; returns the smallest real root > 1e-7 or +inf */
 double ltpo_roots(const double* coeffs, int deg, double* re, double* im);
+/* record every polynomial handed to ltpo_roots (8 doubles each: degree, coefficients);
+ * buf = NULL stops. Not thread-safe: trace single-threaded runs only. */
+void ltpo_trace_roots(double* buf, int64_t capacity);
+int64_t ltpo_trace_count(void);
 
 /* item-array forms of the per-joint primitives (joint may be NULL -> joint 0) */
 void ltpo_opt_braking_items(const ltpo_planner* L, int64_t n, const int* joint, const double* v_0,

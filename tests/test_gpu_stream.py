@@ -251,3 +251,72 @@ def test_refined_single_joint_grid_matches_oracle_at_every_point():
     acc = r["pass3_goal_accuracy"]["results"]
     assert acc["optimal"]["max_abs_goal_error"] < 0.02  # the reference's own bar, tests.cc:318
     assert all(acc[k]["max_abs_goal_error"] < 0.02 for k in acc)
+
+
+class _DlpackOnly:
+    """a producer that is NOT a torch tensor: only the DLPack protocol (what CuPy / JAX arrays offer)"""
+
+    def __init__(self, t):
+        self._t = t
+
+    def __dlpack__(self, stream=None):
+        return self._t.__dlpack__(stream=stream) if stream is not None else self._t.__dlpack__()
+
+    def __dlpack_device__(self):
+        return self._t.__dlpack_device__()
+
+
+def test_problem_major_and_dlpack_inputs_on_a_side_stream_match_the_oracle():
+    """the binding a vectorised environment uses: [n, dof] state, any DLPack producer, the caller's
+    current (non-default) stream -- inputs are still being written by a kernel on that stream when
+    the planner is called; results equal the joint-major path bit for bit and the oracle"""
+    lim, n, H = W.FRANKA7, 3000, 300
+    ltp = _planner(lim)
+    qg, q0, v0, a0 = W.random_states(lim, n, 91)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        # produced on the side stream right before the call (no synchronisation in between)
+        pm = [torch.from_numpy(np.ascontiguousarray(x)).cuda(non_blocking=True) for x in (qg, q0, v0, a0)]
+        pm = [(t * 2.0) * 0.5 for t in pm]
+        sol, traj, jm_in = ltp.planEnvs(*[_DlpackOnly(t) for t in pm], horizon=H)
+        stats_q = traj.q.sum(dim=0)          # consumer on the same stream
+    side.synchronize()
+    ref_jm = [torch.from_numpy(jm(x)).cuda() for x in (qg, q0, v0, a0)]
+    for a, b in zip(jm_in, ref_jm):
+        assert torch.equal(a, b)
+    sol2 = ltp.solve(*ref_jm)
+    traj2 = ltp.sample(ref_jm[1], ref_jm[2], ref_jm[3], sol2, horizon=H)
+    torch.cuda.synchronize()
+    assert torch.equal(sol.t_scaled, sol2.t_scaled) and torch.equal(sol.traj_len, sol2.traj_len)
+    for k in "qvaj":
+        assert torch.equal(getattr(traj, k), getattr(traj2, k)), k
+    assert torch.equal(stats_q, traj2.q.sum(dim=0))
+    ref = OraclePort.from_limits(lim).solve(qg, q0, v0, a0, threads=4)
+    assert np.array_equal(sol.traj_len.cpu().numpy(), ref["traj_len"])
+    assert count_bad(sol.t_scaled.cpu().numpy().transpose(2, 1, 0), ref["t_scaled"]) == 0
+    # the outputs are DLPack producers themselves (zero copy out)
+    back = torch.from_dlpack(traj.q)
+    assert back.data_ptr() == traj.q.data_ptr()
+    # transpose round trip, odd shapes
+    x = torch.randn(1237, 7, dtype=torch.float64, device="cuda")
+    assert torch.equal(ltp.transpose(ltp.transpose(x)), x) and torch.equal(ltp.transpose(x), x.t().contiguous())
+
+
+def test_env_batch_replans_in_the_callers_layout():
+    from longtermplanner_b200 import EnvBatch
+    lim, n, H, tick = W.FRANKA7, 512, 200, 9
+    ltp = _planner(lim)
+    qg, q0, v0, a0 = W.random_states(lim, n, 93)
+    envs = EnvBatch(ltp, *[torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (q0, v0, a0)])
+    state_jm = [torch.from_numpy(jm(x)).cuda() for x in (q0, v0, a0)]
+    for step in range(4):
+        goal = W.random_states(lim, n, 200 + step)[0]
+        traj = envs.replan(torch.from_numpy(np.ascontiguousarray(goal)).cuda(), H)
+        sol = ltp.solve(torch.from_numpy(jm(goal)).cuda(), *state_jm)
+        ref = ltp.sample(*state_jm, sol, horizon=H)
+        torch.cuda.synchronize()
+        assert traj.q.shape == (H, n, lim.dof) and torch.equal(traj.q, ref.q) and torch.equal(traj.j, ref.j)
+        envs.advance(tick)
+        ltp.advance(ref, tick, *state_jm, valid=sol.reached)
+        q_pm, v_pm, a_pm = envs.state()
+        assert torch.equal(q_pm, state_jm[0].t().contiguous()) and torch.equal(a_pm, state_jm[2].t().contiguous())
