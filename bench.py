@@ -361,12 +361,12 @@ def generic_section(LongTermPlanner, local, dev, steps, cores):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
         ltp6.setProfiling(True)
-        for k in ("solve_fast", "solve_attempt2", "solve_generic"):
+        for k in ("solve_fast", "solve_attempt2", "solve_items", "solve_generic"):
             ltp6.kernelTime(k)
         for _ in range(steps):
             ltp6.solve(*ins, out=sol)
         kern = {}
-        for k in ("solve_fast", "solve_attempt2", "solve_generic"):
+        for k in ("solve_fast", "solve_attempt2", "solve_items", "solve_generic"):
             k_ms, k_cnt = ltp6.kernelTime(k)
             kern[k] = k_ms / max(k_cnt, 1)
         ltp6.setProfiling(False)
@@ -606,7 +606,7 @@ def main():
     for k in range(args.steps):
         ltp.solve(*dev_in, out=sol)
     per_kernel = {}
-    for kname in ("solve_fast", "solve_attempt2", "solve_generic"):
+    for kname in ("solve_fast", "solve_attempt2", "solve_items", "solve_generic"):
         k_ms, k_cnt = ltp.kernelTime(kname)
         per_kernel[kname] = k_ms / max(k_cnt, 1)
     ltp.setProfiling(False)

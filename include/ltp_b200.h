@@ -73,7 +73,8 @@ int ltp_set_solve_mode(ltp_planner* p, int mode);
 #define LTP_PROFILE_SAMPLE_TIME_MAJOR 2
 #define LTP_PROFILE_SAMPLE_ROWS 3
 #define LTP_PROFILE_SOLVE_ATTEMPT2 4  /* second candidate for the queued joints */
-#define LTP_PROFILE_KERNELS 5
+#define LTP_PROFILE_SOLVE_ITEMS 5     /* tail + pending + search kernels (item mode, large batches) */
+#define LTP_PROFILE_KERNELS 6
 int ltp_set_profiling(ltp_planner* p, int on);
 int ltp_profile_read(ltp_planner* p, int kernel, double* ms_sum, int64_t* launches, int reset);
 int ltp_get_dof(const ltp_planner* p);

@@ -75,17 +75,19 @@ struct Attempt2Queue {
 };
 
 constexpr int kDeferredMark = 0x7fffffff;  // traj_len of a problem that sits in the work list
+constexpr int64_t kItemModeMin = 8192;     // problems from which the solve runs in item mode
 
 struct SolveShared {
   double* t6;            // [dof][32]
   int* len;              // [dof][32]
   int* arrived;          // [32]
   int* warp_items;       // [dof + 2]   queued joints per warp, then their total and queue base
+  int* tail_items;       // [dof + 2]   the same for the tail items
   unsigned char* flag;   // [dof][32]  bit0 fail, bit1 defer
 };
 
 __host__ __device__ inline size_t solve_smem_bytes(int dof) {
-  return (size_t)dof * kTile * (sizeof(double) + sizeof(int) + 1) + (kTile + dof + 2) * sizeof(int);
+  return (size_t)dof * kTile * (sizeof(double) + sizeof(int) + 1) + (kTile + 2 * (dof + 2)) * sizeof(int);
 }
 
 __device__ __forceinline__ SolveShared carve_shared(unsigned char* raw, int dof) {
@@ -94,37 +96,61 @@ __device__ __forceinline__ SolveShared carve_shared(unsigned char* raw, int dof)
   s.len = reinterpret_cast<int*>(s.t6 + dof * kTile);
   s.arrived = s.len + dof * kTile;
   s.warp_items = s.arrived + kTile;
-  s.flag = reinterpret_cast<unsigned char*>(s.warp_items + dof + 2);
+  s.tail_items = s.warp_items + dof + 2;
+  s.flag = reinterpret_cast<unsigned char*>(s.tail_items + dof + 2);
   return s;
 }
 
-// Device scratch of one solve: [0] work-list length, [1] attempt-2 queue length, then the
-// work list (n problem indices) and the queue (at most (dof - 1) * n entries).
+// Device scratch of one solve. counters: [0] whole-problem work list, [1] attempt-2 queue,
+// [2] tail items, [3] tail-pending problems, [4] search items. Lists:
+//   work_list   problems the every-branch kernel recomputes as a whole (n ints)
+//   queue       joints whose first cruise-speed candidate was rejected ((dof - 1) * n entries)
+//   tail_items  (problem, joint) pairs whose time-optimal solve needs the quartic tail (dof * n)
+//   pending     problems with at least one tail item: their stages 2-3 wait for it (n ints)
+//   search_*    (problem, joint) pairs whose search needs a polynomial root, with the required
+//               end time (dof * n)
 struct SolveScratch {
   int* counters;
   int* work_list;
   Attempt2Queue queue;
+  int2* tail_items;
+  int* pending;
+  int2* search_items;
+  double* search_t_req;
 };
+enum { kCntWork = 0, kCntQueue = 1, kCntTail = 2, kCntPending = 3, kCntSearch = 4, kCounters = 8 };
+
+inline size_t round16(size_t x) { return (x + 15) / 16 * 16; }
 
 inline size_t solve_scratch_bytes(int dof, int64_t n) {
-  const size_t lists = 16 + (((size_t)n * sizeof(int) + 15) / 16) * 16;
   const size_t cap = (size_t)(dof > 1 ? dof - 1 : 0) * (size_t)n;
-  return lists + cap * (5 * sizeof(double) + sizeof(int2));
+  const size_t dn = (size_t)dof * (size_t)n;
+  return 32 + 2 * round16((size_t)n * sizeof(int)) + cap * (5 * sizeof(double) + sizeof(int2)) +
+         dn * (2 * sizeof(int2) + sizeof(double));
 }
 
 inline SolveScratch carve_scratch(void* base, int dof, int64_t n) {
   SolveScratch s;
   unsigned char* b = static_cast<unsigned char*>(base);
-  s.counters = reinterpret_cast<int*>(b);
-  s.work_list = reinterpret_cast<int*>(b + 16);
   const size_t cap = (size_t)(dof > 1 ? dof - 1 : 0) * (size_t)n;
-  double* q = reinterpret_cast<double*>(b + 16 + (((size_t)n * sizeof(int) + 15) / 16) * 16);
+  const size_t dn = (size_t)dof * (size_t)n;
+  s.counters = reinterpret_cast<int*>(b);
+  b += 32;
+  s.work_list = reinterpret_cast<int*>(b);
+  b += round16((size_t)n * sizeof(int));
+  s.pending = reinterpret_cast<int*>(b);
+  b += round16((size_t)n * sizeof(int));
+  double* q = reinterpret_cast<double*>(b);
   s.queue.t_req = q;
   s.queue.q_goal = q + cap;
   s.queue.q_0 = q + 2 * cap;
   s.queue.v_0 = q + 3 * cap;
   s.queue.a_0 = q + 4 * cap;
-  s.queue.where = reinterpret_cast<int2*>(q + 5 * cap);
+  s.search_t_req = q + 5 * cap;
+  int2* w = reinterpret_cast<int2*>(q + 5 * cap + dn);
+  s.queue.where = w;
+  s.tail_items = w + cap;
+  s.search_items = w + cap + dn;
   return s;
 }
 
@@ -172,12 +198,14 @@ __device__ __forceinline__ int joint_samples(const double* t_sc, double Ts) {
 // The last of a problem's dof threads to get here reduces the per-joint lengths and writes
 // the per-problem outputs; no CTA-wide barrier, so a warp that is still busy with a slow
 // joint does not hold the others back. Returns true in that last thread if the problem
-// must be appended to the work list.
+// must be appended to the whole-problem work list.
+// tail_pending (item mode): a joint of the problem waits for its quartic tail; stages 2-3 of the
+// whole problem are redone by ltp_solve_pending_kernel, nothing is decided here.
 __device__ __forceinline__ bool finish_problem(const SolveShared& sh, const DeviceSolution& S, int dof,
                                                int lane, int jt, int64_t p, int my_len, bool my_defer,
-                                               bool reached, int slowest) {
+                                               bool reached, int slowest, bool tail_pending = false) {
   sh.len[jt * kTile + lane] = my_len;
-  if (my_defer) sh.flag[jt * kTile + lane] |= 2;
+  if (my_defer) sh.flag[jt * kTile + lane] |= 4;
   __threadfence_block();
   const int prev = atomicAdd(&sh.arrived[lane], 1);
   if (prev != dof - 1) return false;
@@ -188,12 +216,45 @@ __device__ __forceinline__ bool finish_problem(const SolveShared& sh, const Devi
     const int li = sh.len[i * kTile + lane];
     bad |= li < 0;
     len = li > len ? li : len;
-    defer |= (sh.flag[i * kTile + lane] & 2) != 0;
+    defer |= (sh.flag[i * kTile + lane] & 4) != 0;
   }
   S.slowest[p] = slowest;
-  S.traj_len[p] = defer ? kDeferredMark : ((reached && !bad) ? len : 0);
   S.reached[p] = (uint8_t)reached;
+  if (tail_pending) {
+    S.traj_len[p] = 0;
+    return false;
+  }
+  S.traj_len[p] = defer ? kDeferredMark : ((reached && !bad) ? len : 0);
   return defer;
+}
+
+// Item mode (large batches): what cannot be settled in closed form is handed on per (problem,
+// joint), so that the kernels that run the root finder do so on full warps of joints that all
+// need it -- the every-branch kernel run on whole problems keeps 4 of 32 lanes busy on the
+// reference's test limits (ncu: 4.1 active threads per instruction, 9 ms for the 22 % of 2^20
+// problems that reach it).
+//   tail item    the joint's time-optimal solve needs the quartic tail (cc:245-337)
+//                -> ltp_solve_tail_kernel computes it; the problem waits in `pending`
+//   pending      -> ltp_solve_pending_kernel: stages 2-3 of those problems, closed form
+//   search item  the joint's cruise-speed search needs candidates 3..8 (cc:449-644) or a nested
+//                solve with a tail -> ltp_solve_search_kernel, one thread per joint
+// Only a problem with a non-finite switching time still goes to the whole-problem list.
+__device__ __forceinline__ void push_search_item(const SolveScratch& X, int64_t p, int jt, double t_req) {
+  const int e = atomicAdd(X.counters + kCntSearch, 1);
+  X.search_items[e] = make_int2((int)p, jt);
+  X.search_t_req[e] = t_req;
+}
+
+__device__ __forceinline__ void push_whole_problem(const DeviceSolution& S, const SolveScratch& X, int64_t p) {
+  if (atomicExch(S.traj_len + p, kDeferredMark) != kDeferredMark) {
+    const int slot = atomicAdd(X.counters + kCntWork, 1);
+    X.work_list[slot] = (int)p;
+  }
+}
+
+// what the tail kernel leaves for the pending kernel in v_drive: mod, opt_case, "solve succeeded"
+__device__ __forceinline__ double pack_tail_flags(unsigned mod, unsigned opt_case, unsigned ok) {
+  return __longlong_as_double((long long)((mod & 255u) | ((opt_case & 255u) << 8) | ((ok & 1u) << 16)));
 }
 
 // Register budget: the kernel is bound by FP64 dependency latency, so it is compiled for
@@ -210,12 +271,12 @@ template <int MAXW>
 __global__ void __launch_bounds__(kTile * MAXW, fast_min_blocks(MAXW))
 ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_goal,
                       const double* __restrict__ q_0, const double* __restrict__ v_0,
-                      const double* __restrict__ a_0, DeviceSolution S, SolveScratch X) {
+                      const double* __restrict__ a_0, DeviceSolution S, SolveScratch X, int items) {
   extern __shared__ unsigned char smem_raw[];
   const int dof = P.dof;
   const SolveShared sh = carve_shared(smem_raw, dof);
   int* const work_list = X.work_list;
-  int* const work_count = X.counters;
+  int* const work_count = X.counters + kCntWork;
   const int lane = threadIdx.x, jt = threadIdx.y;
   const int64_t p = (int64_t)blockIdx.x * kTile + lane;
   const bool valid = p < n;
@@ -237,7 +298,10 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
   const int st1 = ost_body_t<false>(L, Ts, pro, qg, q0, L.v_max, t_opt, mod, opt_case);
   sh.t6[jt * kTile + lane] = t_opt[6];
   sh.flag[jt * kTile + lane] = (unsigned char)((!(in_ok && st1 != OST_FAIL) ? 1 : 0) | (st1 == OST_DEFER ? 2 : 0));
-  __syncthreads();
+  // item mode: the joints that need the quartic tail are listed below; the barrier that stage 2
+  // needs anyway tells every thread whether the CTA has any (none for realistic limits)
+  const bool tail_item = items && valid && st1 == OST_DEFER;
+  const int cta_has_tail = __syncthreads_or(tail_item);
   // stage 2 (cc:31-39): strict '>' so the lowest joint index wins ties, NaN never wins
   double t_req = -1;
   int slowest = -1;
@@ -253,6 +317,29 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
   // a joint that needs the quartic tail has no t_opt yet: the whole problem is deferred
   const bool defer1 = (any & 2) != 0;
   const bool reached = !(any & 1) && slowest != -1;
+  if (cta_has_tail) {  // uniform over the CTA
+    // tail items: slot = base of this CTA (one atomic per CTA) + items of the warps before mine +
+    // those of the lanes before mine; the problems that wait for them (every warp sees the same
+    // set; warp 0 lists them)
+    const unsigned tail_mask = __ballot_sync(0xffffffffu, tail_item);
+    const unsigned pend = __ballot_sync(0xffffffffu, defer1 && valid);
+    if (lane == 0) sh.tail_items[jt] = __popc(tail_mask);
+    __syncthreads();
+    int t_before = 0, t_total = 0;
+    for (int w = 0; w < dof; ++w) {
+      const int c = sh.tail_items[w];
+      t_before += (w < jt) ? c : 0;
+      t_total += c;
+    }
+    if (jt == 0 && lane == 0) {
+      sh.tail_items[dof] = atomicAdd(X.counters + kCntTail, t_total);
+      sh.tail_items[dof + 1] = atomicAdd(X.counters + kCntPending, __popc(pend));
+    }
+    __syncthreads();
+    const unsigned below = (1u << lane) - 1u;
+    if (tail_item) X.tail_items[sh.tail_items[dof] + t_before + __popc(tail_mask & below)] = make_int2((int)p, jt);
+    if (jt == 0 && ((pend >> lane) & 1u)) X.pending[sh.tail_items[dof + 1] + __popc(pend & below)] = (int)p;
+  }
   // stage 3 (cc:42-55), closed-form attempts only. Attempt 1 runs here; the joints it does
   // not settle (about a third) are queued for ltp_solve_attempt2_kernel, which runs attempt 2
   // on full warps of such joints ("grouped by case").
@@ -270,6 +357,7 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
       const int c = time_scaling_attempt1(L, Ts, pro, I, t_sc, v_drive, mod, final_case);
       my_defer = (c == 0);
       need2 = (c == -1) && valid;
+      if (items && my_defer && valid) push_search_item(X, p, jt, t_req);  // rare: a nested solve with a tail
       ts_case = (unsigned char)c;
       if (c == 9) final_case = opt_case;
     }
@@ -296,7 +384,7 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
     total += c;
   }
   if (total > 0) {  // uniform over the CTA
-    if (jt == 0 && lane == 0) sh.warp_items[dof + 1] = atomicAdd(X.counters + 1, total);
+    if (jt == 0 && lane == 0) sh.warp_items[dof + 1] = atomicAdd(X.counters + kCntQueue, total);
     __syncthreads();
     if (need2) {
       const int e = sh.warp_items[dof + 1] + before + __popc(need_mask & ((1u << lane) - 1u));
@@ -312,11 +400,14 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
   store_joint_opt(S, dof, jt, n, p, t_opt, pro.dir, opt_case);
   // a queued joint contributes length 0 here; its length arrives by atomicMax later
   const int my_len = (reached && !defer1 && !my_defer && !need2) ? joint_samples(t_sc, Ts) : 0;
-  if (finish_problem(sh, S, dof, lane, jt, p, my_len, my_defer, reached, slowest)) {
+  // legacy mode: a joint that is not settled here sends its whole problem to the every-branch
+  // kernel; item mode: only a non-finite time does (the joint itself is listed as an item)
+  const bool whole = items ? (my_len < 0) : (my_defer || defer1);
+  if (finish_problem(sh, S, dof, lane, jt, p, my_len, whole, reached, slowest, items && defer1)) {
     const int slot = atomicAdd(work_count, 1);
     work_list[slot] = (int)p;
   }
-  if (!need2) store_joint_scaled(S, dof, jt, n, p, t_sc, v_drive, mod, ts_case, final_case);
+  if (!need2 && !(items && my_defer)) store_joint_scaled(S, dof, jt, n, p, t_sc, v_drive, mod, ts_case, final_case);
 }
 
 // Attempt 2 of the cruise-speed search (reference cc:408-446) for the queued joints: one
@@ -333,10 +424,11 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
 #define LTP_A2_MINB 2
 #endif
 __global__ void __launch_bounds__(256, LTP_A2_MINB)
-ltp_solve_attempt2_kernel(const __grid_constant__ PlannerParams P, int64_t n, DeviceSolution S, SolveScratch X) {
+ltp_solve_attempt2_kernel(const __grid_constant__ PlannerParams P, int64_t n, DeviceSolution S, SolveScratch X,
+                          int items) {
   const int dof = P.dof;
   const double Ts = P.ts;
-  const int count = X.counters[1];
+  const int count = X.counters[kCntQueue];
   const int step = gridDim.x * blockDim.x;
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= count) return;
@@ -374,12 +466,12 @@ ltp_solve_attempt2_kernel(const __grid_constant__ PlannerParams P, int64_t n, De
       if (m < t[k]) m = t[k];
     // an accepted solve with no positive time falls back to the time-optimal times (cc:50-55),
     // which are not at hand here: that (degenerate) problem goes to the generic kernel too
-    const int len = (c == 0 || m <= 0.0) ? -1 : joint_samples(t, Ts);
-    if (len < 0) {
-      if (atomicExch(S.traj_len + p, kDeferredMark) != kDeferredMark) {
-        const int slot = atomicAdd(X.counters, 1);
-        X.work_list[slot] = (int)p;
-      }
+    const bool open = (c == 0 || m <= 0.0);
+    const int len = open ? -1 : joint_samples(t, Ts);
+    if (items && open) {
+      push_search_item(X, p, jt, t_req);  // candidates 3..8 (or the fallback) for this joint alone
+    } else if (len < 0) {
+      push_whole_problem(S, X, p);
     } else {
       store_joint_scaled(S, dof, jt, n, p, t, v_drive, mod, (unsigned char)c, final_case);
       atomicMax(S.traj_len + p, len);
@@ -388,6 +480,182 @@ ltp_solve_attempt2_kernel(const __grid_constant__ PlannerParams P, int64_t n, De
     e = en;
     where = where_n;
     t_req = t_req_n; qg = qg_n; q0 = q0_n; v0 = v0_n; a0 = a0_n;
+  }
+}
+
+// Tail items: the time-optimal solve of one (problem, joint) including the quartic tail
+// (cc:245-337, one or two quartic root solves), one thread per item -- every lane of a warp runs
+// the root finder. The result is parked in the joint's t_scaled / v_drive entries (which the
+// pending kernel overwrites with the final values) and in dir / t_opt / opt_case.
+__global__ void __launch_bounds__(128)
+ltp_solve_tail_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_goal,
+                      const double* __restrict__ q_0, const double* __restrict__ v_0,
+                      const double* __restrict__ a_0, DeviceSolution S, SolveScratch X) {
+  const int dof = P.dof;
+  const int count = X.counters[kCntTail];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+    const int2 w = X.tail_items[e];
+    const int64_t p = w.x;
+    const int jt = w.y;
+    const JointLimits L = P.lim[jt];
+    const int64_t at = (int64_t)jt * n + p;
+    const double qg = q_goal[at], q0 = q_0[at];
+    const Prologue pro = ost_prologue(L, P.ts, qg, q0, v_0[at], a_0[at]);
+    double t_opt[7];
+    zero7(t_opt);
+    unsigned char mod = 0, opt_case = 255;
+    const bool ok = ost_body(L, P.ts, pro, qg, q0, L.v_max, t_opt, mod, opt_case);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) S.t_scaled[((int64_t)k * dof + jt) * n + p] = t_opt[k];
+    S.v_drive[at] = pack_tail_flags(mod, opt_case, ok ? 1u : 0u);
+    store_joint_opt(S, dof, jt, n, p, t_opt, pro.dir, opt_case);
+  }
+}
+
+// Pending problems: stages 2 and 3 of the problems that waited for a tail, same mapping as the
+// closed-form kernel (32 problems x dof joints per CTA, grid-stride over the pending list). The
+// tail joints read their time-optimal solve back; the search runs its two closed-form candidates
+// (cc:378-446); a joint they do not settle becomes a search item.
+template <int MAXW>
+__global__ void __launch_bounds__(kTile * MAXW, MAXW <= 8 ? 2 : 1)
+ltp_solve_pending_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_goal,
+                         const double* __restrict__ q_0, const double* __restrict__ v_0,
+                         const double* __restrict__ a_0, DeviceSolution S, SolveScratch X) {
+  extern __shared__ unsigned char smem_raw[];
+  const int dof = P.dof;
+  const SolveShared sh = carve_shared(smem_raw, dof);
+  const int lane = threadIdx.x, jt = threadIdx.y;
+  const JointLimits L = P.lim[jt];
+  const double Ts = P.ts;
+  const int64_t count = X.counters[kCntPending];
+  for (int64_t tile = blockIdx.x; tile * kTile < count; tile += gridDim.x) {
+    const int64_t w = tile * kTile + lane;
+    const bool valid = w < count;
+    const int64_t p = valid ? (int64_t)X.pending[w] : 0;
+    const int64_t at = (int64_t)jt * n + p;
+    double qg = 0, q0 = 0, v0 = 0, a0 = 0;
+    if (valid) {
+      qg = q_goal[at]; q0 = q_0[at]; v0 = v_0[at]; a0 = a_0[at];
+    }
+    if (jt == 0) sh.arrived[lane] = 0;
+    // stage 1 again (cc:14-30), the tail joints from what ltp_solve_tail_kernel left
+    const bool in_ok = check_joint_input(L, q0, v0, a0);
+    const Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0);
+    double t_opt[7];
+    zero7(t_opt);
+    unsigned char mod = 0, opt_case = 255;
+    const int st1 = ost_body_t<false>(L, Ts, pro, qg, q0, L.v_max, t_opt, mod, opt_case);
+    bool ost_ok = st1 == OST_OK;
+    if (st1 == OST_DEFER && valid) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) t_opt[k] = S.t_scaled[((int64_t)k * dof + jt) * n + p];
+      const unsigned f = (unsigned)__double2loint(S.v_drive[at]);
+      mod = (unsigned char)(f & 255u);
+      opt_case = (unsigned char)((f >> 8) & 255u);
+      ost_ok = ((f >> 16) & 1u) != 0;
+    }
+    sh.t6[jt * kTile + lane] = t_opt[6];
+    sh.flag[jt * kTile + lane] = (unsigned char)(!(in_ok && ost_ok));
+    __syncthreads();
+    // stage 2 (cc:31-39)
+    double t_req = -1;
+    int slowest = -1;
+    bool any_fail = false;
+    for (int i = 0; i < dof; ++i) {
+      any_fail |= (sh.flag[i * kTile + lane] & 1) != 0;
+      const double ti = sh.t6[i * kTile + lane];
+      if (ti > t_req) {
+        t_req = ti;
+        slowest = i;
+      }
+    }
+    const bool reached = !any_fail && slowest != -1;
+    // stage 3 (cc:42-55), closed-form candidates
+    double t_sc[7];
+    zero7(t_sc);
+    double v_drive = L.v_max;
+    unsigned char ts_case = 255, final_case = 255;
+    bool open = false;
+    if (reached) {
+      if (jt == slowest) {
+        ts_case = 0;
+        final_case = opt_case;
+      } else {
+        const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
+        const int c = time_scaling_closed_form(L, Ts, pro, I, t_sc, v_drive, mod, final_case);
+        open = c == 0;
+        ts_case = (unsigned char)c;
+        if (c == 9) final_case = opt_case;
+      }
+      double m = t_sc[0];
+#pragma unroll
+      for (int k = 1; k < 7; ++k)
+        if (m < t_sc[k]) m = t_sc[k];
+      if (m <= 0.0) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t_sc[k] = t_opt[k];
+      }
+    }
+    if (valid) {
+      if (open) push_search_item(X, p, jt, t_req);
+      const int my_len = (reached && !open) ? joint_samples(t_sc, Ts) : 0;
+      if (finish_problem(sh, S, dof, lane, jt, p, my_len, my_len < 0, reached, slowest)) {
+        const int slot = atomicAdd(X.counters + kCntWork, 1);
+        X.work_list[slot] = (int)p;
+      }
+      if (!open) store_joint_scaled(S, dof, jt, n, p, t_sc, v_drive, mod, ts_case, final_case);  // else: search kernel
+    }
+    __syncthreads();  // shared arrays are reused by the next tile
+  }
+}
+
+// Search items: the whole cruise-speed search (cc:358-645) of one (problem, joint) whose two
+// closed-form candidates did not settle it, one thread per item -- full warps of joints that all
+// go on to the root-finder candidates. The result joins the problem like in the attempt-2 kernel.
+__global__ void __launch_bounds__(128)
+ltp_solve_search_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_goal,
+                        const double* __restrict__ q_0, const double* __restrict__ v_0,
+                        const double* __restrict__ a_0, DeviceSolution S, SolveScratch X) {
+  const int dof = P.dof;
+  const double Ts = P.ts;
+  const int count = X.counters[kCntSearch];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+    const int2 w = X.search_items[e];
+    const double t_req = X.search_t_req[e];
+    const int64_t p = w.x;
+    const int jt = w.y;
+    const JointLimits L = P.lim[jt];
+    const int64_t at = (int64_t)jt * n + p;
+    const double qg = q_goal[at], q0 = q_0[at], v0 = v_0[at], a0 = a_0[at];
+    const Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0);
+    // the joint's time-optimal solve again: its case byte and times are what a failed search
+    // (cc:641-644) and the cc:50-55 fallback report
+    double t_opt[7];
+    zero7(t_opt);
+    unsigned char mod = 0, opt_case = 255;
+    ost_body(L, Ts, pro, qg, q0, L.v_max, t_opt, mod, opt_case);
+    const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
+    double t_sc[7];
+    zero7(t_sc);
+    double v_drive = L.v_max;
+    unsigned char final_case = 255;
+    const unsigned char ts_case = (unsigned char)time_scaling_from(1, L, Ts, pro, I, t_sc, v_drive, mod, final_case);
+    if (ts_case == 9) final_case = opt_case;
+    double m = t_sc[0];
+#pragma unroll
+    for (int k = 1; k < 7; ++k)
+      if (m < t_sc[k]) m = t_sc[k];
+    if (m <= 0.0) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) t_sc[k] = t_opt[k];
+    }
+    const int len = joint_samples(t_sc, Ts);
+    if (len < 0) {
+      push_whole_problem(S, X, p);
+    } else {
+      store_joint_scaled(S, dof, jt, n, p, t_sc, v_drive, mod, ts_case, final_case);
+      atomicMax(S.traj_len + p, len);
+    }
   }
 }
 
@@ -1530,10 +1798,13 @@ static int solve_launch(ltp_planner* p, int64_t n, const double* q_goal, const d
     LTP_DISPATCH_W(ltp_solve_generic_kernel, tiles, p->params, n, q_goal, q_0, v_0, a_0, ds,
                    (const int*)nullptr, (const int*)nullptr);
   } else {
-    LTP_CUDA(cudaMemsetAsync(X.counters, 0, 2 * sizeof(int), st));
+    LTP_CUDA(cudaMemsetAsync(X.counters, 0, kCounters * sizeof(int), st));
+    // large batches hand unsettled joints on one by one (item mode); a small batch is a handful of
+    // CTAs whichever way it is run and keeps the three-launch sequence
+    const int items = n >= kItemModeMin ? 1 : 0;
     {
       ProfScope ps(p, LTP_PROFILE_SOLVE_FAST, st);
-      LTP_DISPATCH_FAST(tiles, p->params, n, q_goal, q_0, v_0, a_0, ds, X);
+      LTP_DISPATCH_FAST(tiles, p->params, n, q_goal, q_0, v_0, a_0, ds, X, items);
     }
     // the queue and the work list are drained by fixed-size grid-stride launches: their
     // lengths never leave the device
@@ -1541,13 +1812,23 @@ static int solve_launch(ltp_planner* p, int64_t n, const double* q_goal, const d
       ProfScope ps(p, LTP_PROFILE_SOLVE_ATTEMPT2, st);
       const int64_t want = ((int64_t)(dof - 1) * n + 255) / 256;
       const int64_t cap = (int64_t)p->sm_count * 16;
-      ltp_solve_attempt2_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(p->params, n, ds, X);
+      ltp_solve_attempt2_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(p->params, n, ds, X, items);
       p->launches++;
+    }
+    if (items) {
+      // list lengths never leave the device: fixed-size grid-stride launches
+      ProfScope ps(p, LTP_PROFILE_SOLVE_ITEMS, st);
+      const unsigned gi = (unsigned)(p->sm_count * 3);
+      ltp_solve_tail_kernel<<<gi, 128, 0, st>>>(p->params, n, q_goal, q_0, v_0, a_0, ds, X);
+      const unsigned gp = tiles < (unsigned)(p->sm_count * 2) ? tiles : (unsigned)(p->sm_count * 2);
+      LTP_DISPATCH_W(ltp_solve_pending_kernel, gp, p->params, n, q_goal, q_0, v_0, a_0, ds, X);
+      ltp_solve_search_kernel<<<gi, 128, 0, st>>>(p->params, n, q_goal, q_0, v_0, a_0, ds, X);
+      p->launches += 2;
     }
     const unsigned g2 = tiles < (unsigned)(p->sm_count * 4) ? tiles : (unsigned)(p->sm_count * 4);
     ProfScope ps(p, LTP_PROFILE_SOLVE_GENERIC, st);
     LTP_DISPATCH_W(ltp_solve_generic_kernel, g2, p->params, n, q_goal, q_0, v_0, a_0, ds,
-                   (const int*)X.work_list, (const int*)X.counters);
+                   (const int*)X.work_list, (const int*)(X.counters + kCntWork));
   }
 #undef LTP_DISPATCH_FAST
 #undef LTP_DISPATCH_W

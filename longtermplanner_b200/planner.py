@@ -144,7 +144,8 @@ class LongTermPlanner:
         """validation switch: run every problem through the generic kernel (same results)"""
         capi.check(capi.set_solve_mode(self._h, 1 if generic_only else 0), "ltp_set_solve_mode")
 
-    KERNELS = {"solve_fast": 0, "solve_generic": 1, "sample_time_major": 2, "sample_rows": 3, "solve_attempt2": 4}
+    KERNELS = {"solve_fast": 0, "solve_generic": 1, "sample_time_major": 2, "sample_rows": 3, "solve_attempt2": 4,
+               "solve_items": 5}
 
     def setProfiling(self, on: bool) -> None:
         """bracket every launch of the hot kernels with CUDA events on the launching stream"""
