@@ -8,8 +8,9 @@
   pass 3  goal accuracy (README.md:126-136: average 0.003 rad, worst < 0.015 rad, fewer than 1 in
           1000 scaling failures): every `acc_stride`-th point is sampled densely and the final
           position compared with the goal
-  parity  every `par_stride`-th point against the CPU oracle: exact fields must agree, values
-          within 1e-9 rel / 1e-12 abs; mismatches are counted, not hidden
+  parity  every `par_stride`-th point (default: EVERY point, in slabs of 2^21) against the CPU
+          oracle: exact fields must agree, values within 1e-9 rel / 1e-12 abs; mismatches are
+          counted, not hidden
 
 Usage (GPU box): python tools/grid_sweep.py [m] [acc_stride] [par_stride] > profiles/rNN_grid_sweep.json
 """
@@ -74,7 +75,7 @@ def goal_error(ltp, lim, d, t7, direction, v_drive, mod, chunk=32768):
 def main():
     m = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     acc_stride = int(sys.argv[2]) if len(sys.argv) > 2 else 16
-    par_stride = int(sys.argv[3]) if len(sys.argv) > 3 else 97
+    par_stride = int(sys.argv[3]) if len(sys.argv) > 3 else 1
     lim = W.REF_GRID
     ltp = LongTermPlanner(lim.dof, lim.t_sample, *lim.arrays(), device=0)
     qg, q0, v0, a0 = W.grid_one_joint(m, lim)
@@ -145,26 +146,30 @@ def main():
         from helpers import count_bad
         from oracle.bindings import OraclePort
         P = OraclePort.from_limits(lim)
-        idx = np.arange(0, n, par_stride)
+        all_idx = np.arange(0, n, par_stride)
         t0 = time.perf_counter()
-        ref = P.opt_switch_times(qg[idx], q0[idx], v0[idx], a0[idx], np.full(idx.size, lim.v_max[0]), threads=os.cpu_count())
-        it = torch.from_numpy(idx).cuda()
-        par = {"points": int(idx.size), "exact_field_mismatches": {}, "value_mismatches": {}}
-        for k, g in (("ok", opt["ok"]), ("case", opt["case"]), ("mod", opt["mod"]), ("dir", opt["dir"])):
-            par["exact_field_mismatches"]["opt_" + k] = int((g[0, it].cpu().numpy() != ref[k]).sum())
-        par["value_mismatches"]["opt_t"] = count_bad(opt["t"][:, 0, it].cpu().numpy().T, ref["t"])
-        for inc in INCS:
-            tr = ref["t"][:, 6] + inc
-            r2 = P.time_scaling(qg[idx], q0[idx], v0[idx], a0[idx], ref["dir"], tr, threads=os.cpu_count())
-            s = scaled[inc]
-            for k in ("ok", "mod", "ts_case", "final_case"):
-                key = f"ts_{k}"
-                par["exact_field_mismatches"][key] = par["exact_field_mismatches"].get(key, 0) + \
-                    int((s[k][0, it].cpu().numpy() != r2[k]).sum())
-            par["value_mismatches"]["ts_t"] = par["value_mismatches"].get("ts_t", 0) + \
-                count_bad(s["t"][:, 0, it].cpu().numpy().T, r2["t"])
-            par["value_mismatches"]["ts_v_drive"] = par["value_mismatches"].get("ts_v_drive", 0) + \
-                count_bad(s["v_drive"][0, it].cpu().numpy(), r2["v_drive"])
+        par = {"points": int(all_idx.size), "exact_field_mismatches": {}, "value_mismatches": {}}
+
+        def add(d_, key, v):
+            d_[key] = d_.get(key, 0) + int(v)
+
+        for c0 in range(0, all_idx.size, 1 << 21):
+            idx = all_idx[c0:c0 + (1 << 21)]
+            ref = P.opt_switch_times(qg[idx], q0[idx], v0[idx], a0[idx], np.full(idx.size, lim.v_max[0]),
+                                     threads=os.cpu_count())
+            it = torch.from_numpy(idx).cuda()
+            for k, g in (("ok", opt["ok"]), ("case", opt["case"]), ("mod", opt["mod"]), ("dir", opt["dir"])):
+                add(par["exact_field_mismatches"], "opt_" + k, (g[0, it].cpu().numpy() != ref[k]).sum())
+            add(par["value_mismatches"], "opt_t", count_bad(opt["t"][:, 0, it].cpu().numpy().T, ref["t"]))
+            for inc in INCS:
+                tr = ref["t"][:, 6] + inc
+                r2 = P.time_scaling(qg[idx], q0[idx], v0[idx], a0[idx], ref["dir"], tr, threads=os.cpu_count())
+                s = scaled[inc]
+                for k in ("ok", "mod", "ts_case", "final_case"):
+                    add(par["exact_field_mismatches"], f"ts_{k}", (s[k][0, it].cpu().numpy() != r2[k]).sum())
+                add(par["value_mismatches"], "ts_t", count_bad(s["t"][:, 0, it].cpu().numpy().T, r2["t"]))
+                add(par["value_mismatches"], "ts_v_drive", count_bad(s["v_drive"][0, it].cpu().numpy(), r2["v_drive"]))
+        par["evaluations_compared"] = int(all_idx.size) * (1 + len(INCS))
         par["oracle_seconds"] = time.perf_counter() - t0
         out["parity_vs_cpu_oracle"] = par
     except Exception as e:  # the oracle is test infrastructure; the sweep itself does not need it

@@ -37,3 +37,15 @@ for lim, n in ((W.FRANKA7, 333), (W.REF_RANDOM6, 257), (W.FRANKA12, 100), (W.REF
         ltp.timeScaling(0, float(host[0][i][0]), float(host[1][i][0]), float(host[2][i][0]), float(host[3][i][0]),
                         d, float(t7[6]) + 0.2)
     print(lim.name, "ok", int(sol.reached.sum()), "reached")
+
+# item mode (batches of 8192 problems and more): tail / pending / search kernels, transpose bridge
+for lim in (W.REF_RANDOM6, W.REF_GRID, W.FRANKA7):
+    n = 8192 + 37
+    ltp = LongTermPlanner(lim.dof, lim.t_sample, *lim.arrays(), device=0)
+    ins = devtools.random_states_device(lim, n, 13)
+    sol = ltp.solve(*ins, with_opt=True, with_cases=True)
+    pm = [ltp.transpose(t) for t in ins]
+    sol2, traj2, _ = ltp.planEnvs(*pm, horizon=64)
+    torch.cuda.synchronize()
+    assert torch.equal(sol.t_scaled, sol2.t_scaled)
+    print(lim.name, "item mode ok", int((sol.ts_case >= 3).sum()), "joints past the second candidate")
