@@ -162,3 +162,24 @@ def test_device_math_on_random_limit_sets(dof):
     for k in ("t_scaled", "v_drive"):
         assert count_bad(got[k][r], ref[k][r]) == 0, k
 
+
+
+def test_device_math_with_every_root_finder_candidate_accepted():
+    """a one-joint limit set under which candidates 3..8 of the search (quartics, quintic, sextic)
+    are each the accepted attempt of some joint: device math (host build) == oracle, exact fields
+    and values"""
+    lim = W.random_limits(1, 1001)
+    n = 200_000
+    qg, q0, v0, a0 = (x[:, 0].copy() for x in W.random_states(lim, n, 78))
+    P, S = OraclePort.from_limits(lim), Shadow.from_limits(lim)
+    o = P.opt_switch_times(qg, q0, v0, a0, np.full(n, lim.v_max[0]), threads=4)
+    seen = np.zeros(10, np.int64)
+    for inc in (0.02, 0.05, 0.2):
+        tr = o["t"][:, 6] + inc
+        x = P.time_scaling(qg, q0, v0, a0, o["dir"], tr, threads=4)
+        y = S.time_scaling(qg, q0, v0, a0, o["dir"], tr)
+        for k in ("ok", "mod", "ts_case", "final_case"):
+            assert np.array_equal(x[k], y[k]), (inc, k)
+        assert count_bad(y["t"], x["t"]) == 0 and count_bad(y["v_drive"], x["v_drive"]) == 0
+        seen += np.bincount(x["ts_case"], minlength=10)[:10]
+    assert all(seen[k] > 0 for k in range(1, 9)), seen

@@ -536,3 +536,31 @@ def test_rows_layout_equals_time_major_on_batches(lim, n, mode):
         m = min(full["length"], cap) if H == 0 else min(full["length"], H)
         for k in "qvaj":
             assert count_bad(rr[k][i, :, :m], full[k][:, :m]) == 0, (k, i)
+
+
+def test_every_root_finder_candidate_is_accepted_somewhere_and_matches_the_oracle():
+    """The reference's own limits never let the sextic candidate (cc:606-629) win the search; a
+    one-joint random limit set does (found by scanning limit sets with the oracle): candidates
+    3..8 -- quartic, quartic, quintic, quartic, quartic, sextic -- are all the ACCEPTED attempt of
+    some joint here, so smallest_root<4|5|6> is checked on the accept path as well."""
+    lim = W.random_limits(1, 1001)
+    n = 400_000
+    qg, q0, v0, a0 = (x[:, 0].copy() for x in W.random_states(lim, n, 78))
+    ltp = _planner(lim)
+    P = OraclePort.from_limits(lim)
+    vd = np.full(n, lim.v_max[0])
+    o = P.opt_switch_times(qg, q0, v0, a0, vd, threads=8)
+    d = [_dev(x[None, :]) for x in (qg, q0, v0, a0)]
+    seen = np.zeros(10, np.int64)
+    for inc in (0.02, 0.05, 0.2):
+        tr = o["t"][:, 6] + inc
+        got = ltp.timeScalingBatch(d[0], d[1], d[2], d[3], _dev(o["dir"][None, :]), _dev(tr[None, :]))
+        torch.cuda.synchronize()
+        ref = P.time_scaling(qg, q0, v0, a0, o["dir"], tr, threads=8)
+        for k in ("ok", "mod", "ts_case", "final_case"):
+            assert np.array_equal(got[k].cpu().numpy()[0], ref[k]), (inc, k)
+        assert count_bad(pm(got["t"].cpu().numpy())[:, 0, :], ref["t"]) == 0
+        assert count_bad(got["v_drive"].cpu().numpy()[0], ref["v_drive"]) == 0
+        seen += np.bincount(ref["ts_case"], minlength=10)[:10]
+    assert all(seen[k] > 0 for k in range(1, 9)), seen
+    assert seen[8] >= 50 and seen[5] >= 50, seen

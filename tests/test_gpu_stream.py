@@ -320,3 +320,45 @@ def test_env_batch_replans_in_the_callers_layout():
         ltp.advance(ref, tick, *state_jm, valid=sol.reached)
         q_pm, v_pm, a_pm = envs.state()
         assert torch.equal(q_pm, state_jm[0].t().contiguous()) and torch.equal(a_pm, state_jm[2].t().contiguous())
+
+
+def test_advance_respects_the_sample_capacity_and_reserve_preallocates():
+    """ltp_advance_batch reads at most sample capacity - 1 (a trajectory clipped by the capacity is
+    shorter than its traj_len says) and refuses a tick past the capacity when no lengths are given;
+    ltp_reserve sizes the solve scratch up front so that a captured solve never allocates"""
+    from longtermplanner_b200 import _capi as capi
+    lim, n = W.FRANKA7, 640
+    ltp = _planner(lim)
+    qg, q0, v0, a0 = W.random_states(lim, n, 97)
+    ins = [torch.from_numpy(jm(x)).cuda() for x in (qg, q0, v0, a0)]
+    ltp.reserve(n)
+    g = torch.cuda.CUDAGraph()
+    sol = ltp.alloc_solution(n)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ltp.solve(*ins, out=sol)            # warm (lazy module loading must not happen inside the capture)
+        with torch.cuda.graph(g, stream=s):
+            ltp.solve(*ins, out=sol)        # would fail with an allocation inside the capture
+        sol.traj_len.zero_()
+        g.replay()
+    s.synchronize()
+    ref = OraclePort.from_limits(lim).solve(qg, q0, v0, a0, threads=4)
+    assert np.array_equal(sol.traj_len.cpu().numpy(), ref["traj_len"])
+    # exact-length trajectories clipped by a small capacity: the tick is limited to the last stored sample
+    cap = 64
+    short = ltp.alloc_trajectories(n, cap, "time_major")
+    ltp.sample(ins[1], ins[2], ins[3], sol, out=short)
+    nq, nv, na = (t.clone() for t in ins[1:])
+    cs = sol.c_struct()
+    rc = capi.advance_batch(ltp._h, n, 10_000, 0, cap, sol.traj_len.data_ptr(), None, short.q.data_ptr(),
+                            short.v.data_ptr(), short.a.data_ptr(), nq.data_ptr(), nv.data_ptr(), na.data_ptr(),
+                            torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(nq, short.q[cap - 1].T.contiguous())      # every trajectory here is longer than 64 samples
+    # fixed-horizon tensors (no lengths): a tick past the capacity is an argument error, nothing is read
+    rc = capi.advance_batch(ltp._h, n, cap, 0, cap, None, None, short.q.data_ptr(), short.v.data_ptr(),
+                            short.a.data_ptr(), nq.data_ptr(), nv.data_ptr(), na.data_ptr(),
+                            torch.cuda.current_stream().cuda_stream)
+    assert rc == capi.ERR_ARG if hasattr(capi, "ERR_ARG") else rc != 0
+    del cs

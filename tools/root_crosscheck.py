@@ -17,15 +17,19 @@ from longtermplanner_b200 import workloads as W  # noqa: E402
 from oracle.bindings import OraclePort, build  # noqa: E402
 
 
-def traced_polynomials(lim, states, capacity=4_000_000):
-    """-> (records [m, 8], total count) of the polynomials a single-threaded solve of `states` root-solves"""
+def traced_polynomials(lim, states, capacity=4_000_000, run=None):
+    """-> (records [m, 8], total count) of the polynomials a single-threaded solve of `states`
+    (or run(P), any single-threaded sequence of oracle calls) root-solves"""
     P = OraclePort.from_limits(lim)
     buf = np.zeros((capacity, 8))
     P.lib.ltpo_trace_roots.restype = None
     P.lib.ltpo_trace_count.restype = C.c_int64
     P.lib.ltpo_trace_roots(buf.ctypes.data_as(C.c_void_p), C.c_int64(capacity))
     try:
-        P.solve(*states, threads=1)
+        if run is not None:
+            run(P)
+        else:
+            P.solve(*states, threads=1)
         total = int(P.lib.ltpo_trace_count())
     finally:
         P.lib.ltpo_trace_roots(None, C.c_int64(0))
@@ -46,8 +50,8 @@ def lapack_choice(rec):
     return (real.min() if real.size else np.inf), ev
 
 
-def crosscheck(lim, states, name):
-    recs, total, P = traced_polynomials(lim, states)
+def crosscheck(lim, states, name, run=None):
+    recs, total, P = traced_polynomials(lim, states, run=run)
     out = {"workload": name, "polynomials": total, "compared": len(recs), "by_degree": {},
            "non_finite_companion": 0, "existence_disagree": 0, "chosen_root_rel_gt_1e-9": 0,
            "chosen_root_rel_gt_1e-6": 0, "real_count_disagree": 0, "worst_rel": 0.0}
@@ -102,6 +106,18 @@ if __name__ == "__main__":
     res.append(crosscheck(lim, st, "REF_GRID 48^3 single-joint grid (time-optimal solves: quartic tails)"))
     res.append(crosscheck(W.REF_RANDOM6, W.random_states(W.REF_RANDOM6, 60000, W.SEEDS[2]),
                           "REF_RANDOM6, 60000 random 6-DoF problems (stage-1 tails + TS3..TS8)"))
+
+    # a one-joint limit set under which the quintic and the sextic candidate are ACCEPTED (the
+    # reference's own limits only ever reject them): tests/test_gpu_parity.py uses the same set
+    lim1 = W.random_limits(1, 1001)
+    qg, q0, v0, a0 = (x[:, 0].copy() for x in W.random_states(lim1, 100000, 78))
+
+    def search(P):
+        o = P.opt_switch_times(qg, q0, v0, a0, np.full(qg.size, lim1.v_max[0]), threads=1)
+        for inc in (0.02, 0.05, 0.2):
+            P.time_scaling(qg, q0, v0, a0, o["dir"], o["t"][:, 6] + inc, threads=1)
+    res.append(crosscheck(lim1, None, "random one-joint limit set 1001: searches at t_opt + {0.02, 0.05, 0.2} "
+                                      "(every candidate 3..8 accepted somewhere)", run=search))
     print(json.dumps(res, indent=1))
     if len(sys.argv) > 2 and sys.argv[1] == "--json":
         json.dump(res, open(sys.argv[2], "w"), indent=1)
