@@ -73,6 +73,7 @@ class BatchTrajectories:
     success: torch.Tensor   # [n] u8
     traj_len: torch.Tensor  # [n] i32
     order: Optional[torch.Tensor] = None  # [n] i32: slot k holds problem order[k] (sorted-slot sampling)
+    reached: Optional[torch.Tensor] = None  # [n] u8: the solution's flag (problems that were planned at all)
 
 
 def as_tensor(x) -> torch.Tensor:
@@ -358,6 +359,7 @@ class LongTermPlanner:
             out = self.alloc_trajectories(n, samples, layout)
         out.horizon = horizon
         out.traj_len = sol.traj_len
+        out.reached = sol.reached
         cs = sol.c_struct()
         if sorted_slots:
             if out.layout != "time_major" or horizon != 0:
@@ -441,7 +443,11 @@ class LongTermPlanner:
     def advance(self, traj: BatchTrajectories, tick: int, q_0, v_0, a_0, valid: Optional[torch.Tensor] = None,
                 clamp: bool = True) -> None:
         """receding horizon: the state at sample index `tick` of time-major trajectories becomes
-        the next start state (written into q_0, v_0, a_0 in place), ltp_advance_batch"""
+        the next start state (written into q_0, v_0, a_0 in place), ltp_advance_batch. Problems
+        that were not planned (valid, default: the `reached` flag of the solution the trajectories
+        were sampled from) keep their state."""
+        if valid is None:
+            valid = traj.reached
         if traj.layout != "time_major":
             raise ValueError("advance needs time-major trajectories")
         n = q_0.shape[1]
