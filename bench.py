@@ -616,8 +616,8 @@ def main():
     # ---- end to end through the host-buffer C-ABI entry point ------------------------------
     host_np = [t.numpy() for t in host_in]
     host_out_t = {k: torch.empty(s, dtype=d).pin_memory() for k, s, d in (
-        ("t_scaled", (7, lim.dof, n), torch.float64), ("dir", (lim.dof, n), torch.float64),
-        ("v_drive", (lim.dof, n), torch.float64), ("mod", (lim.dof, n), torch.uint8),
+        ("records", (lim.dof, n, 8), torch.float64), ("dir", (lim.dof, n), torch.float64),
+        ("mod", (lim.dof, n), torch.uint8),
         ("slowest", (n,), torch.int32), ("traj_len", (n,), torch.int32), ("reached", (n,), torch.uint8))}
     host_out = {k: t.numpy() for k, t in host_out_t.items()}
     e2e_steps = max(3, min(args.steps, 10))
@@ -636,15 +636,16 @@ def main():
     e2e_value = world * n * e2e_steps / e2e_s
     assert np.array_equal(host_out["traj_len"], sol.traj_len.cpu().numpy())  # what was timed is what was solved
     h2d = sum(x.nbytes for x in host_np)
-    d2h = sum(x.nbytes for x in host_out.values())
+    d2h = sum(host_out[k].nbytes for k in host_out_t)  # (the call adds views of the records to the dict)
     # the same call with the output mask a caller sets who goes on to sample on the device or only
     # needs the durations: switching times, lengths and flags (ltp_solve_host: NULL = not copied)
-    lean_out = {k: host_out[k] for k in ("t_scaled", "traj_len", "reached")}
+    lean_out = {k: host_out[k] for k in ("records", "traj_len", "reached")}
     lean_s = time_host_calls(lean_out)
-    lean_d2h = sum(x.nbytes for x in lean_out.values())
+    lean_d2h = sum(host_out[k].nbytes for k in ("records", "traj_len", "reached"))
     # the ceiling: the same bytes as bare pinned copies in both directions at once
     probe_s = pcie_probe(host_in, list(host_out_t.values()), dev, 5, barrier, max_over_ranks)
-    probe_lean_s = pcie_probe(host_in, [host_out_t[k] for k in lean_out], dev, 5, barrier, max_over_ranks)
+    probe_lean_s = pcie_probe(host_in, [host_out_t[k] for k in ("records", "traj_len", "reached")], dev, 5, barrier,
+                              max_over_ranks)
     clock_info = clocks.stop() if rank == 0 else None
     os.sched_setaffinity(0, all_cpus)  # the CPU baseline below uses every host core
 
@@ -877,7 +878,8 @@ def main():
                              "at once, all ranks at once) take pcie_probe_ms per step; frac = that / the call",
                     "pcie_probe_ms": probe_s * 1e3,
                     "lean": {"value": world * n * e2e_steps / lean_s, "unit": "plans/s",
-                             "outputs": "t_scaled, traj_len, reached (output mask: the other fields NULL)",
+                             "outputs": "records (switching times + v_drive), traj_len, reached (output mask: the "
+                                        "other fields NULL)",
                              "d2h_bytes_per_step": lean_d2h, "pcie_probe_ms": probe_lean_s * 1e3,
                              "frac": probe_lean_s / (lean_s / e2e_steps)}},
             "gpu_launches": int(gpu_launches), "clocks": clock_info, "reached_frac": reached_frac,

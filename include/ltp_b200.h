@@ -111,9 +111,13 @@ int ltp_time_scaling_batch(ltp_planner* p, int64_t n, const double* q_goal, cons
 /* Result of stages 1-3 (phase times, synchronisation, time scaling). Device pointers.
  * Pointers marked optional may be NULL. */
 typedef struct {
-  double* t_scaled;    /* [7][dof][n]  final switching times (reference t_scaled, cc:50-55) */
+  double* t_scaled;    /* [dof][n][8]  one 64-byte record per (joint, problem), 32-byte aligned:
+                        *      t_scaled[(joint * n + problem) * 8 + k], k = 0..6 the final cumulative
+                        *      switching times (reference t_scaled, cc:50-55), k = 7 v_drive.
+                        *      A record is two whole 32-byte sectors written once by whichever
+                        *      kernel settles the joint: no store of the solve is ever partial */
   double* dir;         /* [dof][n] */
-  double* v_drive;     /* [dof][n] */
+  double* v_drive;     /* optional [dof][n]  copy of slot 7 of the records */
   uint8_t* mod;        /* [dof][n]  modified jerk profile flag */
   int32_t* slowest;    /* [n]  index of the slowest joint, -1 if none */
   int32_t* traj_len;   /* [n]  samples of the trajectory (cc:716-719); 0 if not reached */
@@ -270,8 +274,8 @@ int ltp_transpose(ltp_planner* p, int64_t rows, int64_t cols, const double* src,
  * outputs back, and synchronises. Same layouts as ltp_solve_batch; the ltp_solution
  * holds HOST pointers here. Output mask: every field except traj_len and reached may be NULL
  * and is then not copied back -- the device->host transfer is what bounds this call (520 B per
- * 7-DoF plan for the full solution, 397 B for t_scaled + traj_len + reached, 5 B for the
- * durations alone). Pinned host memory makes the copies asynchronous and lets chunks overlap. */
+ * 7-DoF plan for the full solution: records incl. v_drive, dir, mod, slowest, traj_len, reached;
+ * 453 B for records + traj_len + reached, 5 B for the durations alone). Pinned host memory makes the copies asynchronous and lets chunks overlap. */
 int ltp_solve_host(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
                    const double* v_0, const double* a_0, const ltp_solution* host_sol);
 

@@ -166,17 +166,41 @@ __device__ __forceinline__ void store_joint_opt(const DeviceSolution& S, int dof
   if (S.opt_case) S.opt_case[at] = opt_case;
 }
 
+// The switching times of a (problem, joint) live in one 64-byte record -- t[0..6] and v_drive,
+// t_scaled[(joint * n + problem) * 8 + k] -- i.e. two whole 32-byte sectors that belong to nobody
+// else. Whichever kernel settles the joint writes the record with two 256-bit stores, so no sector
+// of the solution is ever written partially, however many kernels hand the joint on before it is
+// settled (with the round-1 layout [7][dof][n] a sector held the same time of four problems, and
+// every joint settled by a later kernel cost the memory system a read-modify-write per time).
+__device__ __forceinline__ double* record_of(const DeviceSolution& S, int jt, int64_t n, int64_t p) {
+  return S.t_scaled + ((int64_t)jt * n + p) * 8;
+}
+
+__device__ __forceinline__ void store_record(double* rec, const double* t, double v_drive) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(rec), "d"(t[0]), "d"(t[1]), "d"(t[2]), "d"(t[3])
+               : "memory");
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(rec + 4), "d"(t[4]), "d"(t[5]), "d"(t[6]), "d"(v_drive)
+               : "memory");
+}
+
+__device__ __forceinline__ void load_record(const double* rec, double* t, double& v_drive) {
+  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(t[0]), "=d"(t[1]), "=d"(t[2]), "=d"(t[3]) : "l"(rec));
+  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];"
+               : "=d"(t[4]), "=d"(t[5]), "=d"(t[6]), "=d"(v_drive)
+               : "l"(rec + 4));
+}
+
 // ... and the part that the time-scaling search decides
 __device__ __forceinline__ void store_joint_scaled(const DeviceSolution& S, int dof, int jt, int64_t n, int64_t p,
                                                    const double* t_sc, double v_drive, unsigned char mod,
                                                    unsigned char ts_case, unsigned char final_case) {
   const int64_t at = (int64_t)jt * n + p;
-#pragma unroll
-  for (int k = 0; k < 7; ++k) S.t_scaled[((int64_t)k * dof + jt) * n + p] = t_sc[k];
-  S.v_drive[at] = v_drive;
+  store_record(record_of(S, jt, n, p), t_sc, v_drive);
+  if (S.v_drive) S.v_drive[at] = v_drive;
   S.mod[at] = mod;
   if (S.ts_case) S.ts_case[at] = ts_case;
   if (S.final_case) S.final_case[at] = final_case;
+  (void)dof;
 }
 
 __device__ __forceinline__ void store_joint(const DeviceSolution& S, int dof, int jt, int64_t n, int64_t p,
@@ -485,8 +509,9 @@ ltp_solve_attempt2_kernel(const __grid_constant__ PlannerParams P, int64_t n, De
 
 // Tail items: the time-optimal solve of one (problem, joint) including the quartic tail
 // (cc:245-337, one or two quartic root solves), one thread per item -- every lane of a warp runs
-// the root finder. The result is parked in the joint's t_scaled / v_drive entries (which the
-// pending kernel overwrites with the final values) and in dir / t_opt / opt_case.
+// the root finder. The result is parked in the joint's record (times in slots 0..6, the flags in
+// the v_drive slot; the pending kernel overwrites it with the final values) and in dir / t_opt /
+// opt_case.
 __global__ void __launch_bounds__(128)
 ltp_solve_tail_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_goal,
                       const double* __restrict__ q_0, const double* __restrict__ v_0,
@@ -505,9 +530,7 @@ ltp_solve_tail_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
     zero7(t_opt);
     unsigned char mod = 0, opt_case = 255;
     const bool ok = ost_body(L, P.ts, pro, qg, q0, L.v_max, t_opt, mod, opt_case);
-#pragma unroll
-    for (int k = 0; k < 7; ++k) S.t_scaled[((int64_t)k * dof + jt) * n + p] = t_opt[k];
-    S.v_drive[at] = pack_tail_flags(mod, opt_case, ok ? 1u : 0u);
+    store_record(record_of(S, jt, n, p), t_opt, pack_tail_flags(mod, opt_case, ok ? 1u : 0u));
     store_joint_opt(S, dof, jt, n, p, t_opt, pro.dir, opt_case);
   }
 }
@@ -547,9 +570,9 @@ ltp_solve_pending_kernel(const __grid_constant__ PlannerParams P, int64_t n, con
     const int st1 = ost_body_t<false>(L, Ts, pro, qg, q0, L.v_max, t_opt, mod, opt_case);
     bool ost_ok = st1 == OST_OK;
     if (st1 == OST_DEFER && valid) {
-#pragma unroll
-      for (int k = 0; k < 7; ++k) t_opt[k] = S.t_scaled[((int64_t)k * dof + jt) * n + p];
-      const unsigned f = (unsigned)__double2loint(S.v_drive[at]);
+      double parked;
+      load_record(record_of(S, jt, n, p), t_opt, parked);
+      const unsigned f = (unsigned)__double2loint(parked);
       mod = (unsigned char)(f & 255u);
       opt_case = (unsigned char)((f >> 8) & 255u);
       ost_ok = ((f >> 16) & 1u) != 0;
@@ -867,16 +890,15 @@ ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, int ppb, c
     if (len > 0) {
       const JointLimits L = P.lim[jt];
       const int64_t at = (int64_t)jt * n + p;
-      double t[7];
-#pragma unroll
-      for (int k = 0; k < 7; ++k) t[k] = S.t_scaled[((int64_t)k * dof + jt) * n + p];
+      double t[7], v_drive_row;
+      load_record(record_of(S, jt, n, p), t, v_drive_row);
       // samples stored: the fixed horizon, or the exact length clipped to the row capacity
       const int n_out = horizon > 0 ? horizon : (len < stride ? len : (int)stride);
       const int n_run = n_out > len ? n_out : len;    // samples computed
       RowCursor C;
       {
         RowSampler R;
-        R.init(P.ts, L.j_max, t, S.dir[at], S.mod[at], q_0[at], v_0[at], a_0[at], S.v_drive[at], n_run);
+        R.init(P.ts, L.j_max, t, S.dir[at], S.mod[at], q_0[at], v_0[at], a_0[at], v_drive_row, n_run);
         T.build(R, n_run);
         cursor_begin(C, R, T);
       }
@@ -1043,13 +1065,12 @@ ltp_sample_row_latency_kernel(const __grid_constant__ PlannerParams P, int64_t n
     if (len > 0) {
       const JointLimits L = P.lim[jt];
       const int64_t at = (int64_t)jt * n + p;
-      double t[7];
-#pragma unroll
-      for (int k = 0; k < 7; ++k) t[k] = S.t_scaled[((int64_t)k * dof + jt) * n + p];
+      double t[7], v_drive_row;
+      load_record(record_of(S, jt, n, p), t, v_drive_row);
       const int n_out = horizon > 0 ? horizon : (len < stride ? len : (int)stride);
       const int n_run = n_out > len ? n_out : len;
       RowSampler R;
-      R.init(P.ts, L.j_max, t, S.dir[at], S.mod[at], q_0[at], v_0[at], a_0[at], S.v_drive[at], n_run);
+      R.init(P.ts, L.j_max, t, S.dir[at], S.mod[at], q_0[at], v_0[at], a_0[at], v_drive_row, n_run);
       {
         // The piece table, built by the whole warp instead of piece after piece by one thread:
         // every lane takes one of the 26 places where the jerk or the update rule can change
@@ -1183,16 +1204,15 @@ ltp_sample_tm_kernel(const __grid_constant__ PlannerParams P, int64_t n, const d
     return;
   }
   const JointLimits L = P.lim[jt];
-  double t[7];
-#pragma unroll
-  for (int k = 0; k < 7; ++k) t[k] = S.t_scaled[((int64_t)k * dof + jt) * n + p];
+  double t[7], v_drive_row;
+  load_record(record_of(S, jt, n, p), t, v_drive_row);
   // samples stored: the fixed horizon, or the exact length clipped to the sample capacity
   const int n_out = horizon > 0 ? horizon : (len < capacity ? len : (int)capacity);
   const int n_run = n_out > len ? n_out : len;    // samples computed
   RowCursor C;
   {
     RowSampler R;
-    R.init(P.ts, L.j_max, t, S.dir[at], S.mod[at], q_0[at], v_0[at], a_0[at], S.v_drive[at], n_run);
+    R.init(P.ts, L.j_max, t, S.dir[at], S.mod[at], q_0[at], v_0[at], a_0[at], v_drive_row, n_run);
     T.build(R, n_run, LTP_TM_BUILD_EARLY_EXIT != 0);
     cursor_begin(C, R, T);
   }
@@ -1556,7 +1576,7 @@ size_t carve_solution(unsigned char* base, int dof, int64_t n, ltp_solution* s) 
     return r;
   };
   const size_t dn = (size_t)dof * (size_t)n;
-  s->t_scaled = (double*)take(7 * dn * 8);
+  s->t_scaled = (double*)take(8 * dn * 8);  // 64-byte records: t[0..6], v_drive
   s->t_opt = (double*)take(7 * dn * 8);
   s->dir = (double*)take(dn * 8);
   s->v_drive = (double*)take(dn * 8);
@@ -1858,9 +1878,9 @@ int ltp_solve_batch(ltp_planner* p, int64_t n, const double* q_goal, const doubl
   if (!p || n < 0 || p->params.dof < 1) return LTP_ERR_ARG;
   if (n == 0) return LTP_OK;
   if (!q_goal || !q_0 || !v_0 || !a_0 || !sol) return LTP_ERR_ARG;
-  if (!sol->t_scaled || !sol->dir || !sol->v_drive || !sol->mod || !sol->slowest || !sol->traj_len ||
-      !sol->reached)
+  if (!sol->t_scaled || !sol->dir || !sol->mod || !sol->slowest || !sol->traj_len || !sol->reached)
     return LTP_ERR_ARG;
+  if (!aligned32(sol->t_scaled)) return LTP_ERR_ARG;  // the records are written with 256-bit stores
   if (n > 0x7fffffff) return LTP_ERR_ARG;  // problem indices travel as int32 in the work list
   DeviceGuard g(p->device);
   if (p->solve_mode != LTP_SOLVE_GENERIC && n > kTile) {
@@ -1924,7 +1944,7 @@ int ltp_sample_batch_sorted(ltp_planner* p, int64_t n, const double* q_0, const 
   if (!p || n < 0 || p->params.dof < 1 || capacity < 1) return LTP_ERR_ARG;
   if (n == 0) return LTP_OK;
   if (!q_0 || !v_0 || !a_0 || !sol || !q || !v || !a || !j || !success || !order) return LTP_ERR_ARG;
-  if (!sol->t_scaled || !sol->dir || !sol->v_drive || !sol->mod || !sol->traj_len || !sol->reached)
+  if (!sol->t_scaled || !sol->dir || !sol->mod || !sol->traj_len || !sol->reached || !aligned32(sol->t_scaled))
     return LTP_ERR_ARG;
   if (n > 0x7fffffff) return LTP_ERR_ARG;
   DeviceGuard g(p->device);
@@ -1942,7 +1962,7 @@ int ltp_sample_batch(ltp_planner* p, int64_t n, const double* q_0, const double*
   if (!q_0 || !v_0 || !a_0 || !sol || !q || !v || !a || !j || !success || stride < 1 ||
       (horizon > 0 && stride < horizon))
     return LTP_ERR_ARG;
-  if (!sol->t_scaled || !sol->dir || !sol->v_drive || !sol->mod || !sol->traj_len || !sol->reached)
+  if (!sol->t_scaled || !sol->dir || !sol->mod || !sol->traj_len || !sol->reached || !aligned32(sol->t_scaled))
     return LTP_ERR_ARG;
   DeviceGuard g(p->device);
   const int dof = p->params.dof;
@@ -2010,6 +2030,7 @@ int ltp_solve_host(ltp_planner* p, int64_t n, const double* q_goal, const double
     for (int i = 0; i < 4; ++i) d_in[s][i] = (double*)(base + i * in_bytes);
     carve_solution(base + 4 * in_bytes, dof, c_max, &ds[s]);
     d_work[s] = base + 4 * in_bytes + sol_bytes;
+    if (!hs->v_drive) ds[s].v_drive = nullptr;  // slot 7 of the records holds it anyway
     if (!hs->t_opt) ds[s].t_opt = nullptr;
     if (!hs->opt_case) ds[s].opt_case = nullptr;
     if (!hs->ts_case) ds[s].ts_case = nullptr;
@@ -2030,7 +2051,9 @@ int ltp_solve_host(ltp_planner* p, int64_t n, const double* q_goal, const double
 #define LTP_OUT2D(FIELD, ROWS, ELEM)                                                                   \
   LTP_CUDA(cudaMemcpy2DAsync(hs->FIELD + p0, (size_t)n * (ELEM), d.FIELD, (size_t)c * (ELEM),           \
                              (size_t)c * (ELEM), (ROWS), cudaMemcpyDeviceToHost, st))
-    if (hs->t_scaled) LTP_OUT2D(t_scaled, 7 * dof, 8);
+    if (hs->t_scaled)  // [dof][n] records of 64 bytes: dof pieces of c records at a pitch of n records
+      LTP_CUDA(cudaMemcpy2DAsync(hs->t_scaled + p0 * 8, (size_t)n * 64, d.t_scaled, (size_t)c * 64, (size_t)c * 64, dof,
+                                 cudaMemcpyDeviceToHost, st));
     if (hs->dir) LTP_OUT2D(dir, dof, 8);
     if (hs->v_drive) LTP_OUT2D(v_drive, dof, 8);
     if (hs->mod) LTP_OUT2D(mod, dof, 1);
@@ -2095,6 +2118,7 @@ int ltp_plan_stream(ltp_planner* p, int64_t n, const double* q_goal, const doubl
     for (int i = 0; i < 4; ++i) d_in[s][i] = (double*)(base + i * in_bytes);
     carve_solution(base + 4 * in_bytes, dof, c_max, &ds[s]);
     ds[s].t_opt = nullptr; ds[s].opt_case = nullptr; ds[s].ts_case = nullptr; ds[s].final_case = nullptr;
+    ds[s].v_drive = nullptr;  // slot 7 of the records
     d_work[s] = base + 4 * in_bytes + sol_bytes;
     d_order[s] = (int*)(base + 4 * in_bytes + sol_bytes + work_bytes);
     unsigned char* ring = (unsigned char*)p->ring_buf[s];
@@ -2250,6 +2274,7 @@ static int plan_small_run(ltp_planner* p, int64_t n, const double* q_goal, const
   if (rc != LTP_OK) return rc;
   carve_solution((unsigned char*)p->d_scratch, dof, n, &ds);
   ds.t_opt = nullptr; ds.opt_case = nullptr; ds.ts_case = nullptr; ds.final_case = nullptr;
+  ds.v_drive = nullptr;
   ds.traj_len = h_len;
   ds.reached = h_reached;
   cudaStream_t st = p->stream;
@@ -2483,9 +2508,8 @@ int ltp_get_trajectory_host(ltp_planner* p, const double* t7, const double* dir,
     if (rc != LTP_OK) return rc;
     double* h = (double*)p->h_stage;
     std::memset(&ds, 0, sizeof ds);
-    ds.t_scaled = h;                       // [7][dof][1]
-    ds.dir = h + 7 * dof;
-    ds.v_drive = h + 8 * dof;
+    ds.t_scaled = h;                       // [dof][1] records of 8 doubles (the block is page-aligned)
+    ds.dir = h + 8 * dof;
     double* h_in = h + 9 * dof;            // q_0, v_0, a_0
     ds.traj_len = (int32_t*)(h + 12 * dof);
     ds.mod = (uint8_t*)(ds.traj_len + 2);
@@ -2493,9 +2517,9 @@ int ltp_get_trajectory_host(ltp_planner* p, const double* t7, const double* dir,
     uint8_t* row_ok = ds.reached + 1;
     double* h_rows = (double*)((unsigned char*)p->h_stage + kStageHeadBytes);
     for (int i = 0; i < dof; ++i) {
-      for (int k = 0; k < 7; ++k) ds.t_scaled[k * dof + i] = t7[7 * i + k];
+      for (int k = 0; k < 7; ++k) ds.t_scaled[8 * i + k] = t7[7 * i + k];
+      ds.t_scaled[8 * i + 7] = v_drive[i];
       ds.dir[i] = dir[i];
-      ds.v_drive[i] = v_drive[i];
       h_in[i] = q_0[i]; h_in[dof + i] = v_0[i]; h_in[2 * dof + i] = a_0[i];
       ds.mod[i] = mod[i];
     }
@@ -2528,15 +2552,16 @@ int ltp_get_trajectory_host(ltp_planner* p, const double* t7, const double* dir,
   double* d_rows[4];
   for (int i = 0; i < 4; ++i) d_rows[i] = (double*)(base + off + i * row_bytes);
   cudaStream_t st = p->stream;
-  // [dof][7] -> [7][dof][1]
-  double tt[7 * LTP_MAX_DOF];
-  for (int i = 0; i < dof; ++i)
-    for (int k = 0; k < 7; ++k) tt[k * dof + i] = t7[7 * i + k];
+  // [dof][7] + v_drive -> [dof][1] records
+  double tt[8 * LTP_MAX_DOF];
+  for (int i = 0; i < dof; ++i) {
+    for (int k = 0; k < 7; ++k) tt[8 * i + k] = t7[7 * i + k];
+    tt[8 * i + 7] = v_drive[i];
+  }
   const uint8_t one = 1;
   const int32_t len32 = len;
-  LTP_CUDA(cudaMemcpyAsync(ds.t_scaled, tt, sizeof(double) * 7 * dof, cudaMemcpyHostToDevice, st));
+  LTP_CUDA(cudaMemcpyAsync(ds.t_scaled, tt, sizeof(double) * 8 * dof, cudaMemcpyHostToDevice, st));
   LTP_CUDA(cudaMemcpyAsync(ds.dir, dir, sizeof(double) * dof, cudaMemcpyHostToDevice, st));
-  LTP_CUDA(cudaMemcpyAsync(ds.v_drive, v_drive, sizeof(double) * dof, cudaMemcpyHostToDevice, st));
   LTP_CUDA(cudaMemcpyAsync(ds.mod, mod, dof, cudaMemcpyHostToDevice, st));
   LTP_CUDA(cudaMemcpyAsync(ds.traj_len, &len32, 4, cudaMemcpyHostToDevice, st));
   LTP_CUDA(cudaMemcpyAsync(ds.reached, &one, 1, cudaMemcpyHostToDevice, st));

@@ -36,12 +36,14 @@ class Trajectory:
 
 @dataclasses.dataclass
 class BatchSolution:
-    """Device-resident result of stages 1-3 for n problems (joint-major tensors)."""
+    """Device-resident result of stages 1-3 for n problems. `records` is what the library writes:
+    [dof, n, 8] float64, one 64-byte record per (joint, problem) = the seven final switching times
+    and v_drive (include/ltp_b200.h). `t_scaled` ([7, dof, n]) and `v_drive` ([dof, n]) are strided
+    views of it, so code written for the round-1 field layout keeps working."""
     n: int
     dof: int
-    t_scaled: torch.Tensor   # [7, dof, n] f64
+    records: torch.Tensor    # [dof, n, 8] f64
     dir: torch.Tensor        # [dof, n] f64
-    v_drive: torch.Tensor    # [dof, n] f64
     mod: torch.Tensor        # [dof, n] u8
     slowest: torch.Tensor    # [n] i32
     traj_len: torch.Tensor   # [n] i32
@@ -51,10 +53,29 @@ class BatchSolution:
     ts_case: Optional[torch.Tensor] = None
     final_case: Optional[torch.Tensor] = None
 
+    @property
+    def t_scaled(self) -> torch.Tensor:
+        """[7, dof, n] view: t_scaled[k, joint, problem]"""
+        return self.records[:, :, :7].permute(2, 0, 1)
+
+    @property
+    def v_drive(self) -> torch.Tensor:
+        """[dof, n] view"""
+        return self.records[:, :, 7]
+
+    @classmethod
+    def from_fields(cls, t_scaled, dir, v_drive, mod, slowest, traj_len, reached) -> "BatchSolution":
+        """pack separate [7, dof, n] times and [dof, n] v_drive tensors into records"""
+        _, dof, n = t_scaled.shape
+        rec = torch.empty(dof, n, 8, dtype=torch.float64, device=t_scaled.device)
+        rec[:, :, :7] = t_scaled.permute(1, 2, 0)
+        rec[:, :, 7] = v_drive
+        return cls(n, dof, rec, dir, mod, slowest, traj_len, reached)
+
     def c_struct(self) -> capi.Solution:
         def ptr(t):
             return None if t is None else t.data_ptr()
-        return capi.Solution(ptr(self.t_scaled), ptr(self.dir), ptr(self.v_drive), ptr(self.mod),
+        return capi.Solution(ptr(self.records), ptr(self.dir), None, ptr(self.mod),
                              ptr(self.slowest), ptr(self.traj_len), ptr(self.reached), ptr(self.t_opt),
                              ptr(self.opt_case), ptr(self.ts_case), ptr(self.final_case))
 
@@ -312,7 +333,7 @@ class LongTermPlanner:
         f = lambda *s: torch.empty(*s, dtype=torch.float64, device=dev)
         b = lambda *s: torch.empty(*s, dtype=torch.uint8, device=dev)
         i = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
-        return BatchSolution(n, dof, f(7, dof, n), f(dof, n), f(dof, n), b(dof, n), i(n), i(n), b(n),
+        return BatchSolution(n, dof, f(dof, n, 8), f(dof, n), b(dof, n), i(n), i(n), b(n),
                              f(7, dof, n) if with_opt else None,
                              b(dof, n) if with_cases else None, b(dof, n) if with_cases else None,
                              b(dof, n) if with_cases else None)
@@ -416,13 +437,15 @@ class LongTermPlanner:
                     first=int(c.first), count=cnt, capacity=cap, horizon=int(c.horizon),
                     q_goal=_alias(c.q_goal, (dof, cnt), torch.float64), q_0=_alias(c.q_0, (dof, cnt), torch.float64),
                     v_0=_alias(c.v_0, (dof, cnt), torch.float64), a_0=_alias(c.a_0, (dof, cnt), torch.float64),
-                    t_scaled=_alias(sol.t_scaled, (7, dof, cnt), torch.float64),
+                    records=_alias(sol.t_scaled, (dof, cnt, 8), torch.float64),
                     traj_len=_alias(sol.traj_len, (cnt,), torch.int32),
                     reached=_alias(sol.reached, (cnt,), torch.uint8),
                     success=_alias(c.success, (cnt,), torch.uint8),
                     order=_alias(c.order, (cnt,), torch.int32) if c.order else None,
                     q=_alias(c.q, (cap, cnt, dof), torch.float64), v=_alias(c.v, (cap, cnt, dof), torch.float64),
                     a=_alias(c.a, (cap, cnt, dof), torch.float64), j=_alias(c.j, (cap, cnt, dof), torch.float64))
+                view["t_scaled"] = view["records"][:, :, :7].permute(2, 0, 1)   # [7, dof, cnt] view
+                view["v_drive"] = view["records"][:, :, 7]
                 ext = torch.cuda.ExternalStream(int(stream), device=dev)
                 with torch.cuda.stream(ext):
                     consumer(view, ext)
@@ -498,19 +521,31 @@ class LongTermPlanner:
     # host-buffer forms (numpy, joint-major [dof, n]); copies are inside the call
     def solve_host(self, q_goal, q_0, v_0, a_0, out: Optional[dict] = None, with_opt=False,
                    with_cases=False) -> dict:
+        """ltp_solve_host. `out` (optional) names the host arrays to fill -- records [dof, n, 8]
+        (switching times + v_drive), dir, mod, slowest, traj_len, reached, t_opt, opt_case, ts_case,
+        final_case, v_drive (a separate contiguous copy); an absent key is the output mask of the C
+        call (not copied back). The returned dict also carries `t_scaled` ([7, dof, n]) and
+        `v_drive` as views of the records."""
         dof = self.dof_
         ins = [np.ascontiguousarray(x, dtype=np.float64) for x in (q_goal, q_0, v_0, a_0)]
         n = ins[0].shape[1]
         if out is None:
-            out = dict(t_scaled=np.empty((7, dof, n)), dir=np.empty((dof, n)), v_drive=np.empty((dof, n)),
+            out = dict(records=np.empty((dof, n, 8)), dir=np.empty((dof, n)),
                        mod=np.empty((dof, n), np.uint8), slowest=np.empty(n, np.int32),
                        traj_len=np.empty(n, np.int32), reached=np.empty(n, np.uint8),
                        t_opt=np.empty((7, dof, n)) if with_opt else None,
                        opt_case=np.empty((dof, n), np.uint8) if with_cases else None,
                        ts_case=np.empty((dof, n), np.uint8) if with_cases else None,
                        final_case=np.empty((dof, n), np.uint8) if with_cases else None)
-        cs = capi.Solution(*[_np_ptr(out.get(k)) for k in ("t_scaled", "dir", "v_drive", "mod", "slowest",
-                                                            "traj_len", "reached", "t_opt", "opt_case",
-                                                            "ts_case", "final_case")])
+        rec = out.get("records")
+        own_vd = out.get("v_drive") if (rec is None or out.get("v_drive") is None or
+                                        not np.shares_memory(out["v_drive"], rec)) else None
+        cs = capi.Solution(_np_ptr(rec), _np_ptr(out.get("dir")), _np_ptr(own_vd),
+                           *[_np_ptr(out.get(k)) for k in ("mod", "slowest", "traj_len", "reached", "t_opt",
+                                                           "opt_case", "ts_case", "final_case")])
         capi.check(capi.solve_host(self._h, n, *[_np_ptr(x) for x in ins], C.byref(cs)), "ltp_solve_host")
+        if rec is not None:
+            out["t_scaled"] = rec[:, :, :7].transpose(2, 0, 1)
+            if own_vd is None:
+                out["v_drive"] = rec[:, :, 7]
         return out

@@ -80,7 +80,7 @@ int main() {
   const int64_t cap = 4096;
   BatchPlan plan;
   std::memset(&plan.solution, 0, sizeof plan.solution);
-  plan.solution.t_scaled = dev_alloc<double>(7 * dof * n);
+  plan.solution.t_scaled = dev_alloc<double>(8 * dof * n);  // 64-byte records: t[0..6], v_drive
   plan.solution.dir = dev_alloc<double>(dof * n);
   plan.solution.v_drive = dev_alloc<double>(dof * n);
   plan.solution.mod = dev_alloc<uint8_t>(dof * n);

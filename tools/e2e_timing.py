@@ -13,8 +13,8 @@ lim, n = W.FRANKA7, 1 << 20
 ltp = LongTermPlanner(lim.dof, lim.t_sample, *lim.arrays(), device=0)
 host_in = [torch.from_numpy(W.to_joint_major(x)).pin_memory().numpy() for x in W.random_states(lim, n, W.SEEDS[2])]
 out = {k: torch.empty(s, dtype=d).pin_memory().numpy() for k, s, d in (
-    ("t_scaled", (7, lim.dof, n), torch.float64), ("dir", (lim.dof, n), torch.float64),
-    ("v_drive", (lim.dof, n), torch.float64), ("mod", (lim.dof, n), torch.uint8),
+    ("records", (lim.dof, n, 8), torch.float64), ("dir", (lim.dof, n), torch.float64),
+    ("mod", (lim.dof, n), torch.uint8),
     ("slowest", (n,), torch.int32), ("traj_len", (n,), torch.int32), ("reached", (n,), torch.uint8))}
 for _ in range(3):
     ltp.solve_host(*host_in, out=out)

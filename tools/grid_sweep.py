@@ -60,9 +60,9 @@ def goal_error(ltp, lim, d, t7, direction, v_drive, mod, chunk=32768):
         c = b - a
         t = t7[:, :, a:b].contiguous()
         tl = (torch.ceil(t[6, 0] / ts).to(torch.int32) + 1)
-        sol = BatchSolution(c, 1, t, direction[:, a:b].contiguous(), v_drive[:, a:b].contiguous(),
-                            mod[:, a:b].contiguous(), torch.zeros(c, dtype=torch.int32, device="cuda"), tl,
-                            torch.ones(c, dtype=torch.uint8, device="cuda"))
+        sol = BatchSolution.from_fields(t, direction[:, a:b].contiguous(), v_drive[:, a:b].contiguous(),
+                                        mod[:, a:b].contiguous(), torch.zeros(c, dtype=torch.int32, device="cuda"),
+                                        tl, torch.ones(c, dtype=torch.uint8, device="cuda"))
         ins = [x[:, a:b].contiguous() for x in d[1:4]]
         traj = ltp.sample(*ins, sol)
         st = devtools.row_stats(traj, tl)
