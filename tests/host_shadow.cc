@@ -228,6 +228,157 @@ int64_t shadow_solve_batch_auto(void* h, int64_t n, const double* q_goal, const 
   return deferred;
 }
 
+// Mirrors ITEM MODE of ltp_b200.cu (batches of 8192 problems and more): what the closed forms do
+// not settle is handed on per (problem, joint) -- tail items (ltp_solve_tail_kernel), pending
+// problems (ltp_solve_pending_kernel), search items (ltp_solve_search_kernel) -- with the same
+// per-joint device functions and the same hand-over rules, lists instead of device queues.
+// stats[0..3] = tail items, pending problems, search items, whole-problem deferrals.
+int64_t shadow_solve_batch_items(void* h, int64_t n, const double* q_goal, const double* q_0, const double* v_0,
+                                 const double* a_0, double* t_opt, double* t_scaled, double* dir, double* v_drive,
+                                 unsigned char* mod, unsigned char* opt_case, unsigned char* ts_case,
+                                 unsigned char* final_case, int* slowest, int* traj_len, unsigned char* reached,
+                                 int64_t* stats) {
+  Shadow* s = static_cast<Shadow*>(h);
+  const int dof = s->dof;
+  const double Ts = s->ts;
+  struct Item { int64_t p; int j; double t_req; };
+  std::vector<Item> tails, searches;
+  std::vector<int64_t> pending, whole;
+  std::vector<unsigned char> tail_ok((size_t)n * dof, 0);
+  auto sample_count = [&](const double* t) {
+    bool fin = true;
+    for (int k = 0; k < 7; ++k) fin &= (bool)std::isfinite(t[k]);
+    return (fin && t[6] / Ts <= 2.0e9) ? samples_for(t[6], Ts) : -1;
+  };
+  auto fallback = [&](double* t, const double* topt) {
+    double m = t[0];
+    for (int k = 1; k < 7; ++k)
+      if (m < t[k]) m = t[k];
+    if (m <= 0.0) std::memcpy(t, topt, 56);
+  };
+  // stages 2-3 of one problem with closed forms only; joints that stay open become search items.
+  // from_tail: the problem waited for tail items (their t_opt / flags are in place already)
+  auto finish_problem = [&](int64_t p, bool from_tail) {
+    const int64_t o = p * dof;
+    std::vector<Prologue> pro(dof);
+    bool any_fail = false, need_tail = false;
+    for (int j = 0; j < dof; ++j) {
+      const JointLimits& L = s->lim[j];
+      const bool in_ok = check_joint_input(L, q_0[o + j], v_0[o + j], a_0[o + j]);
+      pro[j] = ost_prologue(L, Ts, q_goal[o + j], q_0[o + j], v_0[o + j], a_0[o + j]);
+      double t[7];
+      zero7(t);
+      unsigned char m = 0, oc = 255;
+      const int st = ost_body_t<false>(L, Ts, pro[j], q_goal[o + j], q_0[o + j], L.v_max, t, m, oc);
+      dir[o + j] = pro[j].dir;
+      bool ok = st == OST_OK;
+      if (st == OST_DEFER) {
+        if (!from_tail) {
+          need_tail = true;
+          tails.push_back({p, j, 0.0});
+          continue;
+        }
+        ok = tail_ok[o + j] != 0;  // t_opt, mod, opt_case were written by the tail step
+      } else {
+        std::memcpy(t_opt + 7 * (o + j), t, 56);
+        mod[o + j] = m;
+        opt_case[o + j] = oc;
+      }
+      any_fail |= !(in_ok && ok);
+    }
+    if (need_tail) {
+      pending.push_back(p);
+      return;
+    }
+    double t_req = -1;
+    int sl = -1;
+    for (int j = 0; j < dof; ++j)
+      if (t_opt[7 * (o + j) + 6] > t_req) { t_req = t_opt[7 * (o + j) + 6]; sl = j; }
+    const bool rch = !any_fail && sl != -1;
+    int len = 0;
+    bool bad = false;
+    for (int j = 0; j < dof; ++j) {
+      const JointLimits& L = s->lim[j];
+      double* t = t_scaled + 7 * (o + j);
+      zero7(t);
+      v_drive[o + j] = L.v_max;
+      ts_case[o + j] = 255;
+      final_case[o + j] = 255;
+      if (!rch) continue;
+      bool open = false;
+      if (j == sl) {
+        ts_case[o + j] = 0;
+        final_case[o + j] = opt_case[o + j];
+      } else {
+        const TsInput I = make_ts_input(q_goal[o + j], q_0[o + j], v_0[o + j], a_0[o + j], pro[j].dir, t_req);
+        const int c = time_scaling_closed_form(L, Ts, pro[j], I, t, v_drive[o + j], mod[o + j], final_case[o + j]);
+        open = c == 0;
+        ts_case[o + j] = (unsigned char)c;
+        if (c == 9) final_case[o + j] = opt_case[o + j];
+      }
+      if (open) {
+        searches.push_back({p, j, t_req});
+        continue;
+      }
+      fallback(t, t_opt + 7 * (o + j));
+      const int li = sample_count(t);
+      bad |= li < 0;
+      len = li > len ? li : len;
+    }
+    slowest[p] = sl;
+    reached[p] = rch;
+    traj_len[p] = (rch && !bad) ? len : 0;
+    if (bad) whole.push_back(p);
+  };
+  for (int64_t p = 0; p < n; ++p) finish_problem(p, false);
+  for (const Item& it : tails) {  // ltp_solve_tail_kernel
+    const int64_t o = it.p * dof + it.j;
+    const JointLimits& L = s->lim[it.j];
+    const Prologue pro = ost_prologue(L, Ts, q_goal[o], q_0[o], v_0[o], a_0[o]);
+    double* t = t_opt + 7 * o;
+    zero7(t);
+    mod[o] = 0;
+    opt_case[o] = 255;
+    tail_ok[o] = ost_body(L, Ts, pro, q_goal[o], q_0[o], L.v_max, t, mod[o], opt_case[o]);
+  }
+  const std::vector<int64_t> waiting = pending;
+  for (int64_t p : waiting) finish_problem(p, true);  // ltp_solve_pending_kernel
+  for (const Item& it : searches) {  // ltp_solve_search_kernel
+    const int64_t o = it.p * dof + it.j;
+    const JointLimits& L = s->lim[it.j];
+    const Prologue pro = ost_prologue(L, Ts, q_goal[o], q_0[o], v_0[o], a_0[o]);
+    double topt[7];
+    zero7(topt);
+    unsigned char om = 0, oc = 255;
+    ost_body(L, Ts, pro, q_goal[o], q_0[o], L.v_max, topt, om, oc);
+    const TsInput I = make_ts_input(q_goal[o], q_0[o], v_0[o], a_0[o], pro.dir, it.t_req);
+    double* t = t_scaled + 7 * o;
+    zero7(t);
+    v_drive[o] = L.v_max;
+    unsigned char m = om, fc = 255;
+    const int c = time_scaling_from(1, L, Ts, pro, I, t, v_drive[o], m, fc);
+    if (c == 9) fc = oc;
+    mod[o] = m;
+    ts_case[o] = (unsigned char)c;
+    final_case[o] = fc;
+    fallback(t, topt);
+    const int li = sample_count(t);
+    if (li < 0) whole.push_back(it.p);
+    else if (traj_len[it.p] < li) traj_len[it.p] = li;  // atomicMax
+  }
+  for (int64_t p : whole) {
+    const int64_t o = p * dof;
+    shadow_solve_batch(h, 1, q_goal + o, q_0 + o, v_0 + o, a_0 + o, t_opt + 7 * o, t_scaled + 7 * o, dir + o,
+                       v_drive + o, mod + o, opt_case + o, ts_case + o, final_case + o, slowest + p, traj_len + p,
+                       reached + p, 0);
+  }
+  if (stats) {
+    stats[0] = (int64_t)tails.size(); stats[1] = (int64_t)waiting.size();
+    stats[2] = (int64_t)searches.size(); stats[3] = (int64_t)whole.size();
+  }
+  return (int64_t)whole.size();
+}
+
 int shadow_get_trajectory(void* h, const double* t7, const double* dir, const unsigned char* mod,
                           const double* q_0, const double* v_0, const double* a_0, const double* v_drive,
                           int64_t stride, double* q, double* v, double* a, double* j) {

@@ -183,3 +183,43 @@ def test_device_math_with_every_root_finder_candidate_accepted():
         assert count_bad(y["t"], x["t"]) == 0 and count_bad(y["v_drive"], x["v_drive"]) == 0
         seen += np.bincount(x["ts_case"], minlength=10)[:10]
     assert all(seen[k] > 0 for k in range(1, 9)), seen
+
+
+class ShadowItems(Shadow):
+    """item mode (tail items -> pending problems -> search items), replayed on the host"""
+
+    def _fn(self, name, restype=None):
+        if name == "solve_batch":
+            import ctypes
+            f = getattr(self.lib, "shadow_solve_batch_items")
+            f.restype = ctypes.c_int64
+            self.stats = np.zeros(4, np.int64)
+
+            def call(*a):
+                self.whole = f(*a[:-1], ctypes.c_void_p(self.stats.ctypes.data))
+            return call
+        return super()._fn(name, restype)
+
+
+@pytest.mark.parametrize("lim,n,seed,kind", [
+    (W.REF_RANDOM6, 40_000, 251, "random"), (W.REF_GRID, 60_000, 252, "random"), (W.FRANKA7, 30_000, 253, "random"),
+    (W.REF_RANDOM6, 30_000, 254, "edge"), (W.FRANKA7, 30_000, 255, "edge"), (W.random_limits(5, 27), 30_000, 256, "random")])
+def test_item_mode_hand_overs_equal_the_every_branch_sequence(lim, n, seed, kind):
+    """what ltp_solve_batch does with large batches -- joints that need a polynomial root handed on
+    one by one (tail items, pending problems, search items) -- gives, with the device's own per-joint
+    functions, exactly what the every-branch sequence gives, and every list is exercised"""
+    qg, q0, v0, a0 = W.random_states(lim, n, seed) if kind == "random" else W.edge_states(lim, n, seed)
+    gen = Shadow.from_limits(lim).solve(qg, q0, v0, a0)
+    S = ShadowItems.from_limits(lim)
+    it = S.solve(qg, q0, v0, a0)
+    for k in gen:
+        a, b = gen[k], it[k]
+        assert np.array_equal(a, b, equal_nan=True) if a.dtype.kind == "f" else np.array_equal(a, b), k
+    tails, pending, searches, whole = (int(x) for x in S.stats)
+    assert whole == S.whole and pending <= tails
+    if lim in (W.REF_RANDOM6, W.REF_GRID) and kind == "random":
+        assert tails > 0.01 * n and pending > 0
+    if lim is W.REF_RANDOM6 and kind == "random":
+        assert searches > 0
+    if lim is W.FRANKA7 and kind == "random":
+        assert tails == 0 and pending == 0
