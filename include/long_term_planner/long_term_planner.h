@@ -61,7 +61,8 @@ int sign(T val) {
 /// laid out as described in ltp_b200.h (inputs joint-major [dof][n]; trajectories time-major
 /// (samples, n, dof) or one row per (problem, joint)).
 struct BatchPlan {
-  ltp_solution solution;   ///< phase times, directions, cruise speeds, lengths, flags
+  ltp_solution solution;   ///< 64-byte records [dof][n][8] (seven switching times + v_drive), directions,
+                           ///< lengths, flags -- see ltp_b200.h; v_drive as a separate array is optional
   double* q = nullptr;     ///< sampled positions     (may all four be null: solve only)
   double* v = nullptr;     ///< sampled velocities
   double* a = nullptr;     ///< sampled accelerations
