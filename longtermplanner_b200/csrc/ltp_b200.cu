@@ -291,13 +291,18 @@ __device__ __forceinline__ double pack_tail_flags(unsigned mod, unsigned opt_cas
 constexpr int fast_min_blocks(int maxw) {
   return (LTP_FAST_WARPS + maxw / 2) / maxw > 0 ? (LTP_FAST_WARPS + maxw / 2) / maxw : 1;
 }
-template <int MAXW>
+#ifndef LTP_FAST_EXACT
+#define LTP_FAST_EXACT 1
+#endif
+// EXACT: the CTA has exactly MAXW warps (the arm sizes the kernel is specialised for), so the
+// shared-memory offsets are constants and the loops over the joints unroll
+template <int MAXW, bool EXACT = false>
 __global__ void __launch_bounds__(kTile * MAXW, fast_min_blocks(MAXW))
 ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const double* __restrict__ q_goal,
                       const double* __restrict__ q_0, const double* __restrict__ v_0,
                       const double* __restrict__ a_0, DeviceSolution S, SolveScratch X, int items) {
   extern __shared__ unsigned char smem_raw[];
-  const int dof = P.dof;
+  const int dof = EXACT ? MAXW : P.dof;
   const SolveShared sh = carve_shared(smem_raw, dof);
   int* const work_list = X.work_list;
   int* const work_count = X.counters + kCntWork;
@@ -1805,9 +1810,9 @@ static int solve_launch(ltp_planner* p, int64_t n, const double* q_goal, const d
   // its register budget is the largest that still fits the intended number of CTAs per SM
 #define LTP_DISPATCH_FAST(GRID, ...)                                                        \
   do {                                                                                      \
-    if (dof == 6) ltp_solve_fast_kernel<6><<<GRID, block, smem, st>>>(__VA_ARGS__);         \
-    else if (dof == 7) ltp_solve_fast_kernel<7><<<GRID, block, smem, st>>>(__VA_ARGS__);    \
-    else if (dof == 12) ltp_solve_fast_kernel<12><<<GRID, block, smem, st>>>(__VA_ARGS__);  \
+    if (dof == 6) ltp_solve_fast_kernel<6, LTP_FAST_EXACT><<<GRID, block, smem, st>>>(__VA_ARGS__);         \
+    else if (dof == 7) ltp_solve_fast_kernel<7, LTP_FAST_EXACT><<<GRID, block, smem, st>>>(__VA_ARGS__);    \
+    else if (dof == 12) ltp_solve_fast_kernel<12, LTP_FAST_EXACT><<<GRID, block, smem, st>>>(__VA_ARGS__);  \
     else { LTP_DISPATCH_W(ltp_solve_fast_kernel, GRID, __VA_ARGS__); break; }               \
     p->launches++;                                                                          \
   } while (0)
