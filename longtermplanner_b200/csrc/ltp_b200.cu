@@ -291,6 +291,52 @@ __device__ __forceinline__ double pack_tail_flags(unsigned mod, unsigned opt_cas
 constexpr int fast_min_blocks(int maxw) {
   return (LTP_FAST_WARPS + maxw / 2) / maxw > 0 ? (LTP_FAST_WARPS + maxw / 2) / maxw : 1;
 }
+// The closed-form kernel runs stage 1 and attempt 1 with the range test of the prepared-reciprocal
+// divisions deferred (DivDeferred, ltp_math.cuh): one look at a flag per stage instead of a
+// divergent call site per division. The thread whose flag is set -- a zero quotient, e.g. a start at
+// rest, or a quotient near the ends of the exponent range -- discards the stage and repeats it here
+// with every quotient tested where it is computed, out of line; results come back through memory.
+#ifndef LTP_FAST_DEFER
+#define LTP_FAST_DEFER 1
+#endif
+#ifndef LTP_FAST_RV
+#define LTP_FAST_RV 1
+#endif
+struct Stage1Redo {
+  Prologue pro;
+  double t_opt[7];
+  int st;
+  unsigned char mod, opt_case, in_ok;
+};
+__device__ __noinline__ void stage1_checked(const PlannerParams& P, int jt, double qg, double q0, double v0,
+                                            double a0, Stage1Redo* o) {
+  const JointLimits L = P.lim[jt];
+  o->in_ok = check_joint_input(L, q0, v0, a0);
+  o->pro = ost_prologue(L, P.ts, qg, q0, v0, a0);
+  zero7(o->t_opt);
+  o->mod = 0;
+  o->opt_case = 255;
+  o->st = ost_body_t<false, true>(L, P.ts, o->pro, qg, q0, L.v_max, o->t_opt, o->mod, o->opt_case);
+}
+struct Attempt1Redo {
+  double t[7];
+  double v_drive;
+  int c;
+  unsigned char mod, final_case;
+};
+__device__ __noinline__ void attempt1_checked(const PlannerParams& P, int jt, double qg, double q0, double v0,
+                                              double a0, double t_req, unsigned char mod, unsigned char final_case,
+                                              Attempt1Redo* o) {
+  const JointLimits L = P.lim[jt];
+  const Prologue pro = ost_prologue(L, P.ts, qg, q0, v0, a0);
+  const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
+  zero7(o->t);
+  o->v_drive = L.v_max;
+  o->mod = mod;
+  o->final_case = final_case;
+  o->c = time_scaling_attempt1(L, P.ts, pro, I, o->t, o->v_drive, o->mod, o->final_case);
+}
+
 #ifndef LTP_FAST_EXACT
 #define LTP_FAST_EXACT 1
 #endif
@@ -319,12 +365,30 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
   }
   if (jt == 0) sh.arrived[lane] = 0;
   // stage 1 (cc:14-30)
-  const bool in_ok = check_joint_input(L, q0, v0, a0);
-  const Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0);
   double t_opt[7];
   zero7(t_opt);
   unsigned char mod = 0, opt_case = 255;
-  const int st1 = ost_body_t<false>(L, Ts, pro, qg, q0, L.v_max, t_opt, mod, opt_case);
+#if LTP_FAST_DEFER
+  DivDeferred dv;
+  bool in_ok = check_joint_input(L, q0, v0, a0, dv);
+  Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0, dv);
+  int st1 = ost_body_dv<false, LTP_FAST_RV != 0>(L, Ts, pro, qg, q0, L.v_max, t_opt, mod, opt_case, dv);
+  if (dv.bad) {
+    Stage1Redo r;
+    stage1_checked(P, jt, qg, q0, v0, a0, &r);
+    in_ok = r.in_ok != 0;
+    pro = r.pro;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) t_opt[k] = r.t_opt[k];
+    st1 = r.st;
+    mod = r.mod;
+    opt_case = r.opt_case;
+  }
+#else
+  const bool in_ok = check_joint_input(L, q0, v0, a0);
+  const Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0);
+  const int st1 = ost_body_t<false, true>(L, Ts, pro, qg, q0, L.v_max, t_opt, mod, opt_case);
+#endif
   sh.t6[jt * kTile + lane] = t_opt[6];
   sh.flag[jt * kTile + lane] = (unsigned char)((!(in_ok && st1 != OST_FAIL) ? 1 : 0) | (st1 == OST_DEFER ? 2 : 0));
   // item mode: the joints that need the quartic tail are listed below; the barrier that stage 2
@@ -383,7 +447,23 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
       final_case = opt_case;
     } else {
       const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
+#if LTP_FAST_DEFER
+      const unsigned char mod1 = mod;
+      DivDeferred dv2;
+      int c = time_scaling_attempt1(L, Ts, pro, I, t_sc, v_drive, mod, final_case, dv2);
+      if (dv2.bad) {
+        Attempt1Redo r;
+        attempt1_checked(P, jt, qg, q0, v0, a0, t_req, mod1, 255, &r);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t_sc[k] = r.t[k];
+        v_drive = r.v_drive;
+        c = r.c;
+        mod = r.mod;
+        final_case = r.final_case;
+      }
+#else
       const int c = time_scaling_attempt1(L, Ts, pro, I, t_sc, v_drive, mod, final_case);
+#endif
       my_defer = (c == 0);
       need2 = (c == -1) && valid;
       if (items && my_defer && valid) push_search_item(X, p, jt, t_req);  // rare: a nested solve with a tail

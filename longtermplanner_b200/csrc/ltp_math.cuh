@@ -47,7 +47,7 @@ enum : unsigned char {
 struct JointLimits {
   double q_min, q_max, v_max, a_max, j_max;
   // derived once on the host (derive_limits): correctly rounded reciprocals for div_by()
-  double r_a, r_j, a_over_j;
+  double r_a, r_j, a_over_j, r_v;
 };
 
 constexpr double kEps = 4e-3;     // cc:96
@@ -103,10 +103,55 @@ LTP_HD double div_by(double x, double d, double rd) {
 LTP_HD double div3(double x) { return div_by(x, 3.0, 1.0 / 3.0); }
 LTP_HD double div12(double x) { return div_by(x, 12.0, 1.0 / 12.0); }
 
+// Two ways to run the range test of div_by, as a policy object that the closed-form functions
+// below take as their last argument (the signatures without it use DivChecked):
+//   DivChecked   tests every quotient where it is computed and takes the plain division at once
+//   DivDeferred  only records that some quotient left the range; the caller looks at `bad` once
+//                the function is through and, if set, discards everything and calls the function
+//                again with DivChecked. Same results by construction -- a run with no quotient out
+//                of range executes the same operations either way -- but the three FP64
+//                operations of a division are then followed by two integer instructions instead
+//                of a divergent call (six), and straight-line code is not cut into a basic block
+//                per division. A zero numerator is not out of range here (see below).
+struct DivChecked {
+  LTP_HD double by(double x, double d, double rd) const { return div_by(x, d, rd); }
+  LTP_HD double by3(double x) const { return div3(x); }
+  LTP_HD double by12(double x) const { return div12(x); }
+};
+struct DivDeferred {
+  bool bad = false;
+  LTP_HD double by(double x, double d, double rd) {
+    const double q = x * rd;
+    // The remainder is exact, so its rounding mode only decides the sign of an exact zero; rounded
+    // down, a zero remainder is -0 and the correction step leaves the sign of q alone. That makes
+    // the three operations return x / d = +-0 with the right sign for a zero numerator (rounded
+    // to nearest, -0 / d came out as +0), so a zero numerator needs no other path.
+#ifdef __CUDA_ARCH__
+    const double r = __fma_rd(-q, d, x);
+    const double f = fma(r, rd, q);
+    const unsigned hi = (unsigned)__double2hiint(f);
+#else
+    double r = fma(-q, d, x);
+    if (r == 0.0) r = -0.0;  // what round-down gives: the two addends are never both +0
+    const double f = fma(r, rd, q);
+    unsigned long long bits;
+    memcpy(&bits, &f, 8);
+    const unsigned hi = (unsigned)(bits >> 32);
+#endif
+    // the same window as div_by, on the high word shifted left by one (drops the sign); a zero
+    // numerator is exempt
+    bad |= (((hi << 1) - (64u << 21)) > (1918u << 21)) & (x != 0.0);
+    return f;
+  }
+  LTP_HD double by3(double x) { return by(x, 3.0, 1.0 / 3.0); }
+  LTP_HD double by12(double x) { return by(x, 12.0, 1.0 / 12.0); }
+};
+
 LTP_HD void derive_limits(JointLimits& L) {
   L.r_a = 1.0 / L.a_max;
   L.r_j = 1.0 / L.j_max;
   L.a_over_j = L.a_max / L.j_max;
+  L.r_v = 1.0 / L.v_max;
 }
 
 // h:54-56: (double)((0 < x) - (x < 0)), written as two selects (no int -> double conversion);
@@ -118,21 +163,22 @@ LTP_HD double neg_sgn(double x) { return x > 0.0 ? -1.0 : (x < 0.0 ? 1.0 : 0.0);
 // ------------------------------------------------------------------------------------
 // cc:650-701. Returns the signed stop displacement; T[0..2] are the three durations.
 // ------------------------------------------------------------------------------------
+template <class DIV>
 LTP_HD double brake_profile(const JointLimits& L, double Ts, double v_0, double a_0,
-                            double& T0, double& T1, double& T2, double& dir) {
+                            double& T0, double& T1, double& T2, double& dir, DIV& dv) {
   const double A = L.a_max, J = L.j_max;
   // cc:658-664 without the three-way branch: both tests are evaluated, one select picks the
   // operand whose sign decides (same values; a warp does not split three ways here)
   const bool same_sign = v_0 * a_0 > 0;
-  const bool fast_enough = fabs(v_0) > div_by(1.0 / 2.0 * sq(a_0), J, L.r_j);
+  const bool fast_enough = fabs(v_0) > dv.by(1.0 / 2.0 * sq(a_0), J, L.r_j);
   dir = neg_sgn((same_sign | fast_enough) ? v_0 : a_0);
   if (dir < 0) {
     a_0 = -a_0;
     v_0 = -v_0;
   }
-  T0 = div_by(A - a_0, J, L.r_j);
+  T0 = dv.by(A - a_0, J, L.r_j);
   T2 = L.a_over_j;
-  T1 = div_by(-v_0 - 1.0 / 2.0 * T0 * a_0, A, L.r_a) - 1.0 / 2.0 * (T0 + T2);
+  T1 = dv.by(-v_0 - 1.0 / 2.0 * T0 * a_0, A, L.r_a) - 1.0 / 2.0 * (T0 + T2);
   if (T1 < -Ts) {
     T0 = -a_0 / J + sqrt(sq(a_0) / (2 * sq(J)) - v_0 / J);
     T2 = T0 + a_0 / J;
@@ -144,6 +190,12 @@ LTP_HD double brake_profile(const JointLimits& L, double Ts, double v_0, double 
                   1.0 / 2.0 * T0 * sq(T2)) +
              A * (1.0 / 2.0 * sq(T1) + T1 * T2);
   return dir * s;
+}
+
+LTP_HD double brake_profile(const JointLimits& L, double Ts, double v_0, double a_0,
+                            double& T0, double& T1, double& T2, double& dir) {
+  DivChecked dv;
+  return brake_profile(L, Ts, v_0, a_0, T0, T1, T2, dir, dv);
 }
 
 // ------------------------------------------------------------------------------------
@@ -430,11 +482,12 @@ struct Prologue {
   bool brake_only;      // cc:102
 };
 
+template <class DIV>
 LTP_HD Prologue ost_prologue(const JointLimits& L, double Ts, double q_goal, double q_0,
-                             double v_0, double a_0) {
+                             double v_0, double a_0, DIV& dv) {
   Prologue P;
   double dirb;
-  double q_stop = brake_profile(L, Ts, v_0, a_0, P.b0, P.b1, P.b2, dirb);
+  double q_stop = brake_profile(L, Ts, v_0, a_0, P.b0, P.b1, P.b2, dirb, dv);
   double q_diff = q_goal - (q_0 + q_stop);
   P.brake_only = fabs(q_diff) < kEps;
   if (P.brake_only) {
@@ -455,6 +508,12 @@ LTP_HD Prologue ost_prologue(const JointLimits& L, double Ts, double q_goal, dou
   return P;
 }
 
+LTP_HD Prologue ost_prologue(const JointLimits& L, double Ts, double q_goal, double q_0,
+                             double v_0, double a_0) {
+  DivChecked dv;
+  return ost_prologue(L, Ts, q_goal, q_0, v_0, a_0, dv);
+}
+
 LTP_HD void cumsum7(const double* T, double* t) {
   double acc = T[0];
   t[0] = acc;
@@ -463,6 +522,46 @@ LTP_HD void cumsum7(const double* T, double* t) {
     acc = acc + T[i];
     t[i] = acc;
   }
+}
+
+// any of T[0..6] < lim (a NaN is not). On the device this is spelled as a chain of seven
+// compare-and-accumulate instructions: left to itself the compiler turns the OR of the seven
+// compares into a minimum reduction, and an FP64 minimum is eight instructions here.
+LTP_HD bool any_below7(const double* T, double lim) {
+#ifdef __CUDA_ARCH__
+  unsigned r;
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.lt.f64 p, %1, %8;\n\t"
+      "setp.lt.or.f64 p, %2, %8, p;\n\t"
+      "setp.lt.or.f64 p, %3, %8, p;\n\t"
+      "setp.lt.or.f64 p, %4, %8, p;\n\t"
+      "setp.lt.or.f64 p, %5, %8, p;\n\t"
+      "setp.lt.or.f64 p, %6, %8, p;\n\t"
+      "setp.lt.or.f64 p, %7, %8, p;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "d"(T[0]), "d"(T[1]), "d"(T[2]), "d"(T[3]), "d"(T[4]), "d"(T[5]), "d"(T[6]), "d"(lim));
+  return r != 0;
+#else
+  bool below = false;
+  for (int i = 0; i < 7; ++i) below |= T[i] < lim;
+  return below;
+#endif
+}
+
+LTP_HD bool any_below2(double a, double b, double lim) {
+#ifdef __CUDA_ARCH__
+  unsigned r;
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.lt.f64 p, %1, %3;\n\t"
+      "setp.lt.or.f64 p, %2, %3, p;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "d"(a), "d"(b), "d"(lim));
+  return r != 0;
+#else
+  return a < lim || b < lim;
+#endif
 }
 
 LTP_HD void zero7(double* t) {
@@ -540,9 +639,11 @@ LTP_HD_NOINLINE unsigned char ost_quartic_tail(const JointLimits& L, const Prolo
 // and the caller must hand the problem to the generic kernel.
 enum { OST_FAIL = 0, OST_OK = 1, OST_DEFER = 2 };
 
-template <bool ALLOW_TAIL>
-LTP_HD int ost_body_t(const JointLimits& L, double Ts, const Prologue& P, double q_goal, double q_0,
-                      double V, double* t, unsigned char& mod, unsigned char& kase) {
+// V_IS_VMAX: the caller passes V = L.v_max (the time-optimal solve of stage 1), so the one
+// division by the cruise speed can use the reciprocal prepared on the host like the others.
+template <bool ALLOW_TAIL, bool V_IS_VMAX, class DIV>
+LTP_HD int ost_body_dv(const JointLimits& L, double Ts, const Prologue& P, double q_goal, double q_0,
+                       double V, double* t, unsigned char& mod, unsigned char& kase, DIV& dv) {
   const double A = L.a_max, J = L.j_max;
   const double eps = kEps;
   double T[7];
@@ -556,20 +657,20 @@ LTP_HD int ost_body_t(const JointLimits& L, double Ts, const Prologue& P, double
   }
   const double v_0 = P.v0m, a_0 = P.a0m;
   double q_brake = 0.0;
-  if (v_0 + div_by(0.5 * a_0 * fabs(a_0), J, L.r_j) > V) {  // cc:119-122
+  if (v_0 + dv.by(0.5 * a_0 * fabs(a_0), J, L.r_j) > V) {  // cc:119-122
     mod = 1;
     flags |= F_MOD;
     double unused;
-    q_brake = brake_profile(L, Ts, v_0 - V, a_0, T[0], T[1], T[2], unused);
+    q_brake = brake_profile(L, Ts, v_0 - V, a_0, T[0], T[1], T[2], unused, dv);
   } else {  // cc:125-143
-    T[0] = div_by(A - a_0, J, L.r_j);
+    T[0] = dv.by(A - a_0, J, L.r_j);
     T[2] = L.a_over_j;
-    T[1] = div_by(V - v_0 - 0.5 * T[0] * a_0, A, L.r_a) - 0.5 * (T[0] + T[2]);
+    T[1] = dv.by(V - v_0 - 0.5 * T[0] * a_0, A, L.r_a) - 0.5 * (T[0] + T[2]);
     if (T[1] < -eps) {
       double rad = J * (V - v_0) + 0.5 * sq(a_0);
       if (rad > 0) {
-        T[2] = div_by(sqrt(rad), J, L.r_j);
-        T[0] = T[2] - div_by(a_0, J, L.r_j);
+        T[2] = dv.by(sqrt(rad), J, L.r_j);
+        T[0] = T[2] - dv.by(a_0, J, L.r_j);
         T[1] = 0;
         flags |= F_NOP2;
       } else {
@@ -582,9 +683,9 @@ LTP_HD int ost_body_t(const JointLimits& L, double Ts, const Prologue& P, double
   // cc:147-165
   T[4] = L.a_over_j;
   T[6] = T[4];
-  T[5] = div_by(V, A, L.r_a) - 1.0 / 2.0 * (T[4] + T[6]);
+  T[5] = dv.by(V, A, L.r_a) - 1.0 / 2.0 * (T[4] + T[6]);
   if (T[5] < -eps) {
-    double rad = div_by(V, J, L.r_j);
+    double rad = dv.by(V, J, L.r_j);
     if (rad > 0) {
       T[4] = sqrt(rad);
       T[6] = T[4];
@@ -610,7 +711,7 @@ LTP_HD int ost_body_t(const JointLimits& L, double Ts, const Prologue& P, double
   double part2 = J * (1.0 / 6.0 * pow3(T[6]) + 1.0 / 2.0 * sq(T[6]) * (T[5] + T[4]) -
                       1.0 / 6.0 * pow3(T[4]) + 1.0 / 2.0 * T[6] * sq(T[4])) +
                  A * (1.0 / 2.0 * sq(T[5]) + T[5] * T[4]);
-  T[3] = (P.dist - part1 - part2) / V;
+  T[3] = V_IS_VMAX ? dv.by(P.dist - part1 - part2, L.v_max, L.r_v) : (P.dist - part1 - part2) / V;
 
   unsigned char base = (unsigned char)(1 + ((flags & F_NOP2) ? 1 : 0) + ((flags & F_NOP6) ? 2 : 0));
 
@@ -624,17 +725,17 @@ LTP_HD int ost_body_t(const JointLimits& L, double Ts, const Prologue& P, double
     double rad = (sq(J) * pow4(T[0])) / 2 - (sq(J) * pow4(T[2])) / 4 +
                  (sq(J) * sq(T[2]) * sq(T[4])) / 2 - (sq(J) * pow4(T[4])) / 4 +
                  (sq(J) * pow4(T[6])) / 2 + 2.0 * J * a_0 * pow3(T[0]) -
-                 div3(2.0 * J * A * pow3(T[0])) - 2.0 * J * A * T[0] * sq(T[2]) +
-                 div3(2.0 * J * A * pow3(T[2])) + div3(2.0 * J * A * pow3(T[4])) -
-                 2.0 * J * A * sq(T[4]) * T[6] - div3(2.0 * J * A * pow3(T[6])) +
+                 dv.by3(2.0 * J * A * pow3(T[0])) - 2.0 * J * A * T[0] * sq(T[2]) +
+                 dv.by3(2.0 * J * A * pow3(T[2])) + dv.by3(2.0 * J * A * pow3(T[4])) -
+                 2.0 * J * A * sq(T[4]) * T[6] - dv.by3(2.0 * J * A * pow3(T[6])) +
                  2.0 * J * v_0 * sq(T[0]) + 2.0 * sq(a_0) * sq(T[0]) - 2.0 * a_0 * A * sq(T[0]) -
                  2.0 * a_0 * A * sq(T[2]) + 4 * a_0 * v_0 * T[0] + 2.0 * sq(A) * sq(T[2]) +
                  2.0 * sq(A) * sq(T[4]) - 4 * A * v_0 * T[0] + 4 * P.dist * A + 2.0 * sq(v_0);
     if (rad > 0) {  // cc:224-236
       // x / (4 A) == (x / A) / 4 bit for bit (scaling by 4 is exact)
-      T[5] = 0.25 * div_by(-(4 * A * T[4] - 2.0 * sqrt(rad) + J * sq(T[2]) - J * sq(T[4]) + 2.0 * J * sq(T[6])),
+      T[5] = 0.25 * dv.by(-(4 * A * T[4] - 2.0 * sqrt(rad) + J * sq(T[2]) - J * sq(T[4]) + 2.0 * J * sq(T[6])),
                            A, L.r_a);
-      T[1] = div_by(-v_0 - a_0 * T[0] - 1.0 / 2.0 * J * sq(T[0]) + 1.0 / 2.0 * J * sq(T[2]) +
+      T[1] = dv.by(-v_0 - a_0 * T[0] - 1.0 / 2.0 * J * sq(T[0]) + 1.0 / 2.0 * J * sq(T[2]) +
                         1.0 / 2.0 * J * sq(T[6]) - 1.0 / 2.0 * J * sq(T[4]),
                     A, L.r_a) -
              T[2] + T[5] + T[4];
@@ -645,19 +746,15 @@ LTP_HD int ost_body_t(const JointLimits& L, double Ts, const Prologue& P, double
       kase = CASE_DEGENERATE | flags;
       return OST_OK;
     }
-    if (T[5] < -eps || T[1] < -eps) {
+    if (any_below2(T[5], T[1], -eps)) {
       if (!ALLOW_TAIL) return OST_DEFER;
       base = ost_quartic_tail(L, P, q_goal, q_0, T, flags);
     }
   }
   // cc:340-348
-#pragma unroll
   // (the reference's second test, T < 0 && T >= -eps, is T < 0 once T < -eps is excluded;
   // a NaN fails both and stays)
-  bool below = false;
-#pragma unroll
-  for (int i = 0; i < 7; ++i) below |= T[i] < -eps;
-  if (below) {
+  if (any_below7(T, -eps)) {
     kase = CASE_FAIL_UNTOUCHED | flags;
     return OST_FAIL;
   }
@@ -667,6 +764,13 @@ LTP_HD int ost_body_t(const JointLimits& L, double Ts, const Prologue& P, double
   cumsum7(T, t);  // cc:351
   kase = base | flags;
   return OST_OK;
+}
+
+template <bool ALLOW_TAIL, bool V_IS_VMAX = false>
+LTP_HD int ost_body_t(const JointLimits& L, double Ts, const Prologue& P, double q_goal, double q_0,
+                      double V, double* t, unsigned char& mod, unsigned char& kase) {
+  DivChecked dv;
+  return ost_body_dv<ALLOW_TAIL, V_IS_VMAX>(L, Ts, P, q_goal, q_0, V, t, mod, kase, dv);
 }
 
 LTP_HD bool ost_body(const JointLimits& L, double Ts, const Prologue& P, double q_goal, double q_0,
@@ -682,16 +786,22 @@ struct TsInput {
   double q_goal, q_0, v_0, a_0, dir, tr;
 };
 
-LTP_HD double ts_candidate1(const JointLimits& L, const TsInput& I) {
+template <class DIV>
+LTP_HD double ts_candidate1(const JointLimits& L, const TsInput& I, DIV& dv) {
   const double A = L.a_max, J = L.j_max, a_0 = I.a_0, v_0 = I.v_0, tr = I.tr, dir = I.dir;
-  return div_by(A * J * tr / 2 - sq(a_0) / 4 + a_0 * A / 2 - sq(A) / 2 + v_0 * J / 2 -
-                    div12(sqrt(36 * sq(A) * sq(J) * sq(tr) - 36 * sq(a_0) * A * J * tr +
+  return dv.by(A * J * tr / 2 - sq(a_0) / 4 + a_0 * A / 2 - sq(A) / 2 + v_0 * J / 2 -
+                    dv.by12(sqrt(36 * sq(A) * sq(J) * sq(tr) - 36 * sq(a_0) * A * J * tr +
                                72.0 * a_0 * sq(A) * J * tr - 72.0 * pow3(A) * J * tr +
                                144 * A * dir * sq(J) * I.q_0 - 144 * A * dir * sq(J) * I.q_goal +
                                72.0 * A * sq(J) * v_0 * tr - 9 * pow4(a_0) + 12.0 * pow3(a_0) * A +
                                36 * sq(a_0) * sq(A) + 36 * sq(a_0) * J * v_0 - 72.0 * a_0 * pow3(A) -
                                72.0 * a_0 * A * J * v_0 + 36 * pow4(A) - 36 * sq(J) * sq(v_0))),
                 J, L.r_j);
+}
+
+LTP_HD double ts_candidate1(const JointLimits& L, const TsInput& I) {
+  DivChecked dv;
+  return ts_candidate1(L, I, dv);
 }
 
 LTP_HD double ts_candidate2(const JointLimits& L, const TsInput& I) {
@@ -838,21 +948,29 @@ LTP_HD void ts_fail_state(const JointLimits& L, double* scaled_t, double& v_driv
 // solve needs the quartic tail: the caller defers the whole problem to the generic kernel) or
 // -1 (rejected: go on with attempt 2). attempt2 returns 2 (accepted) or 0 (the joint needs the
 // root-solver attempts 3..8 or a quartic tail: defer).
+template <class DIV>
 LTP_HD int time_scaling_attempt1(const JointLimits& L, double Ts, const Prologue& P, const TsInput& I,
                                  double* scaled_t, double& v_drive, unsigned char& mod,
-                                 unsigned char& final_case) {
+                                 unsigned char& final_case, DIV& dv) {
   if (ts_brake_only_rejects(P, I.tr)) {
     ts_fail_state(L, scaled_t, v_drive, mod, final_case);
     return 9;
   }
-  const double V = ts_candidate1(L, I);
+  const double V = ts_candidate1(L, I, dv);
   v_drive = V;
   if (!isnan(V) && V > 0) {
-    const int st = ost_body_t<false>(L, Ts, P, I.q_goal, I.q_0, V, scaled_t, mod, final_case);
+    const int st = ost_body_dv<false, false>(L, Ts, P, I.q_goal, I.q_0, V, scaled_t, mod, final_case, dv);
     if (st == OST_DEFER) return 0;
     if (st == OST_OK && I.tr - scaled_t[6] < kTol && I.tr - scaled_t[6] > -kTol / 10) return 1;
   }
   return -1;
+}
+
+LTP_HD int time_scaling_attempt1(const JointLimits& L, double Ts, const Prologue& P, const TsInput& I,
+                                 double* scaled_t, double& v_drive, unsigned char& mod,
+                                 unsigned char& final_case) {
+  DivChecked dv;
+  return time_scaling_attempt1(L, Ts, P, I, scaled_t, v_drive, mod, final_case, dv);
 }
 
 LTP_HD int time_scaling_attempt2(const JointLimits& L, double Ts, const Prologue& P, const TsInput& I,
@@ -919,10 +1037,16 @@ LTP_HD TsInput make_ts_input(double q_goal, double q_0, double v_0, double a_0, 
 }
 
 // cc:68-77 for one joint
-LTP_HD bool check_joint_input(const JointLimits& L, double q_0, double v_0, double a_0) {
+template <class DIV>
+LTP_HD bool check_joint_input(const JointLimits& L, double q_0, double v_0, double a_0, DIV& dv) {
   if (q_0 < L.q_min || q_0 > L.q_max || fabs(v_0) > L.v_max || fabs(a_0) > L.a_max) return false;
-  if (fabs(v_0 + div_by(0.5 * a_0 * fabs(a_0), L.j_max, L.r_j)) > L.v_max) return false;
+  if (fabs(v_0 + dv.by(0.5 * a_0 * fabs(a_0), L.j_max, L.r_j)) > L.v_max) return false;
   return true;
+}
+
+LTP_HD bool check_joint_input(const JointLimits& L, double q_0, double v_0, double a_0) {
+  DivChecked dv;
+  return check_joint_input(L, q_0, v_0, a_0, dv);
 }
 
 // cc:718 for one joint: (int)ceil(t6/Ts) + 1, or 0 when the time is not representable

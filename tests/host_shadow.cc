@@ -37,6 +37,82 @@ void* shadow_create(int dof, double ts, const double* q_min, const double* q_max
 }
 void shadow_destroy(void* h) { delete static_cast<Shadow*>(h); }
 
+// div_by(x, d, RN(1/d)) against the plain division x / d on n numerators: returns the number of
+// results whose bits differ (NaNs compare equal to NaNs) and leaves the first offender in *bad
+int64_t shadow_div_by_mismatches(double d, int64_t n, const double* x, double* bad) {
+  const double rd = 1.0 / d;
+  int64_t miss = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const double a = div_by(x[i], d, rd), b = x[i] / d;
+    if (std::memcmp(&a, &b, 8) != 0 && !(a != a && b != b)) {
+      if (miss == 0 && bad) *bad = x[i];
+      ++miss;
+    }
+  }
+  return miss;
+}
+
+// Stage 1 and attempt 1 of the closed-form kernel with the range test of the divisions deferred
+// (DivDeferred) against the same functions with every quotient tested in place (DivChecked): an
+// item whose deferred run is not flagged must have the bits of the checked run (a flagged item is
+// recomputed by the checked functions on the device, so there is nothing to compare). Returns the
+// number of unflagged items that differ; flagged[0] / flagged[1] count the flagged stage-1 / attempt-1 runs.
+static bool same_bits(const void* a, const void* b, size_t n) { return std::memcmp(a, b, n) == 0; }
+
+int64_t shadow_deferred_vs_checked(void* h, int64_t n, const int* joint, const double* q_goal, const double* q_0,
+                                   const double* v_0, const double* a_0, const double* t_req, int64_t* flagged) {
+  Shadow* s = static_cast<Shadow*>(h);
+  int64_t miss = 0, flg = 0, flg2 = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const JointLimits& L = s->lim[joint ? joint[i] : 0];
+    // stage 1
+    DivDeferred dv;
+    const bool in_d = check_joint_input(L, q_0[i], v_0[i], a_0[i], dv);
+    const Prologue pd = ost_prologue(L, s->ts, q_goal[i], q_0[i], v_0[i], a_0[i], dv);
+    double td[7];
+    zero7(td);
+    unsigned char md = 0, cd = 255;
+    const int sd = ost_body_dv<false, true>(L, s->ts, pd, q_goal[i], q_0[i], L.v_max, td, md, cd, dv);
+    const bool in_c = check_joint_input(L, q_0[i], v_0[i], a_0[i]);
+    const Prologue pc = ost_prologue(L, s->ts, q_goal[i], q_0[i], v_0[i], a_0[i]);
+    double tc[7];
+    zero7(tc);
+    unsigned char mc = 0, cc = 255;
+    const int sc = ost_body_t<false, true>(L, s->ts, pc, q_goal[i], q_0[i], L.v_max, tc, mc, cc);
+    if (dv.bad) {
+      ++flg;
+    } else {
+      const double fd[7] = {pd.v0m, pd.a0m, pd.dir, pd.dist, pd.b0, pd.b1, pd.b2};
+      const double fc[7] = {pc.v0m, pc.a0m, pc.dir, pc.dist, pc.b0, pc.b1, pc.b2};
+      if (in_d != in_c || sd != sc || md != mc || cd != cc || pd.brake_only != pc.brake_only ||
+          !same_bits(fd, fc, 56) || !same_bits(td, tc, 56)) {
+        ++miss;
+        continue;
+      }
+    }
+    // attempt 1 from the checked prologue (what the device has at that point either way)
+    const TsInput I = make_ts_input(q_goal[i], q_0[i], v_0[i], a_0[i], pc.dir, t_req[i]);
+    DivDeferred dv2;
+    double ad[7], ac[7];
+    zero7(ad);
+    zero7(ac);
+    double vd = L.v_max, vc = L.v_max;
+    unsigned char m2d = mc, m2c = mc, fcd = 255, fcc = 255;
+    const int rd = time_scaling_attempt1(L, s->ts, pc, I, ad, vd, m2d, fcd, dv2);
+    const int rc = time_scaling_attempt1(L, s->ts, pc, I, ac, vc, m2c, fcc);
+    if (dv2.bad) {
+      ++flg2;
+    } else if (rd != rc || m2d != m2c || fcd != fcc || !same_bits(&vd, &vc, 8) || !same_bits(ad, ac, 56)) {
+      ++miss;
+    }
+  }
+  if (flagged) {
+    flagged[0] = flg;
+    flagged[1] = flg2;
+  }
+  return miss;
+}
+
 void shadow_opt_braking_items(void* h, int64_t n, const int* joint, const double* v_0, const double* a_0,
                               double* q, double* t_rel3, double* dir) {
   Shadow* s = static_cast<Shadow*>(h);
@@ -173,7 +249,7 @@ int64_t shadow_solve_batch_auto(void* h, int64_t n, const double* q_goal, const 
       zero7(t);
       mod[o + j] = 0;
       opt_case[o + j] = 255;
-      int st = ost_body_t<false>(L, s->ts, pro[j], q_goal[o + j], q_0[o + j], L.v_max, t, mod[o + j], opt_case[o + j]);
+      int st = ost_body_t<false, true>(L, s->ts, pro[j], q_goal[o + j], q_0[o + j], L.v_max, t, mod[o + j], opt_case[o + j]);
       any_fail |= !(in_ok && st != OST_FAIL);
       defer |= st == OST_DEFER;
       dir[o + j] = pro[j].dir;
@@ -269,7 +345,7 @@ int64_t shadow_solve_batch_items(void* h, int64_t n, const double* q_goal, const
       double t[7];
       zero7(t);
       unsigned char m = 0, oc = 255;
-      const int st = ost_body_t<false>(L, Ts, pro[j], q_goal[o + j], q_0[o + j], L.v_max, t, m, oc);
+      const int st = ost_body_t<false, true>(L, Ts, pro[j], q_goal[o + j], q_0[o + j], L.v_max, t, m, oc);
       dir[o + j] = pro[j].dir;
       bool ok = st == OST_OK;
       if (st == OST_DEFER) {

@@ -1,6 +1,6 @@
 """Kernel-level timing of the solve (configs[1], 2^20 Franka problems) and of the time-major
 sampler (configs[2]) through the library's own event hooks. Used to compare builds:
-  LTP_B200_LIB=/path/to/variant.so python tools/solve_timing.py"""
+  LTP_B200_LIB=/path/to/variant.so python tools/solve_timing.py [7|12] [rest]"""
 import os
 import sys
 
@@ -13,6 +13,9 @@ lim = W.FRANKA7 if len(sys.argv) < 2 or sys.argv[1] != "12" else W.FRANKA12
 n = 1 << 20
 ltp = LongTermPlanner(lim.dof, lim.t_sample, *lim.arrays(), device=0)
 ins = [torch.from_numpy(W.to_joint_major(x)).cuda() for x in W.random_states(lim, n, W.SEEDS[2])]
+if len(sys.argv) > 2 and sys.argv[2] == "rest":  # every problem starts at rest: zero numerators
+    ins[2].zero_()
+    ins[3].zero_()
 sol = ltp.alloc_solution(n)
 for _ in range(3):
     ltp.solve(*ins, out=sol)
