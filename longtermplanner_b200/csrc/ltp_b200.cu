@@ -337,6 +337,24 @@ __device__ __noinline__ void attempt1_checked(const PlannerParams& P, int jt, do
   o->c = time_scaling_attempt1(L, P.ts, pro, I, o->t, o->v_drive, o->mod, o->final_case);
 }
 
+struct Attempt2Redo {
+  double t[7];
+  double v_drive;
+  int c;
+  unsigned char mod, final_case;
+};
+__device__ __noinline__ void attempt2_checked(const PlannerParams& P, int jt, double qg, double q0, double v0,
+                                              double a0, double t_req, Attempt2Redo* o) {
+  const JointLimits L = P.lim[jt];
+  const Prologue pro = ost_prologue(L, P.ts, qg, q0, v0, a0);
+  const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
+  zero7(o->t);
+  o->v_drive = L.v_max;
+  o->mod = 0;
+  o->final_case = 255;
+  o->c = time_scaling_attempt2(L, P.ts, pro, I, o->t, o->v_drive, o->mod, o->final_case);
+}
+
 #ifndef LTP_FAST_EXACT
 #define LTP_FAST_EXACT 1
 #endif
@@ -562,13 +580,31 @@ ltp_solve_attempt2_kernel(const __grid_constant__ PlannerParams P, int64_t n, De
     // stored here is overwritten there, and a look at traj_len first costs a second trip to
     // memory per entry)
     const JointLimits L = P.lim[jt];
-    const Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0);
-    const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
     double t[7];
     zero7(t);
     double v_drive = L.v_max;
     unsigned char mod = 0, final_case = 255;
+#if LTP_FAST_DEFER
+    // deferred range test of the divisions, as in the closed-form kernel
+    DivDeferred dv;
+    const Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0, dv);
+    const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
+    int c = time_scaling_attempt2(L, Ts, pro, I, t, v_drive, mod, final_case, dv);
+    if (dv.bad) {
+      Attempt2Redo r;
+      attempt2_checked(P, jt, qg, q0, v0, a0, t_req, &r);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) t[k] = r.t[k];
+      v_drive = r.v_drive;
+      c = r.c;
+      mod = r.mod;
+      final_case = r.final_case;
+    }
+#else
+    const Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0);
+    const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
     const int c = time_scaling_attempt2(L, Ts, pro, I, t, v_drive, mod, final_case);
+#endif
     double m = t[0];
 #pragma unroll
     for (int k = 1; k < 7; ++k)

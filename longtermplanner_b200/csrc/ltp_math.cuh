@@ -48,6 +48,8 @@ struct JointLimits {
   double q_min, q_max, v_max, a_max, j_max;
   // derived once on the host (derive_limits): correctly rounded reciprocals for div_by()
   double r_a, r_j, a_over_j, r_v;
+  // for the second cruise-speed candidate (ts_candidate2): reciprocals of J^2, J^3, 6 J^3, A J
+  double r_j2, r_j3, r_6j3, r_aj;
 };
 
 constexpr double kEps = 4e-3;     // cc:96
@@ -117,6 +119,22 @@ struct DivChecked {
   LTP_HD double by(double x, double d, double rd) const { return div_by(x, d, rd); }
   LTP_HD double by3(double x) const { return div3(x); }
   LTP_HD double by12(double x) const { return div12(x); }
+  // x / (2 d): half the quotient (exact) unless the quotient is outside the window, where the
+  // halving could round a second time -- then the plain division by 2 d
+  LTP_HD double half_by(double x, double d, double rd) const {
+    const double q = x * rd;
+    const double r = fma(-q, d, x);
+    const double f = fma(r, rd, q);
+#ifdef __CUDA_ARCH__
+    const unsigned hi = (unsigned)__double2hiint(f);
+#else
+    unsigned long long bits;
+    memcpy(&bits, &f, 8);
+    const unsigned hi = (unsigned)(bits >> 32);
+#endif
+    if (((hi & 0x7ff00000u) - (64u << 20)) > (1918u << 20)) return div_slow(x, 2.0 * d);
+    return 0.5 * f;
+  }
 };
 struct DivDeferred {
   bool bad = false;
@@ -145,6 +163,7 @@ struct DivDeferred {
   }
   LTP_HD double by3(double x) { return by(x, 3.0, 1.0 / 3.0); }
   LTP_HD double by12(double x) { return by(x, 12.0, 1.0 / 12.0); }
+  LTP_HD double half_by(double x, double d, double rd) { return 0.5 * by(x, d, rd); }
 };
 
 LTP_HD void derive_limits(JointLimits& L) {
@@ -152,6 +171,10 @@ LTP_HD void derive_limits(JointLimits& L) {
   L.r_j = 1.0 / L.j_max;
   L.a_over_j = L.a_max / L.j_max;
   L.r_v = 1.0 / L.v_max;
+  L.r_j2 = 1.0 / sq(L.j_max);
+  L.r_j3 = 1.0 / pow3(L.j_max);
+  L.r_6j3 = 1.0 / (6 * pow3(L.j_max));
+  L.r_aj = 1.0 / (L.a_max * L.j_max);
 }
 
 // h:54-56: (double)((0 < x) - (x < 0)), written as two selects (no int -> double conversion);
@@ -804,7 +827,37 @@ LTP_HD double ts_candidate1(const JointLimits& L, const TsInput& I) {
   return ts_candidate1(L, I, dv);
 }
 
+// cc:408-436. The reference's 17 divisions by 2J, A, 6J^3, 2J^3, 2J^2, J, 2AJ and AJ go through the
+// reciprocals prepared on the host (x / (2 d) as half of x / d: scaling by two is exact; 1.0 / J is
+// the reciprocal itself); the last one, by a sum, is a plain division. Same bits as the expression
+// written with '/' (ts_candidate2_plain below; tests/test_devmath_host.py compares the two).
+template <class DIV>
+LTP_HD double ts_candidate2(const JointLimits& L, const TsInput& I, DIV& dv) {
+  const double A = L.a_max, J = L.j_max, a_0 = I.a_0, v_0 = I.v_0, tr = I.tr, dir = I.dir;
+  // w, h, g: sub-expressions the reference writes out repeatedly (cc:413-431)
+  const double w = dv.by(v_0 + dv.half_by(a_0 * (a_0 - A), J, L.r_j), A, L.r_a);
+  const double h = 0.5 * L.a_over_j;
+  const double g = dv.half_by(a_0 - A, J, L.r_j);
+  const double sA = a_0 + A;
+  const double J2 = sq(J), J3 = pow3(J), J3x6 = 6 * J3, AJ = A * J;
+  return -(dir * (I.q_0 - I.q_goal) -
+           J * (dv.by(pow3(sA), J3x6, L.r_6j3) - dv.by(pow3(A), J3x6, L.r_6j3) +
+                dv.half_by(sq(A) * sA, J3, L.r_j3) + dv.half_by(sq(sA) * (w + h + g), J2, L.r_j2)) +
+           a_0 * (dv.half_by(sq(sA), J2, L.r_j2) + dv.half_by(sq(A), J2, L.r_j2) +
+                  dv.by(sA * (w + h + g), J, L.r_j)) -
+           A * (sq(w - h + g) / 2 + dv.by(A * (w - h + g), J, L.r_j)) + v_0 * (w + dv.by(sA, J, L.r_j) + h + g)) /
+         (h - dv.by(v_0, A, L.r_a) + A * (dv.by(w - h + g, A, L.r_a) + L.r_j) -
+          dv.half_by(sq(a_0) + 2.0 * a_0 * A + 4 * sq(A) - 2.0 * J * tr * A + 2.0 * J * v_0, AJ, L.r_aj) +
+          dv.half_by(sq(sA), AJ, L.r_aj) - dv.by(a_0 * sA, AJ, L.r_aj));
+}
+
 LTP_HD double ts_candidate2(const JointLimits& L, const TsInput& I) {
+  DivChecked dv;
+  return ts_candidate2(L, I, dv);
+}
+
+// the same expression with the reference's divisions written out (test oracle for the above)
+LTP_HD double ts_candidate2_plain(const JointLimits& L, const TsInput& I) {
   const double A = L.a_max, J = L.j_max, a_0 = I.a_0, v_0 = I.v_0, tr = I.tr, dir = I.dir;
   // w, h, g: sub-expressions the reference writes out repeatedly (cc:413-431)
   const double w = (v_0 + (a_0 * (a_0 - A)) / (2.0 * J)) / A;
@@ -973,17 +1026,25 @@ LTP_HD int time_scaling_attempt1(const JointLimits& L, double Ts, const Prologue
   return time_scaling_attempt1(L, Ts, P, I, scaled_t, v_drive, mod, final_case, dv);
 }
 
+template <class DIV>
 LTP_HD int time_scaling_attempt2(const JointLimits& L, double Ts, const Prologue& P, const TsInput& I,
                                  double* scaled_t, double& v_drive, unsigned char& mod,
-                                 unsigned char& final_case) {
-  const double V = ts_candidate2(L, I);
+                                 unsigned char& final_case, DIV& dv) {
+  const double V = ts_candidate2(L, I, dv);
   v_drive = V;
   if (!isnan(V) && V > 0) {
-    const int st = ost_body_t<false>(L, Ts, P, I.q_goal, I.q_0, V, scaled_t, mod, final_case);
+    const int st = ost_body_dv<false, false>(L, Ts, P, I.q_goal, I.q_0, V, scaled_t, mod, final_case, dv);
     if (st == OST_DEFER) return 0;
     if (st == OST_OK && I.tr - scaled_t[6] < kTol && I.tr - scaled_t[6] > -kTol / 10) return 2;
   }
   return 0;
+}
+
+LTP_HD int time_scaling_attempt2(const JointLimits& L, double Ts, const Prologue& P, const TsInput& I,
+                                 double* scaled_t, double& v_drive, unsigned char& mod,
+                                 unsigned char& final_case) {
+  DivChecked dv;
+  return time_scaling_attempt2(L, Ts, P, I, scaled_t, v_drive, mod, final_case, dv);
 }
 
 LTP_HD int time_scaling_closed_form(const JointLimits& L, double Ts, const Prologue& P, const TsInput& I,

@@ -105,10 +105,45 @@ int64_t shadow_deferred_vs_checked(void* h, int64_t n, const int* joint, const d
     } else if (rd != rc || m2d != m2c || fcd != fcc || !same_bits(&vd, &vc, 8) || !same_bits(ad, ac, 56)) {
       ++miss;
     }
+    // attempt 2 the way its kernel runs it: prologue and nested solve under one flag
+    DivDeferred dv3;
+    const Prologue p3 = ost_prologue(L, s->ts, q_goal[i], q_0[i], v_0[i], a_0[i], dv3);
+    const TsInput I3 = make_ts_input(q_goal[i], q_0[i], v_0[i], a_0[i], p3.dir, t_req[i]);
+    double bd[7], bc[7];
+    zero7(bd);
+    zero7(bc);
+    double wd = L.v_max, wc = L.v_max;
+    unsigned char m3d = 0, m3c = 0, gcd = 255, gcc = 255;
+    const int qd = time_scaling_attempt2(L, s->ts, p3, I3, bd, wd, m3d, gcd, dv3);
+    if (dv3.bad) {
+      ++flg2;
+    } else {
+      const int qc = time_scaling_attempt2(L, s->ts, pc, I, bc, wc, m3c, gcc);
+      if (qd != qc || m3d != m3c || gcd != gcc || !same_bits(&wd, &wc, 8) || !same_bits(bd, bc, 56)) ++miss;
+    }
   }
   if (flagged) {
     flagged[0] = flg;
     flagged[1] = flg2;
+  }
+  return miss;
+}
+
+// ts_candidate2 through the prepared reciprocals (checked and deferred) against the expression
+// with the reference's divisions written out; returns the number of items whose bits differ
+int64_t shadow_candidate2_mismatches(void* h, int64_t n, const int* joint, const double* q_goal, const double* q_0,
+                                     const double* v_0, const double* a_0, const double* dir, const double* t_req) {
+  Shadow* s = static_cast<Shadow*>(h);
+  int64_t miss = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const JointLimits& L = s->lim[joint ? joint[i] : 0];
+    const TsInput I = make_ts_input(q_goal[i], q_0[i], v_0[i], a_0[i], dir[i], t_req[i]);
+    const double a = ts_candidate2_plain(L, I), b = ts_candidate2(L, I);
+    DivDeferred dv;
+    const double c = ts_candidate2(L, I, dv);
+    const bool nan_ok = a != a && b != b;
+    if (!same_bits(&a, &b, 8) && !nan_ok) ++miss;
+    else if (!dv.bad && !same_bits(&a, &c, 8) && !(a != a && c != c)) ++miss;
   }
   return miss;
 }

@@ -227,7 +227,8 @@ def test_item_mode_hand_overs_equal_the_every_branch_sequence(lim, n, seed, kind
 
 def test_division_by_prepared_reciprocal_has_the_bits_of_the_plain_division():
     """div_by (ltp_math.cuh: quotient estimate, exact remainder, one correction) against x / d for
-    every divisor the limit sets of the workloads produce (a_max, j_max, v_max, 3, 12): random
+    every divisor the limit sets of the workloads produce (a_max, j_max, v_max, 3, 12, and J^2, J^3,
+    6 J^3, A J of the second cruise-speed candidate): random
     numerators over the whole exponent range plus the special values, bit for bit."""
     import ctypes
     lib = ctypes.CDLL(SHADOW)
@@ -243,9 +244,13 @@ def test_division_by_prepared_reciprocal_has_the_bits_of_the_plain_division():
     x[-12:] = [0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, -5e-324, 2.2250738585072014e-308,
                1.7976931348623157e308, -1.7976931348623157e308, 1e-300, -1e300]
     x = np.ascontiguousarray(x)
+    from fractions import Fraction
     divisors = {3.0, 12.0}
     for lim in (W.FRANKA7, W.FRANKA12, W.REF_RANDOM6, W.random_limits(6, 11), W.random_limits(32, 12)):
         divisors.update(lim.v_max, lim.a_max, lim.j_max)
+        for a, j in zip(lim.a_max, lim.j_max):  # the divisors of the second cruise-speed candidate
+            j3 = float(Fraction(j) ** 3)         # pow3() is the correctly rounded cube
+            divisors.update([j * j, j3, 6 * j3, a * j])
     bad = ctypes.c_double(0.0)
     for d in sorted(divisors):
         miss = f(float(d), n, x.ctypes.data, ctypes.byref(bad))
@@ -293,3 +298,24 @@ def test_deferred_range_test_of_the_divisions_changes_no_bit(kind):
         # (attempt 1 is flagged whenever its candidate is a NaN, which the made-up end times here
         # cause far more often than the real ones)
         assert flagged[0] < 0.001 * m, list(flagged)
+
+
+@pytest.mark.parametrize("lim", [W.FRANKA7, W.REF_RANDOM6, W.random_limits(8, 5)], ids=lambda l: l.name)
+def test_second_candidate_through_reciprocals_has_the_bits_of_the_written_out_divisions(lim):
+    import ctypes
+    lib = ctypes.CDLL(SHADOW)
+    f = lib.shadow_candidate2_mismatches
+    f.restype = ctypes.c_int64
+    f.argtypes = [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 7
+    rng = np.random.default_rng(5)
+    qg, q0, v0, a0 = [np.ascontiguousarray(x.reshape(-1)) for x in W.random_states(lim, 40_000, 99)]
+    m = qg.size
+    joint = np.ascontiguousarray(np.tile(np.arange(lim.dof, dtype=np.int32), m // lim.dof))
+    v0[: m // 8] = 0.0
+    a0[m // 16: m // 4] = 0.0
+    a0[m // 4: m // 3] = (np.asarray(lim.a_max)[joint] * rng.choice([-1.0, 1.0], m))[m // 4: m // 3]
+    direction = np.ascontiguousarray(rng.choice([-1.0, 1.0], m))
+    t_req = np.ascontiguousarray(rng.uniform(0.01, 5.0, m))
+    sh = Shadow(lim.dof, lim.t_sample, *lim.arrays())
+    assert f(sh.h, m, joint.ctypes.data, qg.ctypes.data, q0.ctypes.data, v0.ctypes.data, a0.ctypes.data,
+             direction.ctypes.data, t_req.ctypes.data) == 0

@@ -77,7 +77,7 @@ def main():
     rows = list(csv.reader(src.splitlines()))
     # one section per captured launch: "Kernel Name",<demangled> / header / instructions
     m = re.match(r"(\w+?)ILi(\d+)$", kern)
-    want = f"{m.group(1)}<(int){m.group(2)}>" if m else kern
+    want = f"{m.group(1)}<(int){m.group(2)}" if m else kern  # (further template arguments may follow)
     starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
     sect = next(i for i in starts if want in rows[i][1])
     end = next((i for i in starts if i > sect), len(rows))
