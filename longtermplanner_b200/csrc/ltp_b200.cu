@@ -28,6 +28,7 @@ using namespace ltp;
 struct PlannerParams {
   int dof;
   double ts;
+  double r_ts;  // RN(1 / ts), for the sample counts (div_by)
   JointLimits lim[LTP_MAX_DOF];
 };
 
@@ -211,12 +212,20 @@ __device__ __forceinline__ void store_joint(const DeviceSolution& S, int dof, in
   store_joint_opt(S, dof, jt, n, p, t_opt, dir, opt_case);
 }
 
-// cc:718 for one joint, -1 when a switching time is not finite / not representable
-__device__ __forceinline__ int joint_samples(const double* t_sc, double Ts) {
-  bool fin = true;
-#pragma unroll
-  for (int k = 0; k < 7; ++k) fin &= (bool)isfinite(t_sc[k]);
-  return (fin && t_sc[6] / Ts <= 2.0e9) ? samples_for(t_sc[6], Ts) : -1;
+// cc:718 for one joint, -1 when a switching time is not finite / not representable. The seven
+// times are a running sum (cumsum7) or all zero wherever this is called, so a time that is not
+// finite leaves the last one not finite, and the last one is the only one looked at. t6 / Ts goes
+// through the reciprocal of the sample time (same bits, see DivDeferred: zero -- a joint that does
+// not move -- included); a quotient outside the window takes the plain division.
+__device__ __forceinline__ int joint_samples(const double* t_sc, double Ts, double r_ts) {
+  const double t6 = t_sc[6];
+  DivDeferred dv;
+  double q = dv.by(t6, Ts, r_ts);
+  if (dv.bad) q = t6 / Ts;
+  if (!(isfinite(t6) && q <= 2.0e9)) return -1;
+  const double x = ceil(q);  // samples_for(), with the quotient at hand
+  if (!(x >= -1.0e9 && x <= 2.0e9)) return 0;
+  return (int)x + 1;
 }
 
 // The last of a problem's dof threads to get here reduces the per-joint lengths and writes
@@ -282,14 +291,15 @@ __device__ __forceinline__ double pack_tail_flags(unsigned mod, unsigned opt_cas
 }
 
 // Register budget: the kernel is bound by FP64 dependency latency, so it is compiled for
-// ~28 resident warps per SM (measured on B200, 2^20 Franka problems: 7 joints 1.12 ms at
-// 128 registers / 14 warps, 1.04 ms at 80 / 21, 0.95 ms at 72 / 28; 12 joints 2.10 ms at
-// 128 / 12, 1.51 ms at 80 / 24, 1.52 ms at 56 / 36, 1.88 ms at 40 / 48).
+// ~28 resident warps per SM. Measured on B200, 2^20 Franka problems, round 1: 7 joints 1.12 ms at
+// 128 registers / 14 warps, 1.04 ms at 80 / 21, 0.95 ms at 72 / 28. Round 2, after the instruction
+// diet: 7 joints 0.593 ms at 80 / 21, 0.537 ms at 72 / 28, 0.558 ms at 56 / 35; 12 joints 0.985 ms
+// at 80 / 24, 0.933 ms at 56 / 36 -- hence three CTAs per SM for 12 joints.
 #ifndef LTP_FAST_WARPS
 #define LTP_FAST_WARPS 28
 #endif
 constexpr int fast_min_blocks(int maxw) {
-  return (LTP_FAST_WARPS + maxw / 2) / maxw > 0 ? (LTP_FAST_WARPS + maxw / 2) / maxw : 1;
+  return maxw == 12 ? 3 : ((LTP_FAST_WARPS + maxw / 2) / maxw > 0 ? (LTP_FAST_WARPS + maxw / 2) / maxw : 1);
 }
 // The closed-form kernel runs stage 1 and attempt 1 with the range test of the prepared-reciprocal
 // divisions deferred (DivDeferred, ltp_math.cuh): one look at a flag per stage instead of a
@@ -526,7 +536,7 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
   if (!valid) return;
   store_joint_opt(S, dof, jt, n, p, t_opt, pro.dir, opt_case);
   // a queued joint contributes length 0 here; its length arrives by atomicMax later
-  const int my_len = (reached && !defer1 && !my_defer && !need2) ? joint_samples(t_sc, Ts) : 0;
+  const int my_len = (reached && !defer1 && !my_defer && !need2) ? joint_samples(t_sc, Ts, P.r_ts) : 0;
   // legacy mode: a joint that is not settled here sends its whole problem to the every-branch
   // kernel; item mode: only a non-finite time does (the joint itself is listed as an item)
   const bool whole = items ? (my_len < 0) : (my_defer || defer1);
@@ -612,7 +622,7 @@ ltp_solve_attempt2_kernel(const __grid_constant__ PlannerParams P, int64_t n, De
     // an accepted solve with no positive time falls back to the time-optimal times (cc:50-55),
     // which are not at hand here: that (degenerate) problem goes to the generic kernel too
     const bool open = (c == 0 || m <= 0.0);
-    const int len = open ? -1 : joint_samples(t, Ts);
+    const int len = open ? -1 : joint_samples(t, Ts, P.r_ts);
     if (items && open) {
       push_search_item(X, p, jt, t_req);  // candidates 3..8 (or the fallback) for this joint alone
     } else if (len < 0) {
@@ -742,7 +752,7 @@ ltp_solve_pending_kernel(const __grid_constant__ PlannerParams P, int64_t n, con
     }
     if (valid) {
       if (open) push_search_item(X, p, jt, t_req);
-      const int my_len = (reached && !open) ? joint_samples(t_sc, Ts) : 0;
+      const int my_len = (reached && !open) ? joint_samples(t_sc, Ts, P.r_ts) : 0;
       if (finish_problem(sh, S, dof, lane, jt, p, my_len, my_len < 0, reached, slowest)) {
         const int slot = atomicAdd(X.counters + kCntWork, 1);
         X.work_list[slot] = (int)p;
@@ -793,7 +803,7 @@ ltp_solve_search_kernel(const __grid_constant__ PlannerParams P, int64_t n, cons
 #pragma unroll
       for (int k = 0; k < 7; ++k) t_sc[k] = t_opt[k];
     }
-    const int len = joint_samples(t_sc, Ts);
+    const int len = joint_samples(t_sc, Ts, P.r_ts);
     if (len < 0) {
       push_whole_problem(S, X, p);
     } else {
@@ -874,7 +884,7 @@ ltp_solve_generic_kernel(const __grid_constant__ PlannerParams P, int64_t n, con
         for (int k = 0; k < 7; ++k) t_sc[k] = t_opt[k];
       }
     }
-    const int my_len = reached ? joint_samples(t_sc, Ts) : 0;
+    const int my_len = reached ? joint_samples(t_sc, Ts, P.r_ts) : 0;
     if (valid) {
       finish_problem(sh, S, dof, lane, jt, p, my_len, false, reached, slowest);
       store_joint(S, dof, jt, n, p, t_sc, t_opt, pro.dir, v_drive, mod, opt_case, ts_case, final_case);
@@ -1740,6 +1750,7 @@ int ltp_create(ltp_planner** out, int device, int dof, double t_sample, const do
   p->device = device;
   p->params.dof = dof;
   p->params.ts = t_sample;
+  p->params.r_ts = 1.0 / t_sample;
   p->launches = 0;
   p->d_scratch = nullptr;
   p->d_scratch_bytes = 0;
@@ -1787,6 +1798,7 @@ int ltp_set_limits(ltp_planner* p, const double* q_min, const double* q_max, con
 int ltp_set_sample_time(ltp_planner* p, double t_sample) {
   if (!p) return LTP_ERR_ARG;
   p->params.ts = t_sample;
+  p->params.r_ts = 1.0 / t_sample;
   return LTP_OK;
 }
 

@@ -245,7 +245,7 @@ def test_division_by_prepared_reciprocal_has_the_bits_of_the_plain_division():
                1.7976931348623157e308, -1.7976931348623157e308, 1e-300, -1e300]
     x = np.ascontiguousarray(x)
     from fractions import Fraction
-    divisors = {3.0, 12.0}
+    divisors = {3.0, 12.0, 0.001, 0.004, 0.01}  # (the last three: sample times)
     for lim in (W.FRANKA7, W.FRANKA12, W.REF_RANDOM6, W.random_limits(6, 11), W.random_limits(32, 12)):
         divisors.update(lim.v_max, lim.a_max, lim.j_max)
         for a, j in zip(lim.a_max, lim.j_max):  # the divisors of the second cruise-speed candidate
