@@ -294,12 +294,13 @@ __device__ __forceinline__ double pack_tail_flags(unsigned mod, unsigned opt_cas
 // ~28 resident warps per SM. Measured on B200, 2^20 Franka problems, round 1: 7 joints 1.12 ms at
 // 128 registers / 14 warps, 1.04 ms at 80 / 21, 0.95 ms at 72 / 28. Round 2, after the instruction
 // diet: 7 joints 0.593 ms at 80 / 21, 0.537 ms at 72 / 28, 0.558 ms at 56 / 35; 12 joints 0.985 ms
-// at 80 / 24, 0.933 ms at 56 / 36 -- hence three CTAs per SM for 12 joints.
+// at 80 / 24, 0.933 ms at 56 / 36 -- hence three CTAs per SM for 12 joints; 6 joints 0.476 ms at
+// 64 / 30, 0.447 ms at 80 / 24 -- hence four CTAs for 6.
 #ifndef LTP_FAST_WARPS
 #define LTP_FAST_WARPS 28
 #endif
 constexpr int fast_min_blocks(int maxw) {
-  return maxw == 12 ? 3 : ((LTP_FAST_WARPS + maxw / 2) / maxw > 0 ? (LTP_FAST_WARPS + maxw / 2) / maxw : 1);
+  return maxw == 12 ? 3 : maxw == 6 ? 4 : ((LTP_FAST_WARPS + maxw / 2) / maxw > 0 ? (LTP_FAST_WARPS + maxw / 2) / maxw : 1);
 }
 // The closed-form kernel runs stage 1 and attempt 1 with the range test of the prepared-reciprocal
 // divisions deferred (DivDeferred, ltp_math.cuh): one look at a flag per stage instead of a

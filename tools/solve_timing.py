@@ -1,6 +1,6 @@
 """Kernel-level timing of the solve (configs[1], 2^20 Franka problems) and of the time-major
 sampler (configs[2]) through the library's own event hooks. Used to compare builds:
-  LTP_B200_LIB=/path/to/variant.so python tools/solve_timing.py [7|12] [rest]"""
+  LTP_B200_LIB=/path/to/variant.so python tools/solve_timing.py [6|7|12] [rest]"""
 import os
 import sys
 
@@ -10,6 +10,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from longtermplanner_b200 import LongTermPlanner, workloads as W  # noqa: E402
 
 lim = W.FRANKA7 if len(sys.argv) < 2 or sys.argv[1] != "12" else W.FRANKA12
+if len(sys.argv) > 1 and sys.argv[1] == "6":  # a six-joint arm: the first six joints of the 7-DoF limits
+    lim = W.Limits("franka6", 0.001, *[x[:6] for x in (W.FRANKA7.q_min, W.FRANKA7.q_max, W.FRANKA7.v_max,
+                                                       W.FRANKA7.a_max, W.FRANKA7.j_max)])
 n = 1 << 20
 ltp = LongTermPlanner(lim.dof, lim.t_sample, *lim.arrays(), device=0)
 ins = [torch.from_numpy(W.to_joint_major(x)).cuda() for x in W.random_states(lim, n, W.SEEDS[2])]
