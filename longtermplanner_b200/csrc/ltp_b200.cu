@@ -82,7 +82,7 @@ struct SolveShared {
   double* t6;            // [dof][32]
   int* len;              // [dof][32]
   int* arrived;          // [32]
-  int* warp_items;       // [dof + 2]   queued joints per warp, then their total and queue base
+  int* warp_items;       // [dof + 2]   (spare)
   int* tail_items;       // [dof + 2]   the same for the tail items
   unsigned char* flag;   // [dof][32]  bit0 fail, bit1 defer
 };
@@ -102,10 +102,11 @@ __device__ __forceinline__ SolveShared carve_shared(unsigned char* raw, int dof)
   return s;
 }
 
-// Device scratch of one solve. counters: [0] whole-problem work list, [1] attempt-2 queue,
-// [2] tail items, [3] tail-pending problems, [4] search items. Lists:
+// Device scratch of one solve. counters: [0] whole-problem work list, [2] tail items,
+// [3] tail-pending problems, [4] search items, [8 + joint] that joint's part of the attempt-2
+// queue. Lists:
 //   work_list   problems the every-branch kernel recomputes as a whole (n ints)
-//   queue       joints whose first cruise-speed candidate was rejected ((dof - 1) * n entries)
+//   queue       joints whose first cruise-speed candidate was rejected (dof * n entries)
 //   tail_items  (problem, joint) pairs whose time-optimal solve needs the quartic tail (dof * n)
 //   pending     problems with at least one tail item: their stages 2-3 wait for it (n ints)
 //   search_*    (problem, joint) pairs whose search needs a polynomial root, with the required
@@ -119,24 +120,29 @@ struct SolveScratch {
   int2* search_items;
   double* search_t_req;
 };
-enum { kCntWork = 0, kCntQueue = 1, kCntTail = 2, kCntPending = 3, kCntSearch = 4, kCounters = 8 };
+enum { kCntWork = 0, kCntTail = 2, kCntPending = 3, kCntSearch = 4, kCounters = 8 };
+// The attempt-2 queue is one sub-queue per joint (entries [joint * n, joint * n + count[joint]),
+// counts behind the counters above): a warp of the closed-form kernel holds 32 problems of ONE
+// joint, so it reserves its slots with one atomic of its own and needs no word from the other
+// warps of its CTA -- the CTA-wide slot assignment it replaces cost two barriers after attempt 1.
+constexpr int kCounterInts = kCounters + LTP_MAX_DOF;
 
 inline size_t round16(size_t x) { return (x + 15) / 16 * 16; }
 
 inline size_t solve_scratch_bytes(int dof, int64_t n) {
-  const size_t cap = (size_t)(dof > 1 ? dof - 1 : 0) * (size_t)n;
+  const size_t cap = (size_t)dof * (size_t)n;
   const size_t dn = (size_t)dof * (size_t)n;
-  return 32 + 2 * round16((size_t)n * sizeof(int)) + cap * (5 * sizeof(double) + sizeof(int2)) +
+  return round16(kCounterInts * sizeof(int)) + 2 * round16((size_t)n * sizeof(int)) + cap * (5 * sizeof(double) + sizeof(int2)) +
          dn * (2 * sizeof(int2) + sizeof(double));
 }
 
 inline SolveScratch carve_scratch(void* base, int dof, int64_t n) {
   SolveScratch s;
   unsigned char* b = static_cast<unsigned char*>(base);
-  const size_t cap = (size_t)(dof > 1 ? dof - 1 : 0) * (size_t)n;
+  const size_t cap = (size_t)dof * (size_t)n;
   const size_t dn = (size_t)dof * (size_t)n;
   s.counters = reinterpret_cast<int*>(b);
-  b += 32;
+  b += round16(kCounterInts * sizeof(int));
   s.work_list = reinterpret_cast<int*>(b);
   b += round16((size_t)n * sizeof(int));
   s.pending = reinterpret_cast<int*>(b);
@@ -510,22 +516,15 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
       }
     }
   }
-  // queue slot = base of this CTA (one atomic per CTA) + joints queued by the warps before
-  // mine + those of the lanes before mine
+  // queue slot = base of this warp in its joint's sub-queue (one atomic per warp) + the queued
+  // lanes before mine
   const unsigned need_mask = __ballot_sync(0xffffffffu, need2);
-  if (lane == 0) sh.warp_items[jt] = __popc(need_mask);
-  __syncthreads();
-  int before = 0, total = 0;
-  for (int w = 0; w < dof; ++w) {
-    const int c = sh.warp_items[w];
-    before += (w < jt) ? c : 0;
-    total += c;
-  }
-  if (total > 0) {  // uniform over the CTA
-    if (jt == 0 && lane == 0) sh.warp_items[dof + 1] = atomicAdd(X.counters + kCntQueue, total);
-    __syncthreads();
+  if (need_mask != 0) {  // uniform over the warp
+    int base = 0;
+    if (lane == 0) base = atomicAdd(X.counters + kCounters + jt, __popc(need_mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
     if (need2) {
-      const int e = sh.warp_items[dof + 1] + before + __popc(need_mask & ((1u << lane) - 1u));
+      const int64_t e = (int64_t)jt * n + base + __popc(need_mask & ((1u << lane) - 1u));
       X.queue.t_req[e] = t_req;
       X.queue.q_goal[e] = qg;
       X.queue.q_0[e] = q0;
@@ -566,24 +565,36 @@ ltp_solve_attempt2_kernel(const __grid_constant__ PlannerParams P, int64_t n, De
                           int items) {
   const int dof = P.dof;
   const double Ts = P.ts;
-  const int count = X.counters[kCntQueue];
   const int step = gridDim.x * blockDim.x;
   int e = blockIdx.x * blockDim.x + threadIdx.x;
+  // the sub-queues end to end: flat entry f lives at joint * n + (f - entries of the joints before)
+  __shared__ int sub_count[LTP_MAX_DOF];
+  if ((int)threadIdx.x < dof) sub_count[threadIdx.x] = X.counters[kCounters + threadIdx.x];
+  __syncthreads();
+  int count = 0;
+  for (int j = 0; j < dof; ++j) count += sub_count[j];
+  auto slot_of = [&](int f) -> int64_t {
+    int j = 0;
+    while (j < dof - 1 && f >= sub_count[j]) f -= sub_count[j++];
+    return (int64_t)j * n + f;
+  };
   if (e >= count) return;
   // software pipeline: the next entry's six loads are in flight while this one is evaluated
   // (the kernel was waiting on memory for half of its cycles, four warps per scheduler)
-  int2 where = X.queue.where[e];
-  double t_req = X.queue.t_req[e], qg = X.queue.q_goal[e], q0 = X.queue.q_0[e], v0 = X.queue.v_0[e],
-         a0 = X.queue.a_0[e];
+  int64_t at = slot_of(e);
+  int2 where = X.queue.where[at];
+  double t_req = X.queue.t_req[at], qg = X.queue.q_goal[at], q0 = X.queue.q_0[at], v0 = X.queue.v_0[at],
+         a0 = X.queue.a_0[at];
   while (true) {
     const int en = e + step;
     const bool more = en < count;
     int2 where_n = where;
     double t_req_n = 0, qg_n = 0, q0_n = 0, v0_n = 0, a0_n = 0;
     if (more) {
-      where_n = X.queue.where[en];
-      t_req_n = X.queue.t_req[en]; qg_n = X.queue.q_goal[en]; q0_n = X.queue.q_0[en];
-      v0_n = X.queue.v_0[en]; a0_n = X.queue.a_0[en];
+      at = slot_of(en);
+      where_n = X.queue.where[at];
+      t_req_n = X.queue.t_req[at]; qg_n = X.queue.q_goal[at]; q0_n = X.queue.q_0[at];
+      v0_n = X.queue.v_0[at]; a0_n = X.queue.a_0[at];
     }
     const int64_t p = where.x;
     const int jt = where.y;
@@ -1952,7 +1963,7 @@ static int solve_launch(ltp_planner* p, int64_t n, const double* q_goal, const d
     LTP_DISPATCH_W(ltp_solve_generic_kernel, tiles, p->params, n, q_goal, q_0, v_0, a_0, ds,
                    (const int*)nullptr, (const int*)nullptr);
   } else {
-    LTP_CUDA(cudaMemsetAsync(X.counters, 0, kCounters * sizeof(int), st));
+    LTP_CUDA(cudaMemsetAsync(X.counters, 0, kCounterInts * sizeof(int), st));
     // large batches hand unsettled joints on one by one (item mode); a small batch is a handful of
     // CTAs whichever way it is run and keeps the three-launch sequence
     const int items = n >= kItemModeMin ? 1 : 0;
