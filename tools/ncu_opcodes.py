@@ -11,6 +11,21 @@ top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", f"regex:{kern}", "--launch-count", "1"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
+# one section per captured launch ("Kernel Name" row first): keep the longest launch only
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+if len(starts) > 2:
+    a, b = max(zip(starts, starts[1:]), key=lambda ab: ab[1] - ab[0])
+    sections = [(a, b)]
+    def weight(ab):
+        tot = 0
+        for r in rows[ab[0]:ab[1]]:
+            for c in r[2:6]:
+                if c.isdigit():
+                    tot += int(c)
+                    break
+        return tot
+    a, b = max(zip(starts, starts[1:]), key=weight)
+    rows = rows[a:b]
 hdr = next(r for r in rows if "Source" in r and "Instructions Executed" in r)
 iS, iI, iT, iSm = (hdr.index(k) for k in ("Source", "Instructions Executed", "Thread Instructions Executed", "# Samples"))
 ops, thr, smp = collections.Counter(), collections.Counter(), collections.Counter()
