@@ -46,6 +46,50 @@ def test_solve_matches_oracle(lim, n, seed):
         assert count_bad(got, ref[k]) == 0, (k, bitdiff(got, ref[k]))
 
 
+@pytest.mark.parametrize("n", [40_000, 3_000])  # item mode and the small-batch sequence
+@pytest.mark.parametrize("kind", ["tiny", "signed_zero_rest", "on_the_limits"])
+def test_states_that_leave_the_division_window_match_oracle(kind, n):
+    """The closed-form and attempt-2 kernels test the range of their prepared-reciprocal divisions
+    once per stage and repeat a flagged thread out of line (DivDeferred, csrc/ltp_b200.cu). States
+    that set the flag in a large share of the threads -- magnitudes down to 1e-320 -- and states
+    full of zero numerators of either sign (which must NOT need the second pass to be right),
+    all bit-compared with the oracle like any other batch."""
+    lim = W.FRANKA7
+    rng = np.random.default_rng(20261018)
+    qg, q0, v0, a0 = W.random_states(lim, n, 977)
+    if kind == "tiny":
+        v0 = v0 * 10.0 ** rng.integers(-320, -80, v0.shape)
+        a0 = a0 * 10.0 ** rng.integers(-320, -80, a0.shape)
+    elif kind == "signed_zero_rest":
+        v0 = np.where(rng.random(v0.shape) < 0.5, 0.0, -0.0)
+        a0 = np.where(rng.random(a0.shape) < 0.5, 0.0, -0.0)
+    else:
+        a_max, v_max = np.asarray(lim.a_max), np.asarray(lim.v_max)
+        a0 = np.where(rng.random(a0.shape) < 0.5, a_max, -a_max) * (rng.random(a0.shape) < 0.6)
+        v0 = np.where(rng.random(v0.shape) < 0.2, v_max * rng.choice([-1.0, 1.0], v0.shape), v0 * 0.2)
+    v0, a0 = np.ascontiguousarray(v0), np.ascontiguousarray(a0)
+    ltp = _planner(lim)
+    ins = [_dev(jm(x)) for x in (qg, q0, v0, a0)]
+    sol = ltp.solve(*ins, with_opt=True, with_cases=True)
+    torch.cuda.synchronize()
+    ref = OraclePort.from_limits(lim).solve(qg, q0, v0, a0, threads=8)
+    for k in ("reached", "traj_len"):
+        assert np.array_equal(getattr(sol, k).cpu().numpy(), ref[k]), k
+    # (a start state that checkInputs rejects -- cc:14-15, a fifth of the states on the limits --
+    # has no per-joint results in the reference; the rest is compared field by field)
+    ok = ref["reached"].astype(bool)
+    assert ok.sum() > 0.5 * n
+    assert np.array_equal(sol.slowest.cpu().numpy()[ok], ref["slowest"][ok])
+    for k in ("mod", "opt_case", "ts_case", "final_case", "dir"):
+        assert np.array_equal(pm(getattr(sol, k).cpu().numpy())[ok], ref[k][ok]), k
+    for k in ("t_opt", "t_scaled", "v_drive"):
+        got, want = pm(getattr(sol, k).cpu().numpy())[ok], np.asarray(ref[k])[ok]
+        assert count_bad(got, want) == 0, (k, bitdiff(got, want))
+        # zeros carry the oracle's sign (a zero numerator divided through the reciprocal keeps it)
+        z = want == 0.0
+        assert np.array_equal(np.signbit(got[z]), np.signbit(want[z])), k
+
+
 @pytest.mark.parametrize("lim,n,seed", [(W.FRANKA7, 50_000, 301), (W.REF_RANDOM6, 30_000, 302), (W.FRANKA12, 10_000, 303)])
 def test_controller_like_states_match_oracle(lim, n, seed):
     """what a replanning controller feeds the planner (workloads.edge_states): joints holding
