@@ -140,8 +140,8 @@ typedef struct {
  * stream, or separated by events); for concurrent streams or host threads create one planner
  * per stream -- a planner is a few hundred bytes plus its scratch. (The reference's
  * planTrajectory is re-entrant on one object; the drop-in class is not, for the same reason.)
- * The solve scratch (about n * (4 + 48 * (dof - 1)) bytes: work list and the queue of the second
- * cruise-speed candidate) is allocated on the first call and whenever n grows,
+ * The solve scratch (about n * (8 + 72 * dof) bytes: work lists, the per-joint queues of the second
+ * cruise-speed candidate and the item lists) is allocated on the first call and whenever n grows,
  * which must not happen inside a CUDA-graph capture: call ltp_reserve first. */
 int ltp_reserve(ltp_planner* p, int64_t n); /* scratch for solves of up to n problems, now */
 int ltp_solve_batch(ltp_planner* p, int64_t n, const double* q_goal, const double* q_0,
