@@ -378,6 +378,9 @@ __device__ __noinline__ void attempt2_checked(const PlannerParams& P, int jt, do
 #ifndef LTP_FAST_EXACT
 #define LTP_FAST_EXACT 1
 #endif
+#ifndef LTP_FAST_UNIFORM_JT
+#define LTP_FAST_UNIFORM_JT 0
+#endif
 // EXACT: the CTA has exactly MAXW warps (the arm sizes the kernel is specialised for), so the
 // shared-memory offsets are constants and the loops over the joints unroll
 template <int MAXW, bool EXACT = false>
@@ -390,7 +393,13 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
   const SolveShared sh = carve_shared(smem_raw, dof);
   int* const work_list = X.work_list;
   int* const work_count = X.counters + kCntWork;
+#if LTP_FAST_UNIFORM_JT
+  // a warp is one joint: the warp-wide reduction returns the joint index in a uniform register,
+  // so the limits are addressed through the uniform datapath
+  const int lane = threadIdx.x, jt = (int)__reduce_max_sync(0xffffffffu, (unsigned)threadIdx.y);
+#else
   const int lane = threadIdx.x, jt = threadIdx.y;
+#endif
   const int64_t p = (int64_t)blockIdx.x * kTile + lane;
   const bool valid = p < n;
   const JointLimits L = P.lim[jt];

@@ -52,6 +52,10 @@ struct JointLimits {
   double r_j2, r_j3, r_6j3, r_aj;
 };
 
+#ifndef LTP_OST_MERGE
+#define LTP_OST_MERGE 1
+#endif
+
 constexpr double kEps = 4e-3;     // cc:96
 constexpr double kTol = 0.1;      // cc:370
 constexpr double kDblMin = 2.2250738585072014e-308;
@@ -679,6 +683,56 @@ LTP_HD int ost_body_dv(const JointLimits& L, double Ts, const Prologue& P, doubl
     return OST_OK;
   }
   const double v_0 = P.v0m, a_0 = P.a0m;
+#if LTP_OST_MERGE
+  // cc:119-143 and cc:168-190 with the two jerk profiles on ONE instruction stream. The modified
+  // profile brakes from v_0 - V (optBraking, cc:650-701) and the normal one accelerates to V, and
+  // the reference writes both with the same expressions: T0 = (A - a)/J, T2 = A/J,
+  // T1 = (x - T0 a/2)/A - (T0 + T2)/2 and the same displacement polynomial in (v, a, T0, T1, T2),
+  // on (v, a, x) = (+-(v_0 - V), +-a_0, -v) there and (v_0, a_0, V - v_0) here. Selecting the
+  // operands first lets a warp that holds both kinds of joints (nearly every warp: a fifth of the
+  // searching joints is on the modified profile) evaluate them once instead of one after the
+  // other. Same operations on the same operands per lane, so the same bits; only the fix-up for
+  // a missing phase 2 differs between the two (different expressions in the reference) and
+  // stays a branch.
+  const bool m = v_0 + dv.by(0.5 * a_0 * fabs(a_0), J, L.r_j) > V;  // cc:119
+  double ve = v_0, ae = a_0, x = V - v_0, dirb = 1.0;
+  if (m) {
+    mod = 1;
+    flags |= F_MOD;
+    ve = v_0 - V;
+    // cc:658-667 as in brake_profile
+    const bool same_sign = ve * ae > 0;
+    const bool fast_enough = fabs(ve) > dv.by(1.0 / 2.0 * sq(ae), J, L.r_j);
+    dirb = neg_sgn((same_sign | fast_enough) ? ve : ae);
+    if (dirb < 0) {
+      ae = -ae;
+      ve = -ve;
+    }
+    x = -ve;
+  }
+  T[0] = dv.by(A - ae, J, L.r_j);
+  T[2] = L.a_over_j;
+  T[1] = dv.by(x - 1.0 / 2.0 * T[0] * ae, A, L.r_a) - 1.0 / 2.0 * (T[0] + T[2]);
+  if (m) {
+    if (T[1] < -Ts) {  // cc:682-687
+      T[0] = -ae / J + sqrt(sq(ae) / (2 * sq(J)) - ve / J);
+      T[2] = T[0] + ae / J;
+      T[1] = 0;
+    }
+  } else if (T[1] < -eps) {  // cc:129-143
+    double rad = J * (V - v_0) + 0.5 * sq(a_0);
+    if (rad > 0) {
+      T[2] = dv.by(sqrt(rad), J, L.r_j);
+      T[0] = T[2] - dv.by(a_0, J, L.r_j);
+      T[1] = 0;
+      flags |= F_NOP2;
+    } else {
+      zero7(t);
+      kase = CASE_DEGENERATE | flags;
+      return OST_OK;
+    }
+  }
+#else
   double q_brake = 0.0;
   if (v_0 + dv.by(0.5 * a_0 * fabs(a_0), J, L.r_j) > V) {  // cc:119-122
     mod = 1;
@@ -703,6 +757,7 @@ LTP_HD int ost_body_dv(const JointLimits& L, double Ts, const Prologue& P, doubl
       }
     }
   }
+#endif
   // cc:147-165
   T[4] = L.a_over_j;
   T[6] = T[4];
@@ -722,6 +777,17 @@ LTP_HD int ost_body_dv(const JointLimits& L, double Ts, const Prologue& P, doubl
   }
   // cc:168-190
   double part1;
+#if LTP_OST_MERGE
+  {
+    const double T012 = T[0] + T[1] + T[2];
+    const double s = ve * T012 +
+                     ae * (1.0 / 2.0 * sq(T[0]) + T[0] * (T[1] + T[2]) + 1.0 / 2.0 * sq(T[2])) +
+                     J * (1.0 / 6.0 * pow3(T[0]) + 1.0 / 2.0 * sq(T[0]) * (T[1] + T[2]) -
+                          1.0 / 6.0 * pow3(T[2]) + 1.0 / 2.0 * T[0] * sq(T[2])) +
+                     A * (1.0 / 2.0 * sq(T[1]) + T[1] * T[2]);
+    part1 = m ? dirb * s + V * T012 : s;
+  }
+#else
   if (mod == 1) {
     part1 = q_brake + V * (T[0] + T[1] + T[2]);
   } else {
@@ -731,6 +797,7 @@ LTP_HD int ost_body_dv(const JointLimits& L, double Ts, const Prologue& P, doubl
                  1.0 / 6.0 * pow3(T[2]) + 1.0 / 2.0 * T[0] * sq(T[2])) +
             A * (1.0 / 2.0 * sq(T[1]) + T[1] * T[2]);
   }
+#endif
   double part2 = J * (1.0 / 6.0 * pow3(T[6]) + 1.0 / 2.0 * sq(T[6]) * (T[5] + T[4]) -
                       1.0 / 6.0 * pow3(T[4]) + 1.0 / 2.0 * T[6] * sq(T[4])) +
                  A * (1.0 / 2.0 * sq(T[5]) + T[5] * T[4]);
