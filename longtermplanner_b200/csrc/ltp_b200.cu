@@ -305,8 +305,14 @@ __device__ __forceinline__ double pack_tail_flags(unsigned mod, unsigned opt_cas
 #ifndef LTP_FAST_WARPS
 #define LTP_FAST_WARPS 28
 #endif
+#ifndef LTP_FAST_BLOCKS_12
+#define LTP_FAST_BLOCKS_12 3
+#endif
+#ifndef LTP_FAST_BLOCKS_6
+#define LTP_FAST_BLOCKS_6 4
+#endif
 constexpr int fast_min_blocks(int maxw) {
-  return maxw == 12 ? 3 : maxw == 6 ? 4 : ((LTP_FAST_WARPS + maxw / 2) / maxw > 0 ? (LTP_FAST_WARPS + maxw / 2) / maxw : 1);
+  return maxw == 12 ? LTP_FAST_BLOCKS_12 : maxw == 6 ? LTP_FAST_BLOCKS_6 : ((LTP_FAST_WARPS + maxw / 2) / maxw > 0 ? (LTP_FAST_WARPS + maxw / 2) / maxw : 1);
 }
 // The closed-form kernel runs stage 1 and attempt 1 with the range test of the prepared-reciprocal
 // divisions deferred (DivDeferred, ltp_math.cuh): one look at a flag per stage instead of a
