@@ -10,6 +10,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from longtermplanner_b200 import LongTermPlanner, workloads as W  # noqa: E402
 
 lim = W.FRANKA7 if len(sys.argv) < 2 or sys.argv[1] != "12" else W.FRANKA12
+if len(sys.argv) > 1 and sys.argv[1] == "ref6":  # the reference's test limits: a fifth of the problems needs polynomial roots
+    lim = W.REF_RANDOM6
 if len(sys.argv) > 1 and sys.argv[1] == "6":  # a six-joint arm: the first six joints of the 7-DoF limits
     lim = W.Limits("franka6", 0.001, *[x[:6] for x in (W.FRANKA7.q_min, W.FRANKA7.q_max, W.FRANKA7.v_max,
                                                        W.FRANKA7.a_max, W.FRANKA7.j_max)])
@@ -41,8 +43,12 @@ try:
     ms4, cnt4 = ltp.kernelTime("solve_queues")
 except Exception:
     ms4, cnt4 = 0.0, 0
+try:
+    ms5, cnt5 = ltp.kernelTime("solve_items")
+except Exception:
+    ms5, cnt5 = 0.0, 0
 print(f"{os.environ.get('LTP_B200_LIB', 'default')}: dof {lim.dof} step {step_ms:.4f} ms = {n / step_ms / 1e3:.1f} M plans/s; kernel slot0 {ms / 20:.4f} ms + slot4 {ms3 / 20:.4f} ms + slot5 {ms4 / 20:.4f} ms per solve; "
-      f"generic {ms2 / 20:.4f} ms; traj_len checksum {chk}", flush=True)
+      f"generic {ms2 / 20:.4f} ms; items {ms5 / 20:.4f} ms; traj_len checksum {chk}", flush=True)
 if lim.dof == 7:
     n2, H = 4096, 2001
     ins2 = [torch.from_numpy(W.to_joint_major(x)).cuda() for x in W.random_states(lim, n2, W.SEEDS[3])]
