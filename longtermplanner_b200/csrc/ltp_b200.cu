@@ -11,6 +11,7 @@
 // per-problem reductions (slowest joint, trajectory length, final limit check) go through
 // a few bytes of shared memory per problem.
 #include <cuda_runtime.h>
+#include <type_traits>
 
 #include <atomic>
 #include <cstdio>
@@ -25,11 +26,49 @@ namespace {
 
 using namespace ltp;
 
+// The per-joint limits travel in two arrays: the fields every kernel reads (136 bytes per joint,
+// the stride they had before the limit-only factors were added) and the factors only the
+// closed-form kernel for up to 8 joints reads (DivDeferredWide). One 256-byte record per joint --
+// a power-of-two stride -- cost the 12-joint kernel 27 % (0.83 -> 1.05 ms) even though it never
+// touches the second half: its joints' lines then meet in the same sets of the constant cache
+// (profiles/r02_ab_limit_constants.log, padded strides of 264 / 280 / 296 bytes: 0.94 / 0.85 / 0.85 ms).
+#define LTP_HOT_FIELDS(X)                                                                              \
+  X(q_min) X(q_max) X(v_max) X(a_max) X(j_max) X(r_a) X(r_j) X(a_over_j) X(r_v) X(r_j2) X(r_j3) X(r_6j3) \
+  X(r_aj) X(aoj3) X(aoj4) X(t5v) X(part2v)
+#define LTP_WIDE_FIELDS(X)                                                                             \
+  X(c_aj) X(c_a2h) X(c_36a2j2) X(c_72a3j) X(c_144a) X(c_72aj2) X(c_a3) X(c_36a4) X(c_36j2) X(rk_q) X(rk_m) \
+  X(rk_h) X(rk_3) X(rk_7) X(rk_8)
+#define LTP_DECL(f) double f;
+struct JointHot { LTP_HOT_FIELDS(LTP_DECL) };
+struct JointWide { LTP_WIDE_FIELDS(LTP_DECL) };
+#undef LTP_DECL
+static_assert(sizeof(JointHot) + sizeof(JointWide) == sizeof(JointLimits), "a field of JointLimits is in neither list");
+
 struct PlannerParams {
   int dof;
   double ts;
   double r_ts;  // RN(1 / ts), for the sample counts (div_by)
-  JointLimits lim[LTP_MAX_DOF];
+  JointHot hot[LTP_MAX_DOF];
+  JointWide wide[LTP_MAX_DOF];
+  // the joint's limits as the closed-form functions take them; a field is loaded where it is used
+  __host__ __device__ __forceinline__ JointLimits joint(int jt) const {
+    JointLimits L;
+#define LTP_GET_HOT(f) L.f = hot[jt].f;
+#define LTP_GET_WIDE(f) L.f = wide[jt].f;
+    LTP_HOT_FIELDS(LTP_GET_HOT)
+    LTP_WIDE_FIELDS(LTP_GET_WIDE)
+#undef LTP_GET_HOT
+#undef LTP_GET_WIDE
+    return L;
+  }
+  void set_joint(int jt, const JointLimits& L) {
+#define LTP_PUT_HOT(f) hot[jt].f = L.f;
+#define LTP_PUT_WIDE(f) wide[jt].f = L.f;
+    LTP_HOT_FIELDS(LTP_PUT_HOT)
+    LTP_WIDE_FIELDS(LTP_PUT_WIDE)
+#undef LTP_PUT_HOT
+#undef LTP_PUT_WIDE
+  }
 };
 
 struct DeviceSolution {  // ltp_solution, by value
@@ -336,7 +375,7 @@ struct Stage1Redo {
 };
 __device__ __noinline__ void stage1_checked(const PlannerParams& P, int jt, double qg, double q0, double v0,
                                             double a0, Stage1Redo* o) {
-  const JointLimits L = P.lim[jt];
+  const JointLimits L = P.joint(jt);
   o->in_ok = check_joint_input(L, q0, v0, a0);
   o->pro = ost_prologue(L, P.ts, qg, q0, v0, a0);
   zero7(o->t_opt);
@@ -353,7 +392,7 @@ struct Attempt1Redo {
 __device__ __noinline__ void attempt1_checked(const PlannerParams& P, int jt, double qg, double q0, double v0,
                                               double a0, double t_req, unsigned char mod, unsigned char final_case,
                                               Attempt1Redo* o) {
-  const JointLimits L = P.lim[jt];
+  const JointLimits L = P.joint(jt);
   const Prologue pro = ost_prologue(L, P.ts, qg, q0, v0, a0);
   const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
   zero7(o->t);
@@ -371,7 +410,7 @@ struct Attempt2Redo {
 };
 __device__ __noinline__ void attempt2_checked(const PlannerParams& P, int jt, double qg, double q0, double v0,
                                               double a0, double t_req, Attempt2Redo* o) {
-  const JointLimits L = P.lim[jt];
+  const JointLimits L = P.joint(jt);
   const Prologue pro = ost_prologue(L, P.ts, qg, q0, v0, a0);
   const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
   zero7(o->t);
@@ -408,7 +447,7 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
 #endif
   const int64_t p = (int64_t)blockIdx.x * kTile + lane;
   const bool valid = p < n;
-  const JointLimits L = P.lim[jt];
+  const JointLimits L = P.joint(jt);
   const double Ts = P.ts;
   const int64_t at = (int64_t)jt * n + p;
 
@@ -438,7 +477,10 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
   zero7(t_opt);
   unsigned char mod = 0, opt_case = 255;
 #if LTP_FAST_DEFER
-  DivDeferred dv;
+  // up to 8 joints: the whole JointLimits block of the CTA's joints stays in the constant cache,
+  // so the limit-only factors are read from it (DivDeferredWide, ltp_math.cuh)
+  using Dv = typename std::conditional<(MAXW <= 8), DivDeferredWide, DivDeferred>::type;
+  Dv dv;
   bool in_ok = check_joint_input(L, q0, v0, a0, dv);
   Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0, dv);
   int st1 = ost_body_dv<false, LTP_FAST_RV != 0>(L, Ts, pro, qg, q0, L.v_max, t_opt, mod, opt_case, dv);
@@ -518,7 +560,7 @@ ltp_solve_fast_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
       const TsInput I = make_ts_input(qg, q0, v0, a0, pro.dir, t_req);
 #if LTP_FAST_DEFER
       const unsigned char mod1 = mod;
-      DivDeferred dv2;
+      Dv dv2;
       int c = time_scaling_attempt1(L, Ts, pro, I, t_sc, v_drive, mod, final_case, dv2);
       if (dv2.bad) {
         Attempt1Redo r;
@@ -635,7 +677,7 @@ ltp_solve_attempt2_kernel(const __grid_constant__ PlannerParams P, int64_t n, De
     // (a problem that is already on its way to the generic kernel is not skipped: what is
     // stored here is overwritten there, and a look at traj_len first costs a second trip to
     // memory per entry)
-    const JointLimits L = P.lim[jt];
+    const JointLimits L = P.joint(jt);
     double t[7];
     zero7(t);
     double v_drive = L.v_max;
@@ -699,7 +741,7 @@ ltp_solve_tail_kernel(const __grid_constant__ PlannerParams P, int64_t n, const 
     const int2 w = X.tail_items[e];
     const int64_t p = w.x;
     const int jt = w.y;
-    const JointLimits L = P.lim[jt];
+    const JointLimits L = P.joint(jt);
     const int64_t at = (int64_t)jt * n + p;
     const double qg = q_goal[at], q0 = q_0[at];
     const Prologue pro = ost_prologue(L, P.ts, qg, q0, v_0[at], a_0[at]);
@@ -725,7 +767,7 @@ ltp_solve_pending_kernel(const __grid_constant__ PlannerParams P, int64_t n, con
   const int dof = P.dof;
   const SolveShared sh = carve_shared(smem_raw, dof);
   const int lane = threadIdx.x, jt = threadIdx.y;
-  const JointLimits L = P.lim[jt];
+  const JointLimits L = P.joint(jt);
   const double Ts = P.ts;
   const int64_t count = X.counters[kCntPending];
   for (int64_t tile = blockIdx.x; tile * kTile < count; tile += gridDim.x) {
@@ -824,7 +866,7 @@ ltp_solve_search_kernel(const __grid_constant__ PlannerParams P, int64_t n, cons
     const double t_req = X.search_t_req[e];
     const int64_t p = w.x;
     const int jt = w.y;
-    const JointLimits L = P.lim[jt];
+    const JointLimits L = P.joint(jt);
     const int64_t at = (int64_t)jt * n + p;
     const double qg = q_goal[at], q0 = q_0[at], v0 = v_0[at], a0 = a_0[at];
     const Prologue pro = ost_prologue(L, Ts, qg, q0, v0, a0);
@@ -871,7 +913,7 @@ ltp_solve_generic_kernel(const __grid_constant__ PlannerParams P, int64_t n, con
   const int dof = P.dof;
   const SolveShared sh = carve_shared(smem_raw, dof);
   const int lane = threadIdx.x, jt = threadIdx.y;
-  const JointLimits L = P.lim[jt];
+  const JointLimits L = P.joint(jt);
   const double Ts = P.ts;
   const int64_t count = work_list ? (int64_t)*work_count : n;
   for (int64_t tile = blockIdx.x; tile * kTile < count; tile += gridDim.x) {
@@ -950,7 +992,7 @@ __global__ void ltp_opt_braking_kernel(const __grid_constant__ PlannerParams P, 
   if (p >= n) return;
   const int jt = joint_fixed >= 0 ? joint_fixed : blockIdx.y;
   const int row = joint_fixed >= 0 ? 0 : jt, rows = joint_fixed >= 0 ? 1 : P.dof;
-  const JointLimits L = P.lim[jt];
+  const JointLimits L = P.joint(jt);
   const int64_t at = (int64_t)row * n + p;
   double T0, T1, T2, d;
   const double q = brake_profile(L, P.ts, v_0[at], a_0[at], T0, T1, T2, d);
@@ -972,7 +1014,7 @@ __global__ void ltp_opt_switch_times_kernel(const __grid_constant__ PlannerParam
   if (p >= n) return;
   const int jt = joint_fixed >= 0 ? joint_fixed : blockIdx.y;
   const int row = joint_fixed >= 0 ? 0 : jt, rows = joint_fixed >= 0 ? 1 : P.dof;
-  const JointLimits L = P.lim[jt];
+  const JointLimits L = P.joint(jt);
   const int64_t at = (int64_t)row * n + p;
   const double qg = q_goal[at], q0 = q_0[at];
   const Prologue pro = ost_prologue(L, P.ts, qg, q0, v_0[at], a_0[at]);
@@ -999,7 +1041,7 @@ __global__ void ltp_time_scaling_kernel(const __grid_constant__ PlannerParams P,
   if (p >= n) return;
   const int jt = joint_fixed >= 0 ? joint_fixed : blockIdx.y;
   const int row = joint_fixed >= 0 ? 0 : jt, rows = joint_fixed >= 0 ? 1 : P.dof;
-  const JointLimits L = P.lim[jt];
+  const JointLimits L = P.joint(jt);
   const int64_t at = (int64_t)row * n + p;
   const double qg = q_goal[at], q0 = q_0[at], d = dir[at];
   const TsInput I = make_ts_input(qg, q0, v_0[at], a_0[at], d, t_required[at]);
@@ -1065,7 +1107,7 @@ ltp_sample_kernel(const __grid_constant__ PlannerParams P, int64_t n, int ppb, c
   if (valid && S.reached[p]) {
     const int len = S.traj_len[p];
     if (len > 0) {
-      const JointLimits L = P.lim[jt];
+      const JointLimits L = P.joint(jt);
       const int64_t at = (int64_t)jt * n + p;
       double t[7], v_drive_row;
       load_record(record_of(S, jt, n, p), t, v_drive_row);
@@ -1240,7 +1282,7 @@ ltp_sample_row_latency_kernel(const __grid_constant__ PlannerParams P, int64_t n
   if (S.reached[p]) {  // uniform over the warp
     const int len = S.traj_len[p];
     if (len > 0) {
-      const JointLimits L = P.lim[jt];
+      const JointLimits L = P.joint(jt);
       const int64_t at = (int64_t)jt * n + p;
       double t[7], v_drive_row;
       load_record(record_of(S, jt, n, p), t, v_drive_row);
@@ -1380,7 +1422,7 @@ ltp_sample_tm_kernel(const __grid_constant__ PlannerParams P, int64_t n, const d
     }
     return;
   }
-  const JointLimits L = P.lim[jt];
+  const JointLimits L = P.joint(jt);
   double t[7], v_drive_row;
   load_record(record_of(S, jt, n, p), t, v_drive_row);
   // samples stored: the fixed horizon, or the exact length clipped to the sample capacity
@@ -1538,7 +1580,7 @@ ltp_advance_kernel(const __grid_constant__ PlannerParams P, int64_t n, int tick,
   const int64_t at = (int64_t)jt * n + p;
   if (valid && !valid[p]) return;  // no plan: the environment keeps its state
   const int dof = P.dof;
-  const JointLimits L = P.lim[jt];
+  const JointLimits L = P.joint(jt);
   // exact-length trajectories end at traj_len - 1; from there on the state is the final one
   int at_sample = tick;
   if (traj_len) {
@@ -1674,12 +1716,14 @@ int fill_limits(PlannerParams& P, const double* q_min, const double* q_max, cons
                 const double* a_max, const double* j_max) {
   if (!q_min || !q_max || !v_max || !a_max || !j_max) return LTP_ERR_ARG;
   for (int i = 0; i < P.dof; ++i) {
-    P.lim[i].q_min = q_min[i];
-    P.lim[i].q_max = q_max[i];
-    P.lim[i].v_max = v_max[i];
-    P.lim[i].a_max = a_max[i];
-    P.lim[i].j_max = j_max[i];
-    derive_limits(P.lim[i]);
+    JointLimits L{};
+    L.q_min = q_min[i];
+    L.q_max = q_max[i];
+    L.v_max = v_max[i];
+    L.a_max = a_max[i];
+    L.j_max = j_max[i];
+    derive_limits(L);
+    P.set_joint(i, L);
   }
   return LTP_OK;
 }
@@ -1819,7 +1863,8 @@ int ltp_create(ltp_planner** out, int device, int dof, double t_sample, const do
     p->ring_bytes[i] = 0;
   }
   p->d_totals = nullptr;
-  std::memset(p->params.lim, 0, sizeof p->params.lim);
+  std::memset(p->params.hot, 0, sizeof p->params.hot);
+  std::memset(p->params.wide, 0, sizeof p->params.wide);
   if (dof > 0) {
     int rc = fill_limits(p->params, q_min, q_max, v_max, a_max, j_max);
     if (rc != LTP_OK) { delete p; return rc; }

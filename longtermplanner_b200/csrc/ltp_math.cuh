@@ -50,10 +50,29 @@ struct JointLimits {
   double r_a, r_j, a_over_j, r_v;
   // for the second cruise-speed candidate (ts_candidate2): reciprocals of J^2, J^3, 6 J^3, A J
   double r_j2, r_j3, r_6j3, r_aj;
+  // Powers of A/J. The jerk phases 3, 5 and 7 last A/J unless a fix-up shortens them (cc:129-143,
+  // 153-165, 682-687), so pow(T, 3) and pow(T, 4) of those durations are per-joint constants for
+  // most joints: pow3(a_over_j), pow4(a_over_j), the same bits as evaluated per thread.
+  double aoj3, aoj4;
+  // The braking half of the time-optimal solve (cc:147-165 and the second half of cc:168-190 at
+  // V = v_max) depends on the limits only: T5 and part2 as the body computes them, part2v = NaN
+  // when that half needs the cc:153 fix-up (v_max / a_max < a_max / j_max) and is evaluated per thread.
+  double t5v, part2v;
+  // Limit-only factors of the first cruise-speed candidate (cc:378-396), each the prefix of a
+  // product as C++ evaluates it left to right: A J, A^2 / 2, 36 A^2 J^2, 72 A^3 J, 144 A,
+  // 72 A J^2, A^3, 36 A^4, 36 J^2
+  double c_aj, c_a2h, c_36a2j2, c_72a3j, c_144a, c_72aj2, c_a3, c_36a4, c_36j2;
+  // Terms of the radicand of the solve without a cruise phase (cc:202-223) that hold only the
+  // durations T2 = T4 = T6 = A/J (no fix-up taken): (J^2 T^4)/4, (J^2 T^2 T^2)/2, (J^2 T^4)/2,
+  // (2 J A T^3)/3, 2 J A T^2 T, 2 A^2 T^2
+  double rk_q, rk_m, rk_h, rk_3, rk_7, rk_8;
 };
 
 #ifndef LTP_OST_MERGE
 #define LTP_OST_MERGE 1
+#endif
+#ifndef LTP_OST_CONST
+#define LTP_OST_CONST 2
 #endif
 
 constexpr double kEps = 4e-3;     // cc:96
@@ -120,6 +139,7 @@ LTP_HD double div12(double x) { return div_by(x, 12.0, 1.0 / 12.0); }
 //                of a divergent call (six), and straight-line code is not cut into a basic block
 //                per division. A zero numerator is not out of range here (see below).
 struct DivChecked {
+  static constexpr bool kWideLimits = false;  // see DivDeferredWide
   LTP_HD double by(double x, double d, double rd) const { return div_by(x, d, rd); }
   LTP_HD double by3(double x) const { return div3(x); }
   LTP_HD double by12(double x) const { return div12(x); }
@@ -141,6 +161,7 @@ struct DivChecked {
   }
 };
 struct DivDeferred {
+  static constexpr bool kWideLimits = false;
   bool bad = false;
   LTP_HD double by(double x, double d, double rd) {
     const double q = x * rd;
@@ -170,6 +191,15 @@ struct DivDeferred {
   LTP_HD double half_by(double x, double d, double rd) { return 0.5 * by(x, d, rd); }
 };
 
+// DivDeferred for a caller whose joints' limits stay resident in the constant cache when every
+// field is used: the closed-form functions then also read the limit-only factors c_* and rk_* of
+// JointLimits instead of forming them per thread (same values). With the 256 bytes per joint this
+// makes, 7 joints fit and 12 do not: the 12-joint kernel went from 0.83 to 1.20 ms with them, the
+// 7-joint one from 0.486 to 0.471 ms (profiles/r02_ab_limit_constants.log).
+struct DivDeferredWide : DivDeferred {
+  static constexpr bool kWideLimits = LTP_OST_CONST >= 2;
+};
+
 LTP_HD void derive_limits(JointLimits& L) {
   L.r_a = 1.0 / L.a_max;
   L.r_j = 1.0 / L.j_max;
@@ -179,6 +209,35 @@ LTP_HD void derive_limits(JointLimits& L) {
   L.r_j3 = 1.0 / pow3(L.j_max);
   L.r_6j3 = 1.0 / (6 * pow3(L.j_max));
   L.r_aj = 1.0 / (L.a_max * L.j_max);
+  L.aoj3 = pow3(L.a_over_j);
+  L.aoj4 = pow4(L.a_over_j);
+  {  // cc:147-151 and the part2 of cc:168-190 at V = v_max, the expressions of ost_body_dv
+    const double A = L.a_max, J = L.j_max, T4 = L.a_over_j, T6 = T4;
+    const double T5 = L.v_max / A - 1.0 / 2.0 * (T4 + T6);
+    L.t5v = T5;
+    L.part2v = J * (1.0 / 6.0 * pow3(T6) + 1.0 / 2.0 * sq(T6) * (T5 + T4) - 1.0 / 6.0 * pow3(T4) +
+                    1.0 / 2.0 * T6 * sq(T4)) +
+               A * (1.0 / 2.0 * sq(T5) + T5 * T4);
+    if (!(T5 >= -kEps)) L.part2v = NAN;  // cc:153: the fix-up path, evaluated per thread
+  }
+  {
+    const double A = L.a_max, J = L.j_max, T = L.a_over_j;
+    L.c_aj = A * J;
+    L.c_a2h = sq(A) / 2;
+    L.c_36a2j2 = 36 * sq(A) * sq(J);
+    L.c_72a3j = 72.0 * pow3(A) * J;
+    L.c_144a = 144 * A;
+    L.c_72aj2 = 72.0 * A * sq(J);
+    L.c_a3 = pow3(A);
+    L.c_36a4 = 36 * pow4(A);
+    L.c_36j2 = 36 * sq(J);
+    L.rk_q = (sq(J) * L.aoj4) / 4;
+    L.rk_m = (sq(J) * sq(T) * sq(T)) / 2;
+    L.rk_h = (sq(J) * L.aoj4) / 2;
+    L.rk_3 = (2.0 * J * A * L.aoj3) / 3;
+    L.rk_7 = 2.0 * J * A * sq(T) * T;
+    L.rk_8 = 2.0 * sq(A) * sq(T);
+  }
 }
 
 // h:54-56: (double)((0 < x) - (x < 0)), written as two selects (no int -> double conversion);
@@ -205,15 +264,20 @@ LTP_HD double brake_profile(const JointLimits& L, double Ts, double v_0, double 
   }
   T0 = dv.by(A - a_0, J, L.r_j);
   T2 = L.a_over_j;
+  double p3_2 = L.aoj3;  // pow3(T2): the per-joint constant unless the fix-up below changes T2
   T1 = dv.by(-v_0 - 1.0 / 2.0 * T0 * a_0, A, L.r_a) - 1.0 / 2.0 * (T0 + T2);
   if (T1 < -Ts) {
     T0 = -a_0 / J + sqrt(sq(a_0) / (2 * sq(J)) - v_0 / J);
     T2 = T0 + a_0 / J;
     T1 = 0;
+    p3_2 = pow3(T2);
   }
+#if !LTP_OST_CONST
+  p3_2 = pow3(T2);
+#endif
   double s = v_0 * (T0 + T1 + T2) +
              a_0 * (1.0 / 2.0 * sq(T0) + T0 * (T1 + T2) + 1.0 / 2.0 * sq(T2)) +
-             J * (1.0 / 6.0 * pow3(T0) + 1.0 / 2.0 * sq(T0) * (T1 + T2) - 1.0 / 6.0 * pow3(T2) +
+             J * (1.0 / 6.0 * pow3(T0) + 1.0 / 2.0 * sq(T0) * (T1 + T2) - 1.0 / 6.0 * p3_2 +
                   1.0 / 2.0 * T0 * sq(T2)) +
              A * (1.0 / 2.0 * sq(T1) + T1 * T2);
   return dir * s;
@@ -712,12 +776,14 @@ LTP_HD int ost_body_dv(const JointLimits& L, double Ts, const Prologue& P, doubl
   }
   T[0] = dv.by(A - ae, J, L.r_j);
   T[2] = L.a_over_j;
+  double p3_2 = L.aoj3;  // pow3(T[2]): the per-joint constant unless a fix-up below changes T[2]
   T[1] = dv.by(x - 1.0 / 2.0 * T[0] * ae, A, L.r_a) - 1.0 / 2.0 * (T[0] + T[2]);
   if (m) {
     if (T[1] < -Ts) {  // cc:682-687
       T[0] = -ae / J + sqrt(sq(ae) / (2 * sq(J)) - ve / J);
       T[2] = T[0] + ae / J;
       T[1] = 0;
+      p3_2 = pow3(T[2]);
     }
   } else if (T[1] < -eps) {  // cc:129-143
     double rad = J * (V - v_0) + 0.5 * sq(a_0);
@@ -726,6 +792,7 @@ LTP_HD int ost_body_dv(const JointLimits& L, double Ts, const Prologue& P, doubl
       T[0] = T[2] - dv.by(a_0, J, L.r_j);
       T[1] = 0;
       flags |= F_NOP2;
+      p3_2 = pow3(T[2]);
     } else {
       zero7(t);
       kase = CASE_DEGENERATE | flags;
@@ -761,18 +828,31 @@ LTP_HD int ost_body_dv(const JointLimits& L, double Ts, const Prologue& P, doubl
   // cc:147-165
   T[4] = L.a_over_j;
   T[6] = T[4];
-  T[5] = dv.by(V, A, L.r_a) - 1.0 / 2.0 * (T[4] + T[6]);
-  if (T[5] < -eps) {
-    double rad = dv.by(V, J, L.r_j);
-    if (rad > 0) {
-      T[4] = sqrt(rad);
-      T[6] = T[4];
-      T[5] = 0;
-      flags |= F_NOP6;
-    } else {
-      zero7(t);
-      kase = CASE_DEGENERATE | flags;
-      return OST_OK;
+#if LTP_OST_MERGE && LTP_OST_CONST
+  // the time-optimal solve (V = v_max): this half is a function of the limits, prepared on the host
+  const bool half_prepared = V_IS_VMAX && L.part2v == L.part2v;
+  double p3_4 = L.aoj3;  // pow3(T[4]) = pow3(T[6])
+  if (half_prepared) {
+    T[5] = L.t5v;
+  } else
+#endif
+  {
+    T[5] = dv.by(V, A, L.r_a) - 1.0 / 2.0 * (T[4] + T[6]);
+    if (T[5] < -eps) {
+      double rad = dv.by(V, J, L.r_j);
+      if (rad > 0) {
+        T[4] = sqrt(rad);
+        T[6] = T[4];
+        T[5] = 0;
+        flags |= F_NOP6;
+#if LTP_OST_MERGE && LTP_OST_CONST
+        p3_4 = pow3(T[4]);
+#endif
+      } else {
+        zero7(t);
+        kase = CASE_DEGENERATE | flags;
+        return OST_OK;
+      }
     }
   }
   // cc:168-190
@@ -783,7 +863,7 @@ LTP_HD int ost_body_dv(const JointLimits& L, double Ts, const Prologue& P, doubl
     const double s = ve * T012 +
                      ae * (1.0 / 2.0 * sq(T[0]) + T[0] * (T[1] + T[2]) + 1.0 / 2.0 * sq(T[2])) +
                      J * (1.0 / 6.0 * pow3(T[0]) + 1.0 / 2.0 * sq(T[0]) * (T[1] + T[2]) -
-                          1.0 / 6.0 * pow3(T[2]) + 1.0 / 2.0 * T[0] * sq(T[2])) +
+                          1.0 / 6.0 * (LTP_OST_CONST ? p3_2 : pow3(T[2])) + 1.0 / 2.0 * T[0] * sq(T[2])) +
                      A * (1.0 / 2.0 * sq(T[1]) + T[1] * T[2]);
     part1 = m ? dirb * s + V * T012 : s;
   }
@@ -798,9 +878,20 @@ LTP_HD int ost_body_dv(const JointLimits& L, double Ts, const Prologue& P, doubl
             A * (1.0 / 2.0 * sq(T[1]) + T[1] * T[2]);
   }
 #endif
+#if LTP_OST_MERGE && LTP_OST_CONST
+  double part2;
+  if (half_prepared) {
+    part2 = L.part2v;
+  } else {
+    part2 = J * (1.0 / 6.0 * p3_4 + 1.0 / 2.0 * sq(T[6]) * (T[5] + T[4]) - 1.0 / 6.0 * p3_4 +
+                 1.0 / 2.0 * T[6] * sq(T[4])) +
+            A * (1.0 / 2.0 * sq(T[5]) + T[5] * T[4]);
+  }
+#else
   double part2 = J * (1.0 / 6.0 * pow3(T[6]) + 1.0 / 2.0 * sq(T[6]) * (T[5] + T[4]) -
                       1.0 / 6.0 * pow3(T[4]) + 1.0 / 2.0 * T[6] * sq(T[4])) +
                  A * (1.0 / 2.0 * sq(T[5]) + T[5] * T[4]);
+#endif
   T[3] = V_IS_VMAX ? dv.by(P.dist - part1 - part2, L.v_max, L.r_v) : (P.dist - part1 - part2) / V;
 
   unsigned char base = (unsigned char)(1 + ((flags & F_NOP2) ? 1 : 0) + ((flags & F_NOP6) ? 2 : 0));
@@ -811,16 +902,46 @@ LTP_HD int ost_body_dv(const JointLimits& L, double Ts, const Prologue& P, doubl
       kase = CASE_FAIL | flags;
       return OST_FAIL;
     }
-    // cc:202-223
-    double rad = (sq(J) * pow4(T[0])) / 2 - (sq(J) * pow4(T[2])) / 4 +
-                 (sq(J) * sq(T[2]) * sq(T[4])) / 2 - (sq(J) * pow4(T[4])) / 4 +
-                 (sq(J) * pow4(T[6])) / 2 + 2.0 * J * a_0 * pow3(T[0]) -
-                 dv.by3(2.0 * J * A * pow3(T[0])) - 2.0 * J * A * T[0] * sq(T[2]) +
-                 dv.by3(2.0 * J * A * pow3(T[2])) + dv.by3(2.0 * J * A * pow3(T[4])) -
-                 2.0 * J * A * sq(T[4]) * T[6] - dv.by3(2.0 * J * A * pow3(T[6])) +
+    // cc:202-223; the powers of T[2], T[4] = T[6] are the per-joint constants unless a fix-up
+    // changed those durations (the modified profile, which sets no flag, left above)
+#if LTP_OST_MERGE && LTP_OST_CONST
+    // the terms that hold only T[2], T[4] = T[6]
+    double k_q2, k_m, k_q4, k_h4, k_32, k_34, k_7, k_82, k_84;
+    if (DIV::kWideLimits && !(flags & (F_NOP2 | F_NOP6))) {
+      k_q2 = L.rk_q; k_m = L.rk_m; k_q4 = L.rk_q; k_h4 = L.rk_h; k_32 = L.rk_3; k_34 = L.rk_3;
+      k_7 = L.rk_7; k_82 = L.rk_8; k_84 = L.rk_8;
+    } else {
+      double c3_2 = L.aoj3, c4_2 = L.aoj4, c3_4 = L.aoj3, c4_4 = L.aoj4;
+      if (flags & F_NOP2) {
+        c3_2 = pow3(T[2]);
+        c4_2 = pow4(T[2]);
+      }
+      if (flags & F_NOP6) {
+        c3_4 = pow3(T[4]);
+        c4_4 = pow4(T[4]);
+      }
+      k_q2 = (sq(J) * c4_2) / 4;
+      k_m = (sq(J) * sq(T[2]) * sq(T[4])) / 2;
+      k_q4 = (sq(J) * c4_4) / 4;
+      k_h4 = (sq(J) * c4_4) / 2;
+      k_32 = dv.by3(2.0 * J * A * c3_2);
+      k_34 = dv.by3(2.0 * J * A * c3_4);
+      k_7 = 2.0 * J * A * sq(T[4]) * T[6];
+      k_82 = 2.0 * sq(A) * sq(T[2]);
+      k_84 = 2.0 * sq(A) * sq(T[4]);
+    }
+#else
+    const double k_q2 = (sq(J) * pow4(T[2])) / 4, k_m = (sq(J) * sq(T[2]) * sq(T[4])) / 2,
+                 k_q4 = (sq(J) * pow4(T[4])) / 4, k_h4 = (sq(J) * pow4(T[6])) / 2,
+                 k_32 = dv.by3(2.0 * J * A * pow3(T[2])), k_34 = dv.by3(2.0 * J * A * pow3(T[4])),
+                 k_7 = 2.0 * J * A * sq(T[4]) * T[6], k_82 = 2.0 * sq(A) * sq(T[2]),
+                 k_84 = 2.0 * sq(A) * sq(T[4]);
+#endif
+    double rad = (sq(J) * pow4(T[0])) / 2 - k_q2 + k_m - k_q4 + k_h4 + 2.0 * J * a_0 * pow3(T[0]) -
+                 dv.by3(2.0 * J * A * pow3(T[0])) - 2.0 * J * A * T[0] * sq(T[2]) + k_32 + k_34 - k_7 - k_34 +
                  2.0 * J * v_0 * sq(T[0]) + 2.0 * sq(a_0) * sq(T[0]) - 2.0 * a_0 * A * sq(T[0]) -
-                 2.0 * a_0 * A * sq(T[2]) + 4 * a_0 * v_0 * T[0] + 2.0 * sq(A) * sq(T[2]) +
-                 2.0 * sq(A) * sq(T[4]) - 4 * A * v_0 * T[0] + 4 * P.dist * A + 2.0 * sq(v_0);
+                 2.0 * a_0 * A * sq(T[2]) + 4 * a_0 * v_0 * T[0] + k_82 + k_84 - 4 * A * v_0 * T[0] +
+                 4 * P.dist * A + 2.0 * sq(v_0);
     if (rad > 0) {  // cc:224-236
       // x / (4 A) == (x / A) / 4 bit for bit (scaling by 4 is exact)
       T[5] = 0.25 * dv.by(-(4 * A * T[4] - 2.0 * sqrt(rad) + J * sq(T[2]) - J * sq(T[4]) + 2.0 * J * sq(T[6])),
@@ -879,14 +1000,27 @@ struct TsInput {
 template <class DIV>
 LTP_HD double ts_candidate1(const JointLimits& L, const TsInput& I, DIV& dv) {
   const double A = L.a_max, J = L.j_max, a_0 = I.a_0, v_0 = I.v_0, tr = I.tr, dir = I.dir;
-  return dv.by(A * J * tr / 2 - sq(a_0) / 4 + a_0 * A / 2 - sq(A) / 2 + v_0 * J / 2 -
-                    dv.by12(sqrt(36 * sq(A) * sq(J) * sq(tr) - 36 * sq(a_0) * A * J * tr +
-                               72.0 * a_0 * sq(A) * J * tr - 72.0 * pow3(A) * J * tr +
-                               144 * A * dir * sq(J) * I.q_0 - 144 * A * dir * sq(J) * I.q_goal +
-                               72.0 * A * sq(J) * v_0 * tr - 9 * pow4(a_0) + 12.0 * pow3(a_0) * A +
-                               36 * sq(a_0) * sq(A) + 36 * sq(a_0) * J * v_0 - 72.0 * a_0 * pow3(A) -
-                               72.0 * a_0 * A * J * v_0 + 36 * pow4(A) - 36 * sq(J) * sq(v_0))),
-                J, L.r_j);
+  if constexpr (DIV::kWideLimits) {
+    // the same expression with the limit-only prefixes of its products read from the limits
+    // (derive_limits forms them with the same operations in the same order)
+    return dv.by(L.c_aj * tr / 2 - sq(a_0) / 4 + a_0 * A / 2 - L.c_a2h + v_0 * J / 2 -
+                      dv.by12(sqrt(L.c_36a2j2 * sq(tr) - 36 * sq(a_0) * A * J * tr +
+                                 72.0 * a_0 * sq(A) * J * tr - L.c_72a3j * tr +
+                                 L.c_144a * dir * sq(J) * I.q_0 - L.c_144a * dir * sq(J) * I.q_goal +
+                                 L.c_72aj2 * v_0 * tr - 9 * pow4(a_0) + 12.0 * pow3(a_0) * A +
+                                 36 * sq(a_0) * sq(A) + 36 * sq(a_0) * J * v_0 - 72.0 * a_0 * L.c_a3 -
+                                 72.0 * a_0 * A * J * v_0 + L.c_36a4 - L.c_36j2 * sq(v_0))),
+                  J, L.r_j);
+  } else {
+    return dv.by(A * J * tr / 2 - sq(a_0) / 4 + a_0 * A / 2 - sq(A) / 2 + v_0 * J / 2 -
+                      dv.by12(sqrt(36 * sq(A) * sq(J) * sq(tr) - 36 * sq(a_0) * A * J * tr +
+                                 72.0 * a_0 * sq(A) * J * tr - 72.0 * pow3(A) * J * tr +
+                                 144 * A * dir * sq(J) * I.q_0 - 144 * A * dir * sq(J) * I.q_goal +
+                                 72.0 * A * sq(J) * v_0 * tr - 9 * pow4(a_0) + 12.0 * pow3(a_0) * A +
+                                 36 * sq(a_0) * sq(A) + 36 * sq(a_0) * J * v_0 - 72.0 * a_0 * pow3(A) -
+                                 72.0 * a_0 * A * J * v_0 + 36 * pow4(A) - 36 * sq(J) * sq(v_0))),
+                  J, L.r_j);
+  }
 }
 
 LTP_HD double ts_candidate1(const JointLimits& L, const TsInput& I) {

@@ -65,8 +65,9 @@ int64_t shadow_deferred_vs_checked(void* h, int64_t n, const int* joint, const d
   int64_t miss = 0, flg = 0, flg2 = 0;
   for (int64_t i = 0; i < n; ++i) {
     const JointLimits& L = s->lim[joint ? joint[i] : 0];
-    // stage 1
-    DivDeferred dv;
+    // stage 1 (the policy of the closed-form kernel for up to 8 joints: limit-only factors read
+    // from JointLimits instead of being formed per item)
+    DivDeferredWide dv;
     const bool in_d = check_joint_input(L, q_0[i], v_0[i], a_0[i], dv);
     const Prologue pd = ost_prologue(L, s->ts, q_goal[i], q_0[i], v_0[i], a_0[i], dv);
     double td[7];
@@ -92,7 +93,7 @@ int64_t shadow_deferred_vs_checked(void* h, int64_t n, const int* joint, const d
     }
     // attempt 1 from the checked prologue (what the device has at that point either way)
     const TsInput I = make_ts_input(q_goal[i], q_0[i], v_0[i], a_0[i], pc.dir, t_req[i]);
-    DivDeferred dv2;
+    DivDeferredWide dv2;
     double ad[7], ac[7];
     zero7(ad);
     zero7(ac);
