@@ -300,6 +300,41 @@ def test_deferred_range_test_of_the_divisions_changes_no_bit(kind):
         assert flagged[0] < 0.001 * m, list(flagged)
 
 
+_SLOW = W.Limits("slow_cruise", 0.004, (-3.0,) * 3, (3.0,) * 3, (0.05, 0.4, 1.0), (2.0, 2.0, 2.0), (4.0, 4.0, 4.0))
+
+
+@pytest.mark.parametrize("lim", [W.FRANKA7, W.FRANKA12, W.REF_RANDOM6, W.REF_GRID, W.random_limits(8, 5),
+                                 W.random_limits(5, 11), _SLOW], ids=lambda l: l.name)
+def test_limit_only_factors_from_the_host_have_the_bits_of_the_per_item_expressions(lim):
+    """The closed-form kernel for up to 8 joints reads what depends on the limits alone from
+    JointLimits (derive_limits: powers of A/J, the braking half of the time-optimal solve, product
+    prefixes of the first candidate, constant terms of the no-cruise radicand -- DivDeferredWide);
+    the checked functions form all of it per item. Same bits for every limit set, including one
+    whose cruise speed is so low that the braking half needs the cc:153 fix-up (part2v = NaN: that
+    half is then evaluated per item) and joints with v_max / a_max == a_max / j_max."""
+    import ctypes
+    lib = ctypes.CDLL(SHADOW)
+    f = lib.shadow_deferred_vs_checked
+    f.restype = ctypes.c_int64
+    f.argtypes = [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 6 + [ctypes.c_void_p]
+    n = 60_000 // lim.dof
+    qg, q0, v0, a0 = W.random_states(lim, n, 515)
+    # end times as stage 2 would hand them to the search: the slowest joint's, from the oracle
+    ref = OraclePort.from_limits(lim).solve(qg, q0, v0, a0, threads=4)
+    t_req = np.repeat(ref["t_opt"][:, :, 6].max(axis=1), lim.dof)
+    qg, q0, v0, a0 = [np.ascontiguousarray(x.reshape(-1)) for x in (qg, q0, v0, a0)]
+    m = qg.size
+    joint = np.ascontiguousarray(np.tile(np.arange(lim.dof, dtype=np.int32), n))
+    t_req = np.ascontiguousarray(t_req, dtype=np.float64)
+    assert t_req.size == m
+    sh = Shadow(lim.dof, lim.t_sample, *lim.arrays())
+    flagged = (ctypes.c_int64 * 2)(0, 0)
+    miss = f(sh.h, m, joint.ctypes.data, qg.ctypes.data, q0.ctypes.data, v0.ctypes.data, a0.ctypes.data,
+             t_req.ctypes.data, flagged)
+    assert miss == 0
+    assert flagged[0] < 0.001 * m, list(flagged)
+
+
 @pytest.mark.parametrize("lim", [W.FRANKA7, W.REF_RANDOM6, W.random_limits(8, 5)], ids=lambda l: l.name)
 def test_second_candidate_through_reciprocals_has_the_bits_of_the_written_out_divisions(lim):
     import ctypes
